@@ -1,0 +1,210 @@
+/* slamcu.h -- C ABI of the B200-native (sm_100a) SLAM-frontend kernel library.
+ *
+ * This is the drop-in boundary for the reference's data-parallel hot path.  The reference has no FFI
+ * layer: its boundary is four C++ classes.  Each entry point below names the reference interface it
+ * replaces (paths relative to the reference repo):
+ *
+ *   slam::FeatureDetector   include/slam/frontend/feature_detector.hpp:47-192, src/frontend/feature_detector.cpp
+ *   slam::FeatureMatcher    include/slam/frontend/feature_matcher.hpp:38-87,   src/frontend/feature_matcher.cpp
+ *   slam::PoseEstimator     include/slam/frontend/pose_estimator.hpp:13-36,    src/frontend/pose_estimator.cpp:18-67
+ *   slam::Camera / Preprocessor  include/slam/common/common.hpp:67-190, src/preprocessing/preprocessor.cpp:95-141
+ *
+ * Rules of the ABI: plain pointers and sizes only (no STL / Eigen / OpenCV / torch types), every
+ * function returns an int status (0 = ok), caller allocates outputs and passes capacities, no
+ * exceptions cross the boundary.  One context is single-threaded; different contexts may be driven
+ * from different host threads / GPUs.  There is NO CPU fallback: every call either runs the CUDA path
+ * or fails with a status.
+ */
+#ifndef SLAM_CUDA_SLAMCU_H_
+#define SLAM_CUDA_SLAMCU_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SLAMCU_ABI_VERSION 1
+
+/* ---- status codes -------------------------------------------------------------------------- */
+enum {
+    SLAMCU_OK = 0,
+    SLAMCU_INVALID_ARGUMENT = 1, /* bad pointer / size / config value (adapters throw std::runtime_error)      */
+    SLAMCU_EMPTY_INPUT = 2,      /* "Empty descriptors provided." -> std::invalid_argument (feature_matcher.cpp:99-102) */
+    SLAMCU_SIZE_MISMATCH = 3,    /* "Descriptor dimensions must match." (feature_matcher.cpp:108-110), image size   */
+    SLAMCU_CAPACITY = 4,         /* an output or internal list overflowed its capacity                          */
+    SLAMCU_CUDA_ERROR = 5,       /* CUDA runtime failure; see slamcu_last_error                                 */
+    SLAMCU_UNSUPPORTED = 6       /* e.g. DistanceType L2 on uint8 descriptors (feature_matcher.cpp:86,104-106)    */
+};
+
+/* ---- plain data mirrored from the reference ------------------------------------------------- */
+/* slam::Keypoint, feature_detector.hpp:28-38: five floats, 20 bytes, AoS. */
+typedef struct slamcu_keypoint {
+    float x, y, size, angle, response;
+} slamcu_keypoint;
+
+/* slam::Match, feature_matcher.hpp:18-25. */
+typedef struct slamcu_dmatch {
+    int32_t queryIdx, trainIdx;
+    float distance;
+} slamcu_dmatch;
+
+/* k = 2 nearest-neighbour record (cv::BFMatcher::knnMatch row), mode "orb" only. */
+typedef struct slamcu_knn2 {
+    int32_t trainIdx0, trainIdx1;
+    float distance0, distance1;
+} slamcu_knn2;
+
+#define SLAMCU_MODE_REFERENCE 0 /* exactly slam::FeatureDetector / FeatureMatcher                     */
+#define SLAMCU_MODE_ORB 1       /* OpenCV-ORB compatible: pyramid + FAST-9 + Harris + rBRIEF-256 (opt-in) */
+
+/* The six YAML scalars of feature_detector.hpp:60-93, plus the two host-generated tables whose
+ * provenance must stay on the host (libstdc++ <random> pattern, libm exp weights), plus the opt-in
+ * ORB-mode keys (absent from the reference's YAML => mode 0). */
+typedef struct slamcu_detector_config {
+    int32_t intensity_threshold;         /* IntensityThreshold        [0,255]  */
+    int32_t contiguous_pixels_threshold; /* ContiguousPixelsThreshold [0,16]   */
+    int32_t non_max_suppression;         /* NonMaxSuppression         0|1      */
+    int32_t suppression_window_size;     /* SuppressionWindowSize     > 0      */
+    int32_t patch_size;                  /* PatchSize                 odd > 0  */
+    int32_t num_brief_pairs;             /* NumBRIEFPairs             8k > 0   */
+    int32_t n_pattern;                   /* number of surviving pairs from generateBRIEFPattern()           */
+    const int32_t* pattern;              /* [n_pattern][4] = x1,y1,x2,y2  (feature_detector.cpp:286-313)    */
+    const double* blur_weights;          /* [25] normalised 5x5 sigma=1 kernel (feature_detector.cpp:321-335) */
+    /* --- ORB mode (SLAMCU_MODE_ORB) --- */
+    int32_t mode;
+    int32_t n_levels;      /* NumLevels   (8)    */
+    float scale_factor;    /* ScaleFactor (1.2f) */
+    int32_t max_features;  /* MaxFeatures (2000) */
+    int32_t fast_threshold; /* = intensity_threshold by default */
+    const int32_t* orb_pattern; /* [256][4] OpenCV bit_pattern_31_ (host supplied), or NULL */
+} slamcu_detector_config;
+
+/* feature_matcher.cpp:25-57 */
+#define SLAMCU_DISTANCE_HAMMING 0
+#define SLAMCU_DISTANCE_L2 1
+typedef struct slamcu_matcher_config {
+    int32_t distance_type;      /* DistanceType */
+    int32_t filter_matches;     /* FilterMatches 0|1 */
+    int32_t good_matches_count; /* GoodMatchesCount  */
+    int32_t use_ratio_test;     /* UseRatioTest 0|1  */
+    float ratio_test_threshold; /* RatioTestThreshold [0,1] */
+} slamcu_matcher_config;
+
+typedef struct slamcu_context slamcu_context;
+typedef struct slamcu_detector slamcu_detector;
+typedef struct slamcu_matcher slamcu_matcher;
+typedef struct slamcu_sequence slamcu_sequence;
+
+/* ---- context -------------------------------------------------------------------------------- */
+int slamcu_abi_version(void);
+const char* slamcu_status_string(int status);
+int slamcu_device_count(int* count);
+/* One context per device; owns a stream unless slamcu_set_stream() hands it an external cudaStream_t. */
+int slamcu_create(int device_id, slamcu_context** out);
+void slamcu_destroy(slamcu_context* ctx);
+const char* slamcu_last_error(const slamcu_context* ctx);
+int slamcu_set_stream(slamcu_context* ctx, void* cuda_stream /* cudaStream_t, NULL = own stream */);
+void* slamcu_get_stream(slamcu_context* ctx);
+int slamcu_synchronize(slamcu_context* ctx);
+/* number of kernels this library launched on the context since creation (bench.py gpu_launches) */
+int64_t slamcu_launch_count(const slamcu_context* ctx);
+
+/* ---- FeatureDetector (feature_detector.hpp:53,114-135) ---------------------------------------- */
+/* Constructor-time host tables, produced with the same host-library calls as the reference:
+ * generateBRIEFPattern() (feature_detector.cpp:286-313; std::default_random_engine +
+ * std::normal_distribution<float>) and the 5x5 sigma=1 kernel of gaussianBlur() (:321-335; std::exp). */
+int slamcu_default_brief_pattern(int patch_size, int num_pairs, int32_t* pattern4, int capacity_pairs, int* n_out);
+int slamcu_default_blur_weights(double* weights25);
+int slamcu_detector_create(slamcu_context* ctx, const slamcu_detector_config* cfg, slamcu_detector** out);
+void slamcu_detector_destroy(slamcu_detector* det);
+
+/* FeatureDetector::detect (feature_detector.cpp:8-18).  image: row-major u8, `stride` bytes per row
+ * (EigenGrayMatrix::data(), stride = cols).  *n_out receives the keypoint count; if it exceeds
+ * `capacity` the call fails with SLAMCU_CAPACITY (and *n_out holds the needed size). */
+int slamcu_detect(slamcu_detector* det, const uint8_t* image, int rows, int cols, int stride,
+                  slamcu_keypoint* keypoints, int capacity, int* n_out);
+/* FeatureDetector::compute (feature_detector.cpp:20-47): keypoints in/out (angle written);
+ * descriptors: n x (num_brief_pairs/8) bytes, row stride desc_stride. n == 0 is ok (no output). */
+int slamcu_compute(slamcu_detector* det, const uint8_t* image, int rows, int cols, int stride,
+                   slamcu_keypoint* keypoints, int n, uint8_t* descriptors, int desc_stride);
+/* FeatureDetector::detectAndCompute (feature_detector.cpp:49-54). */
+int slamcu_detect_and_compute(slamcu_detector* det, const uint8_t* image, int rows, int cols, int stride,
+                              slamcu_keypoint* keypoints, uint8_t* descriptors, int desc_stride, int capacity,
+                              int* n_out);
+/* Stage probes used by the parity tests (not part of the reference's public surface):
+ * raster-order FAST corners with their SAD score in `response` (feature_detector.cpp:56-68,190-203) */
+int slamcu_fast_corners(slamcu_detector* det, const uint8_t* image, int rows, int cols, int stride,
+                        slamcu_keypoint* keypoints, int capacity, int* n_out);
+/* FeatureDetector::gaussianBlur(image, 5, 1.0) (feature_detector.cpp:315-364) */
+int slamcu_gaussian_blur(slamcu_detector* det, const uint8_t* image, int rows, int cols, int stride, uint8_t* out,
+                         int out_stride);
+
+/* ---- FeatureMatcher (feature_matcher.hpp:50,64-66) ------------------------------------------- */
+int slamcu_matcher_create(slamcu_context* ctx, const slamcu_matcher_config* cfg, slamcu_matcher** out);
+void slamcu_matcher_destroy(slamcu_matcher* m);
+/* FeatureMatcher::match (feature_matcher.cpp:71-95).  d1: n1 x width bytes (row stride = width),
+ * d2: n2 x width.  kp1/kp2 optional (NULL or n == 0 => no distance penalty, feature_matcher.cpp:150).
+ * Output in the reference's order: query order, or the std::partial_sort / std::sort order when
+ * FilterMatches = 1.  Errors: SLAMCU_EMPTY_INPUT, SLAMCU_SIZE_MISMATCH, SLAMCU_UNSUPPORTED. */
+int slamcu_match(slamcu_matcher* m, const uint8_t* d1, int n1, int width1, const uint8_t* d2, int n2, int width2,
+                 const slamcu_keypoint* kp1, int nkp1, const slamcu_keypoint* kp2, int nkp2, slamcu_dmatch* matches,
+                 int capacity, int* n_out);
+/* Brute-force k = 2 Hamming search for every query (no ratio/filter): best/second by (distance, index).
+ * This is both the sweep benchmark kernel (BASELINE.json config 5) and cv::BFMatcher::knnMatch(k=2). */
+int slamcu_knn2_hamming(slamcu_matcher* m, const uint8_t* d1, int n1, const uint8_t* d2, int n2, int width,
+                        slamcu_knn2* out);
+
+/* ---- device-resident sequences: the batched / asynchronous path -------------------------------
+ * A sequence holds up to max_frames frames of one size in HBM together with every intermediate of
+ * the frontend (corner masks, raw corner lists, keypoints, descriptors, consecutive-frame matches).
+ * All calls enqueue on the context's stream and return immediately unless stated otherwise. */
+int slamcu_sequence_create(slamcu_context* ctx, int rows, int cols, int max_frames, int max_raw_corners,
+                           int max_keypoints, int desc_bytes, slamcu_sequence** out);
+void slamcu_sequence_destroy(slamcu_sequence* seq);
+/* H2D copy of n frames from host memory (pinned for async) into slots [first, first+n). */
+int slamcu_sequence_upload(slamcu_sequence* seq, int first, int n, const uint8_t* host_frames, int stride);
+/* Device pointer / pitch of the frame store, for producers that already live on the device. */
+int slamcu_sequence_frames_device(slamcu_sequence* seq, void** dptr, int* pitch, int64_t* frame_bytes);
+/* detectAndCompute on frames [first, first+n). */
+int slamcu_sequence_extract(slamcu_sequence* seq, slamcu_detector* det, int first, int n);
+/* match(frame f, frame f+1) for f in [first, first+n_pairs); with_keypoints selects the penalty path. */
+int slamcu_sequence_match(slamcu_sequence* seq, slamcu_matcher* m, int first, int n_pairs, int with_keypoints);
+/* D2H of per-frame counts {n_keypoints, n_matches, n_raw_corners, status} (int32[n][4]); synchronises. */
+int slamcu_sequence_counts(slamcu_sequence* seq, int first, int n, int32_t* counts4);
+/* D2H of one frame's keypoints + descriptors / one pair's matches; synchronises. */
+int slamcu_sequence_frame(slamcu_sequence* seq, int f, slamcu_keypoint* keypoints, uint8_t* descriptors,
+                          int desc_stride, int capacity, int* n_out);
+int slamcu_sequence_matches(slamcu_sequence* seq, int f, slamcu_dmatch* matches, int capacity, int* n_out);
+/* Bulk asynchronous D2H of everything a consumer needs for frames [first, first+n): keypoints
+ * [n][max_keypoints], descriptors [n][max_keypoints][desc_bytes], matches [n][max_keypoints],
+ * counts [n][4], into pinned host buffers (any pointer may be NULL to skip it). */
+int slamcu_sequence_download(slamcu_sequence* seq, int first, int n, slamcu_keypoint* keypoints, uint8_t* descriptors,
+                             slamcu_dmatch* matches, int32_t* counts4);
+
+/* ---- image preparation (src/preprocessing) ---------------------------------------------------- */
+/* cv::cvtColor(BGR2GRAY) (preprocessor.cpp:136): gray = (3735 B + 19235 G + 9798 R + 16384) >> 15. */
+int slamcu_bgr_to_gray(slamcu_context* ctx, const uint8_t* bgr, int rows, int cols, int stride, uint8_t* gray,
+                       int gray_stride);
+/* Camera::undistortImage (common.hpp:127-173).  K4 = fx,fy,cx,cy; D4 = k1,k2,p1,p2 (k3 is unused by the
+ * reference).  out_u8 (rows x cols, may be NULL) receives the gathered bytes the detector consumes;
+ * out_f64 (rows x cols row-major, may be NULL) receives the reference's value/255.0 image. */
+int slamcu_undistort(slamcu_context* ctx, const uint8_t* gray, int rows, int cols, int stride, const double* K4,
+                     const double* D4, uint8_t* out_u8, double* out_f64);
+
+/* ---- two-view geometry (pose_estimator.cpp:18-67 -> cv::findEssentialMat(RANSAC)) ------------- */
+/* Sampson-error scoring of n_models 3x3 essential-matrix hypotheses against n correspondences
+ * (already normalised by K, double) with cv's threshold semantics: inlier iff (float)err <= (float)thr2.
+ * counts[n_models] inlier counts; masks (may be NULL) n_models x n bytes. */
+int slamcu_ransac_score(slamcu_context* ctx, const double* models9, int n_models, const double* x1, const double* x2,
+                        int n, double thr2, int32_t* counts, uint8_t* masks);
+/* Full cv::findEssentialMat(p1,p2,K,RANSAC,0.999,1.0,1000) replacement: RNG/sampling sequence,
+ * 5-point minimal solver, scoring, sequential accept / adaptive-iteration replay.  p1/p2: n x 2 float
+ * pixels; K4 = fx,fy,cx,cy.  E9 row-major; mask n bytes.  n < 5 => SLAMCU_INVALID_ARGUMENT. */
+int slamcu_find_essential(slamcu_context* ctx, const float* p1, const float* p2, int n, const double* K4, double prob,
+                          double threshold, int max_iters, double* E9, uint8_t* mask, int* n_inliers);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SLAM_CUDA_SLAMCU_H_ */

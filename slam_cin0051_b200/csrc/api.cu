@@ -1,0 +1,900 @@
+// api.cu -- the C ABI (include/slam/cuda/slamcu.h) over the sm_100a kernels.  No torch, no STL types
+// across the boundary, no CPU fallback: a call either enqueues CUDA work or returns an error status.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#include <new>
+#include <random>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+using namespace slamcu;
+
+namespace slamcu {
+void init_sortnms_attributes(int smem_optin);
+int launch_desc_or(const uint32_t* desc, const int* n_dev, int desc_words, uint32_t* out, cudaStream_t st);
+}
+
+struct slamcu_context {
+    int device = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    int smem_optin = 0;
+    int64_t launches = 0;
+    std::string err;
+    // scratch reused by the preparation / ransac entry points
+    void* scratch = nullptr;
+    size_t scratch_bytes = 0;
+};
+
+namespace {
+
+int fail(slamcu_context* ctx, int status, const char* fmt, ...) {
+    if (ctx) {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof buf, fmt, ap);
+        va_end(ap);
+        ctx->err = buf;
+    }
+    return status;
+}
+
+#define CU(ctx, call)                                                                                  \
+    do {                                                                                               \
+        cudaError_t e__ = (call);                                                                      \
+        if (e__ != cudaSuccess)                                                                        \
+            return fail(ctx, SLAMCU_CUDA_ERROR, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), \
+                        __FILE__, __LINE__);                                                           \
+    } while (0)
+
+int check_launch(slamcu_context* ctx, const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(ctx, SLAMCU_CUDA_ERROR, "%s: %s", what, cudaGetErrorString(e));
+    return SLAMCU_OK;
+}
+
+int ensure_scratch(slamcu_context* ctx, size_t bytes) {
+    if (ctx->scratch_bytes >= bytes) return SLAMCU_OK;
+    if (ctx->scratch) cudaFree(ctx->scratch);
+    ctx->scratch = nullptr;
+    ctx->scratch_bytes = 0;
+    CU(ctx, cudaMalloc(&ctx->scratch, bytes));
+    ctx->scratch_bytes = bytes;
+    return SLAMCU_OK;
+}
+
+template <class T>
+int dev_alloc(slamcu_context* ctx, T** p, size_t count, std::vector<void*>& owned, bool zero = false) {
+    void* q = nullptr;
+    const size_t bytes = (count ? count : 1) * sizeof(T);
+    CU(ctx, cudaMalloc(&q, bytes));
+    owned.push_back(q);
+    if (zero) CU(ctx, cudaMemsetAsync(q, 0, bytes, ctx->stream));
+    *p = static_cast<T*>(q);
+    return SLAMCU_OK;
+}
+
+int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+}  // namespace
+
+struct slamcu_sequence {
+    slamcu_context* ctx = nullptr;
+    SeqView v{};
+    int max_frames = 0;
+    unsigned long long* sort_keys = nullptr;  // [F][cap_kp]
+    int* h_counts = nullptr;                  // pinned [F][4]
+    std::vector<void*> owned;
+};
+
+struct slamcu_detector {
+    slamcu_context* ctx = nullptr;
+    DetParams p{};
+    int mode = 0;
+    int* d_pattern = nullptr;
+    slamcu_sequence* one = nullptr;  // cached single-frame workspace
+};
+
+struct slamcu_matcher {
+    slamcu_context* ctx = nullptr;
+    MatchParams p{};
+    int distance_type = 0;
+    // single-call workspace
+    uint32_t *d1 = nullptr, *d2 = nullptr;
+    slamcu_keypoint *k1 = nullptr, *k2 = nullptr;
+    int4* cand = nullptr;
+    slamcu_dmatch* matches = nullptr;
+    unsigned long long* keys = nullptr;
+    uint32_t* ors = nullptr;
+    int* counts = nullptr;  // nq, nt, n_match, status
+    int cap1 = 0, cap2 = 0, cap_words = 0;
+};
+
+extern "C" {
+
+int slamcu_abi_version(void) { return SLAMCU_ABI_VERSION; }
+
+const char* slamcu_status_string(int status) {
+    switch (status) {
+        case SLAMCU_OK: return "ok";
+        case SLAMCU_INVALID_ARGUMENT: return "invalid argument";
+        case SLAMCU_EMPTY_INPUT: return "Empty descriptors provided.";
+        case SLAMCU_SIZE_MISMATCH: return "size mismatch";
+        case SLAMCU_CAPACITY: return "capacity exceeded";
+        case SLAMCU_CUDA_ERROR: return "CUDA error";
+        case SLAMCU_UNSUPPORTED: return "unsupported";
+        default: return "unknown status";
+    }
+}
+
+int slamcu_device_count(int* count) {
+    if (!count) return SLAMCU_INVALID_ARGUMENT;
+    cudaError_t e = cudaGetDeviceCount(count);
+    if (e != cudaSuccess) {
+        *count = 0;
+        return SLAMCU_CUDA_ERROR;
+    }
+    return SLAMCU_OK;
+}
+
+int slamcu_create(int device_id, slamcu_context** out) {
+    if (!out) return SLAMCU_INVALID_ARGUMENT;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) return SLAMCU_CUDA_ERROR;  // no CPU fallback
+    if (device_id < 0 || device_id >= count) return SLAMCU_INVALID_ARGUMENT;
+    slamcu_context* ctx = new (std::nothrow) slamcu_context();
+    if (!ctx) return SLAMCU_CUDA_ERROR;
+    ctx->device = device_id;
+    if (cudaSetDevice(device_id) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        return SLAMCU_CUDA_ERROR;
+    }
+    ctx->stream = ctx->own_stream;
+    cudaDeviceGetAttribute(&ctx->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device_id);
+    init_sortnms_attributes(ctx->smem_optin);
+    *out = ctx;
+    return SLAMCU_OK;
+}
+
+void slamcu_destroy(slamcu_context* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->scratch) cudaFree(ctx->scratch);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+const char* slamcu_last_error(const slamcu_context* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int slamcu_set_stream(slamcu_context* ctx, void* cuda_stream) {
+    if (!ctx) return SLAMCU_INVALID_ARGUMENT;
+    ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+    return SLAMCU_OK;
+}
+void* slamcu_get_stream(slamcu_context* ctx) { return ctx ? ctx->stream : nullptr; }
+
+int slamcu_synchronize(slamcu_context* ctx) {
+    if (!ctx) return SLAMCU_INVALID_ARGUMENT;
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return SLAMCU_OK;
+}
+int64_t slamcu_launch_count(const slamcu_context* ctx) { return ctx ? ctx->launches : 0; }
+
+/* ---------------------------------------------------------------------------------------------- */
+/* sequences                                                                                       */
+/* ---------------------------------------------------------------------------------------------- */
+int slamcu_sequence_create(slamcu_context* ctx, int rows, int cols, int max_frames, int max_raw, int max_kp,
+                           int desc_bytes, slamcu_sequence** out) {
+    if (!ctx || !out) return SLAMCU_INVALID_ARGUMENT;
+    *out = nullptr;
+    if (rows <= 0 || cols <= 0 || rows > 65535 || cols > 65535 || max_frames <= 0 || desc_bytes <= 0 || desc_bytes > 256)
+        return fail(ctx, SLAMCU_INVALID_ARGUMENT, "bad sequence geometry %dx%d x%d desc %d", rows, cols, max_frames,
+                    desc_bytes);
+    CU(ctx, cudaSetDevice(ctx->device));
+    slamcu_sequence* s = new (std::nothrow) slamcu_sequence();
+    if (!s) return SLAMCU_CUDA_ERROR;
+    s->ctx = ctx;
+    s->max_frames = max_frames;
+    SeqView& v = s->v;
+    v.rows = rows;
+    v.cols = cols;
+    v.pitch = round_up(cols, 128);
+    v.mwords = (cols + 31) / 32;
+    const long long px = (long long)rows * cols;
+    if (max_raw <= 0) max_raw = (int)std::min<long long>(std::max<long long>(px / 20, 8192), kMaxRawCap);
+    if (max_raw > kMaxRawCap) max_raw = kMaxRawCap;
+    if (max_kp <= 0) max_kp = (int)std::min<long long>(std::max<long long>(px / 100, 1024), 65536);
+    v.cap_raw = max_raw;
+    v.cap_kp = max_kp;
+    v.desc_bytes = desc_bytes;
+    v.desc_words = (desc_bytes + 3) / 4;
+    v.qcap = max_raw / 16 + 2;
+    v.frame_bytes = (size_t)rows * v.pitch;
+    v.scratch_words = 2 * (size_t)max_raw + 4 * (size_t)v.qcap + (size_t)max_raw / 32 + 2;
+    const size_t F = (size_t)max_frames;
+    int rc = SLAMCU_OK;
+    auto A = [&](auto** p, size_t count, bool zero) {
+        if (rc == SLAMCU_OK) rc = dev_alloc(ctx, p, count, s->owned, zero);
+    };
+    A(&v.img, F * v.frame_bytes, true);
+    A(&v.blur, F * v.frame_bytes, true);
+    A(&v.mask, F * rows * v.mwords, false);
+    A(&v.raw_xy, F * max_raw, false);
+    A(&v.keys, F * max_raw, false);
+    A(&v.sort_scratch, F * v.scratch_words, false);
+    const size_t bm_bytes = (size_t)rows * v.mwords * 4;
+    if (bm_bytes > (size_t)(ctx->smem_optin - 1024)) A(&v.nms_bitmap, F * rows * v.mwords, false);
+    A(&v.n_raw, F, true);
+    A(&v.kps, F * max_kp, false);
+    A(&v.n_kp, F, true);
+    A(&v.desc, F * max_kp * v.desc_words, true);
+    A(&v.desc_or, F * v.desc_words, true);
+    A(&v.cand, F * max_kp, false);
+    A(&v.matches, F * max_kp, false);
+    A(&v.n_match, F, true);
+    A(&v.status, F, true);
+    A(&s->sort_keys, F * max_kp, false);
+    if (rc == SLAMCU_OK && cudaMallocHost(reinterpret_cast<void**>(&s->h_counts), F * 4 * sizeof(int)) != cudaSuccess)
+        rc = fail(ctx, SLAMCU_CUDA_ERROR, "cudaMallocHost failed");
+    if (rc != SLAMCU_OK) {
+        slamcu_sequence_destroy(s);
+        return rc;
+    }
+    *out = s;
+    return SLAMCU_OK;
+}
+
+void slamcu_sequence_destroy(slamcu_sequence* s) {
+    if (!s) return;
+    cudaSetDevice(s->ctx->device);
+    cudaStreamSynchronize(s->ctx->stream);
+    for (void* p : s->owned) cudaFree(p);
+    if (s->h_counts) cudaFreeHost(s->h_counts);
+    delete s;
+}
+
+int slamcu_sequence_upload(slamcu_sequence* s, int first, int n, const uint8_t* host, int stride) {
+    if (!s || !host) return SLAMCU_INVALID_ARGUMENT;
+    slamcu_context* ctx = s->ctx;
+    if (first < 0 || n < 0 || first + n > s->max_frames || stride < s->v.cols)
+        return fail(ctx, SLAMCU_INVALID_ARGUMENT, "upload range [%d,%d) / stride %d invalid", first, first + n, stride);
+    if (n == 0) return SLAMCU_OK;
+    CU(ctx, cudaMemcpy2DAsync(s->v.img + (size_t)first * s->v.frame_bytes, s->v.pitch, host, stride, s->v.cols,
+                              (size_t)s->v.rows * n, cudaMemcpyHostToDevice, ctx->stream));
+    return SLAMCU_OK;
+}
+
+int slamcu_sequence_frames_device(slamcu_sequence* s, void** dptr, int* pitch, int64_t* frame_bytes) {
+    if (!s) return SLAMCU_INVALID_ARGUMENT;
+    if (dptr) *dptr = s->v.img;
+    if (pitch) *pitch = s->v.pitch;
+    if (frame_bytes) *frame_bytes = (int64_t)s->v.frame_bytes;
+    return SLAMCU_OK;
+}
+
+static int seq_detect(slamcu_sequence* s, slamcu_detector* det, int first, int n, bool raw_probe) {
+    slamcu_context* ctx = s->ctx;
+    ctx->launches += launch_fast_corners(s->v, first, n, det->p, ctx->stream);
+    if (raw_probe) ctx->launches += launch_raster_keypoints(s->v, first, n, true, ctx->stream);
+    else if (det->p.nms) ctx->launches += launch_sort_nms(s->v, first, n, det->p, ctx->smem_optin, ctx->stream);
+    else ctx->launches += launch_raster_keypoints(s->v, first, n, false, ctx->stream);
+    return check_launch(ctx, "detect kernels");
+}
+
+static int seq_compute(slamcu_sequence* s, slamcu_detector* det, int first, int n) {
+    slamcu_context* ctx = s->ctx;
+    ctx->launches += launch_blur(s->v, first, n, det->p, ctx->stream);
+    ctx->launches += launch_describe(s->v, first, n, det->p, det->d_pattern, ctx->stream);
+    return check_launch(ctx, "compute kernels");
+}
+
+int slamcu_sequence_extract(slamcu_sequence* s, slamcu_detector* det, int first, int n) {
+    if (!s || !det || s->ctx != det->ctx) return SLAMCU_INVALID_ARGUMENT;
+    slamcu_context* ctx = s->ctx;
+    if (first < 0 || n < 0 || first + n > s->max_frames) return fail(ctx, SLAMCU_INVALID_ARGUMENT, "bad frame range");
+    if (det->p.pairs / 8 != s->v.desc_bytes)
+        return fail(ctx, SLAMCU_SIZE_MISMATCH, "sequence desc_bytes %d != NumBRIEFPairs/8 = %d", s->v.desc_bytes,
+                    det->p.pairs / 8);
+    if (n == 0) return SLAMCU_OK;
+    int rc = seq_detect(s, det, first, n, false);
+    if (rc != SLAMCU_OK) return rc;
+    return seq_compute(s, det, first, n);
+}
+
+int slamcu_sequence_match(slamcu_sequence* s, slamcu_matcher* m, int first, int n_pairs, int with_kp) {
+    if (!s || !m || s->ctx != m->ctx) return SLAMCU_INVALID_ARGUMENT;
+    slamcu_context* ctx = s->ctx;
+    if (first < 0 || n_pairs < 0 || first + n_pairs + 1 > s->max_frames)
+        return fail(ctx, SLAMCU_INVALID_ARGUMENT, "bad pair range");
+    if (m->distance_type != SLAMCU_DISTANCE_HAMMING)
+        return fail(ctx, SLAMCU_UNSUPPORTED, "L2 distance requires float descriptors. Use the float overload.");
+    if (n_pairs == 0) return SLAMCU_OK;
+    const SeqView& v = s->v;
+    MatchJob j{};
+    const size_t dstride = (size_t)v.cap_kp * v.desc_words;
+    j.dq = v.desc + (size_t)first * dstride;
+    j.dt = j.dq + dstride;
+    j.kq = v.kps + (size_t)first * v.cap_kp;
+    j.kt = j.kq + v.cap_kp;
+    j.nq = v.n_kp + first;
+    j.nt = v.n_kp + first + 1;
+    j.orq = v.desc_or + (size_t)first * v.desc_words;
+    j.ort = j.orq + v.desc_words;
+    j.cand = v.cand + (size_t)first * v.cap_kp;
+    j.matches = v.matches + (size_t)first * v.cap_kp;
+    j.n_match = v.n_match + first;
+    j.status = v.status + first;
+    j.desc_pair_stride = dstride;
+    j.kp_pair_stride = v.cap_kp;
+    j.count_stride = 1;
+    j.cand_pair_stride = v.cap_kp;
+    j.or_stride = v.desc_words;
+    j.desc_words = v.desc_words;
+    j.max_q = v.cap_kp;
+    j.cap_out = v.cap_kp;
+    ctx->launches += launch_match(j, n_pairs, m->p, true, with_kp ? 1 : 0, s->sort_keys + (size_t)first * v.cap_kp,
+                                  ctx->stream);
+    return check_launch(ctx, "match kernels");
+}
+
+int slamcu_sequence_counts(slamcu_sequence* s, int first, int n, int32_t* counts4) {
+    if (!s || !counts4) return SLAMCU_INVALID_ARGUMENT;
+    slamcu_context* ctx = s->ctx;
+    if (first < 0 || n < 0 || first + n > s->max_frames) return fail(ctx, SLAMCU_INVALID_ARGUMENT, "bad frame range");
+    if (n == 0) return SLAMCU_OK;
+    int* h = s->h_counts;
+    const size_t F = (size_t)s->max_frames;
+    CU(ctx, cudaMemcpyAsync(h, s->v.n_kp + first, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(h + F, s->v.n_match + first, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(h + 2 * F, s->v.n_raw + first, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(h + 3 * F, s->v.status + first, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < n; i++) {
+        counts4[4 * i + 0] = h[i];
+        counts4[4 * i + 1] = h[F + i];
+        counts4[4 * i + 2] = h[2 * F + i];
+        counts4[4 * i + 3] = h[3 * F + i];
+    }
+    return SLAMCU_OK;
+}
+
+int slamcu_sequence_frame(slamcu_sequence* s, int f, slamcu_keypoint* kps, uint8_t* desc, int desc_stride, int capacity,
+                          int* n_out) {
+    if (!s || !n_out) return SLAMCU_INVALID_ARGUMENT;
+    slamcu_context* ctx = s->ctx;
+    if (f < 0 || f >= s->max_frames) return fail(ctx, SLAMCU_INVALID_ARGUMENT, "bad frame index");
+    int32_t c[4];
+    int rc = slamcu_sequence_counts(s, f, 1, c);
+    if (rc != SLAMCU_OK) return rc;
+    *n_out = c[0];
+    if (c[3] & (kStRawOverflow | kStKpOverflow))
+        return fail(ctx, SLAMCU_CAPACITY, "frame %d overflowed a device list (status %d): raise max_raw_corners / max_keypoints",
+                    f, c[3]);
+    if (c[0] > capacity) return fail(ctx, SLAMCU_CAPACITY, "need room for %d keypoints, capacity %d", c[0], capacity);
+    if (c[0] == 0) return SLAMCU_OK;
+    const SeqView& v = s->v;
+    if (kps)
+        CU(ctx, cudaMemcpyAsync(kps, v.kps + (size_t)f * v.cap_kp, c[0] * sizeof(slamcu_keypoint), cudaMemcpyDeviceToHost,
+                                ctx->stream));
+    if (desc) {
+        if (desc_stride < v.desc_bytes) return fail(ctx, SLAMCU_INVALID_ARGUMENT, "desc_stride too small");
+        CU(ctx, cudaMemcpy2DAsync(desc, desc_stride, v.desc + (size_t)f * v.cap_kp * v.desc_words, v.desc_words * 4,
+                                  v.desc_bytes, c[0], cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return SLAMCU_OK;
+}
+
+int slamcu_sequence_matches(slamcu_sequence* s, int f, slamcu_dmatch* matches, int capacity, int* n_out) {
+    if (!s || !n_out) return SLAMCU_INVALID_ARGUMENT;
+    slamcu_context* ctx = s->ctx;
+    if (f < 0 || f >= s->max_frames) return fail(ctx, SLAMCU_INVALID_ARGUMENT, "bad frame index");
+    int32_t c[4];
+    int rc = slamcu_sequence_counts(s, f, 1, c);
+    if (rc != SLAMCU_OK) return rc;
+    *n_out = c[1];
+    if (c[3] & kStMatchOverflow) return fail(ctx, SLAMCU_CAPACITY, "match list overflow on pair %d", f);
+    if (c[1] > capacity) return fail(ctx, SLAMCU_CAPACITY, "need room for %d matches, capacity %d", c[1], capacity);
+    if (c[1] && matches) {
+        CU(ctx, cudaMemcpyAsync(matches, s->v.matches + (size_t)f * s->v.cap_kp, c[1] * sizeof(slamcu_dmatch),
+                                cudaMemcpyDeviceToHost, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return SLAMCU_OK;
+}
+
+int slamcu_sequence_download(slamcu_sequence* s, int first, int n, slamcu_keypoint* kps, uint8_t* desc, slamcu_dmatch* matches,
+                             int32_t* counts4) {
+    if (!s) return SLAMCU_INVALID_ARGUMENT;
+    slamcu_context* ctx = s->ctx;
+    if (first < 0 || n < 0 || first + n > s->max_frames) return fail(ctx, SLAMCU_INVALID_ARGUMENT, "bad frame range");
+    if (n == 0) return SLAMCU_OK;
+    const SeqView& v = s->v;
+    if (kps)
+        CU(ctx, cudaMemcpyAsync(kps, v.kps + (size_t)first * v.cap_kp, (size_t)n * v.cap_kp * sizeof(slamcu_keypoint),
+                                cudaMemcpyDeviceToHost, ctx->stream));
+    if (desc)
+        CU(ctx, cudaMemcpy2DAsync(desc, v.desc_bytes, v.desc + (size_t)first * v.cap_kp * v.desc_words, v.desc_words * 4,
+                                  v.desc_bytes, (size_t)n * v.cap_kp, cudaMemcpyDeviceToHost, ctx->stream));
+    if (matches)
+        CU(ctx, cudaMemcpyAsync(matches, v.matches + (size_t)first * v.cap_kp, (size_t)n * v.cap_kp * sizeof(slamcu_dmatch),
+                                cudaMemcpyDeviceToHost, ctx->stream));
+    if (counts4) {
+        // strided D2H of the four count arrays into [n][4]
+        CU(ctx, cudaMemcpy2DAsync(counts4 + 0, 16, v.n_kp + first, 4, 4, n, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(ctx, cudaMemcpy2DAsync(counts4 + 1, 16, v.n_match + first, 4, 4, n, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(ctx, cudaMemcpy2DAsync(counts4 + 2, 16, v.n_raw + first, 4, 4, n, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(ctx, cudaMemcpy2DAsync(counts4 + 3, 16, v.status + first, 4, 4, n, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    return SLAMCU_OK;
+}
+
+/* ---------------------------------------------------------------------------------------------- */
+/* detector                                                                                        */
+/* ---------------------------------------------------------------------------------------------- */
+// Constructor-time host tables.  They are functions of the *host* C++ library the reference is built
+// against -- libstdc++'s minstd_rand0 + Marsaglia-polar normal_distribution<float>, libm's exp -- so
+// they are produced on the host with the very same calls (feature_detector.cpp:286-313, :321-335).
+int slamcu_default_brief_pattern(int patch_size, int num_pairs, int32_t* pattern4, int capacity_pairs, int* n_out) {
+    if (!pattern4 || !n_out || patch_size <= 0 || num_pairs <= 0) return SLAMCU_INVALID_ARGUMENT;
+    const float scale = static_cast<float>(patch_size) / 2.0F;
+    std::default_random_engine gen;
+    std::normal_distribution<float> dist(0.0F, 1.0F);
+    int n = 0;
+    for (int i = 0; i < num_pairs; i++) {
+        const float x1 = dist(gen) * scale;
+        const float y1 = dist(gen) * scale;
+        const float x2 = dist(gen) * scale;
+        const float y2 = dist(gen) * scale;
+        if (std::abs(x1) < scale && std::abs(y1) < scale && std::abs(x2) < scale && std::abs(y2) < scale) {
+            if (n >= capacity_pairs) return SLAMCU_CAPACITY;
+            pattern4[4 * n + 0] = static_cast<int>(x1);
+            pattern4[4 * n + 1] = static_cast<int>(y1);
+            pattern4[4 * n + 2] = static_cast<int>(x2);
+            pattern4[4 * n + 3] = static_cast<int>(y2);
+            n++;
+        }
+    }
+    *n_out = n;
+    return SLAMCU_OK;
+}
+
+int slamcu_default_blur_weights(double* weights25) {
+    if (!weights25) return SLAMCU_INVALID_ARGUMENT;
+    const double sigma = 1.0;
+    double sum = 0.0;
+    for (int i = -2; i <= 2; i++)
+        for (int j = -2; j <= 2; j++) {
+            const double v = std::exp(-((i * i) + (j * j)) / (2 * sigma * sigma));
+            weights25[(i + 2) * 5 + (j + 2)] = v;
+            sum += v;
+        }
+    for (int k = 0; k < 25; k++) weights25[k] /= sum;
+    return SLAMCU_OK;
+}
+
+int slamcu_detector_create(slamcu_context* ctx, const slamcu_detector_config* cfg, slamcu_detector** out) {
+    if (!ctx || !cfg || !out) return SLAMCU_INVALID_ARGUMENT;
+    *out = nullptr;
+    // same range checks (and messages) as the reference constructor, feature_detector.hpp:60-93
+    if (cfg->intensity_threshold < 0 || cfg->intensity_threshold > 255)
+        return fail(ctx, SLAMCU_INVALID_ARGUMENT, "Intensity threshold must be in the range [0, 255].");
+    if (cfg->contiguous_pixels_threshold < 0 || cfg->contiguous_pixels_threshold > 16)
+        return fail(ctx, SLAMCU_INVALID_ARGUMENT, "Contiguous pixels threshold must be in the range [0, 16].");
+    if (cfg->non_max_suppression != 0 && cfg->non_max_suppression != 1)
+        return fail(ctx, SLAMCU_INVALID_ARGUMENT, "Non-max suppression must be either 0 (false) or 1 (true).");
+    if (cfg->suppression_window_size <= 0)
+        return fail(ctx, SLAMCU_INVALID_ARGUMENT, "Suppression window size must be a positive integer.");
+    if (cfg->patch_size <= 0 || cfg->patch_size % 2 == 0)
+        return fail(ctx, SLAMCU_INVALID_ARGUMENT, "Patch size must be a positive odd integer.");
+    if (cfg->num_brief_pairs <= 0 || cfg->num_brief_pairs % 8 != 0)
+        return fail(ctx, SLAMCU_INVALID_ARGUMENT, "Number of BRIEF pairs must be a positive multiple of 8.");
+    if (cfg->num_brief_pairs > 2048) return fail(ctx, SLAMCU_UNSUPPORTED, "NumBRIEFPairs > 2048 is not supported");
+    if (cfg->suppression_window_size > 4096) return fail(ctx, SLAMCU_UNSUPPORTED, "SuppressionWindowSize > 4096");
+    if (cfg->n_pattern < 0 || cfg->n_pattern > cfg->num_brief_pairs || (cfg->n_pattern > 0 && !cfg->pattern))
+        return fail(ctx, SLAMCU_INVALID_ARGUMENT, "BRIEF pattern missing or longer than NumBRIEFPairs");
+    if (!cfg->blur_weights) return fail(ctx, SLAMCU_INVALID_ARGUMENT, "blur weights missing");
+    if (cfg->mode != SLAMCU_MODE_REFERENCE) return fail(ctx, SLAMCU_UNSUPPORTED, "detector mode %d not built", cfg->mode);
+    CU(ctx, cudaSetDevice(ctx->device));
+    slamcu_detector* d = new (std::nothrow) slamcu_detector();
+    if (!d) return SLAMCU_CUDA_ERROR;
+    d->ctx = ctx;
+    d->mode = cfg->mode;
+    d->p.thr = cfg->intensity_threshold;
+    d->p.arc = cfg->contiguous_pixels_threshold;
+    d->p.nms = cfg->non_max_suppression;
+    d->p.window = cfg->suppression_window_size;
+    d->p.patch = cfg->patch_size;
+    d->p.pairs = cfg->num_brief_pairs;
+    d->p.n_pattern = cfg->n_pattern;
+    for (int i = 0; i < 25; i++) d->p.blur_w[i] = cfg->blur_weights[i];
+    const size_t pbytes = (size_t)std::max(cfg->n_pattern, 1) * 4 * sizeof(int);
+    if (cudaMalloc(reinterpret_cast<void**>(&d->d_pattern), pbytes) != cudaSuccess) {
+        delete d;
+        return fail(ctx, SLAMCU_CUDA_ERROR, "cudaMalloc(pattern) failed");
+    }
+    if (cfg->n_pattern > 0)
+        cudaMemcpyAsync(d->d_pattern, cfg->pattern, (size_t)cfg->n_pattern * 4 * sizeof(int), cudaMemcpyHostToDevice,
+                        ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
+    *out = d;
+    return SLAMCU_OK;
+}
+
+void slamcu_detector_destroy(slamcu_detector* d) {
+    if (!d) return;
+    cudaSetDevice(d->ctx->device);
+    if (d->one) slamcu_sequence_destroy(d->one);
+    if (d->d_pattern) cudaFree(d->d_pattern);
+    delete d;
+}
+
+// single-frame workspace, re-created when the image geometry (or needed capacity) changes
+static int detector_workspace(slamcu_detector* d, int rows, int cols, int min_kp) {
+    slamcu_context* ctx = d->ctx;
+    const int desc_bytes = d->p.pairs / 8;
+    if (d->one && d->one->v.rows == rows && d->one->v.cols == cols && d->one->v.cap_kp >= min_kp) return SLAMCU_OK;
+    if (d->one) {
+        slamcu_sequence_destroy(d->one);
+        d->one = nullptr;
+    }
+    const long long px = (long long)rows * cols;
+    // single calls favour safety over footprint: room for one corner per 4 pixels
+    int cap_raw = (int)std::min<long long>(std::max<long long>(px / 4, 8192), kMaxRawCap);
+    int cap_kp = d->p.nms ? (int)std::min<long long>(std::max<long long>(px / 16, 4096), kMaxRawCap) : cap_raw;
+    cap_kp = std::max(cap_kp, min_kp);
+    return slamcu_sequence_create(ctx, rows, cols, 1, cap_raw, cap_kp, desc_bytes, &d->one);
+}
+
+static int check_image(slamcu_context* ctx, const uint8_t* image, int rows, int cols, int stride) {
+    if (!image || rows <= 0 || cols <= 0 || stride < cols) return fail(ctx, SLAMCU_INVALID_ARGUMENT, "bad image");
+    return SLAMCU_OK;
+}
+
+static int detect_common(slamcu_detector* d, const uint8_t* image, int rows, int cols, int stride, slamcu_keypoint* kps,
+                         uint8_t* desc, int desc_stride, int capacity, int* n_out, int what /*0 detect,1 both,2 raw*/) {
+    if (!d || !n_out) return SLAMCU_INVALID_ARGUMENT;
+    slamcu_context* ctx = d->ctx;
+    int rc = check_image(ctx, image, rows, cols, stride);
+    if (rc != SLAMCU_OK) return rc;
+    CU(ctx, cudaSetDevice(ctx->device));
+    rc = detector_workspace(d, rows, cols, 0);
+    if (rc != SLAMCU_OK) return rc;
+    slamcu_sequence* s = d->one;
+    rc = slamcu_sequence_upload(s, 0, 1, image, stride);
+    if (rc != SLAMCU_OK) return rc;
+    rc = seq_detect(s, d, 0, 1, what == 2);
+    if (rc != SLAMCU_OK) return rc;
+    if (what == 1) {
+        rc = seq_compute(s, d, 0, 1);
+        if (rc != SLAMCU_OK) return rc;
+    }
+    return slamcu_sequence_frame(s, 0, kps, what == 1 ? desc : nullptr, desc_stride, capacity, n_out);
+}
+
+int slamcu_detect(slamcu_detector* d, const uint8_t* image, int rows, int cols, int stride, slamcu_keypoint* kps,
+                  int capacity, int* n_out) {
+    return detect_common(d, image, rows, cols, stride, kps, nullptr, 0, capacity, n_out, 0);
+}
+
+int slamcu_fast_corners(slamcu_detector* d, const uint8_t* image, int rows, int cols, int stride, slamcu_keypoint* kps,
+                        int capacity, int* n_out) {
+    if (!d) return SLAMCU_INVALID_ARGUMENT;
+    // raw probe: the keypoint list must be able to hold every raw corner
+    slamcu_context* ctx = d->ctx;
+    int rc = check_image(ctx, image, rows, cols, stride);
+    if (rc != SLAMCU_OK) return rc;
+    const long long px = (long long)rows * cols;
+    rc = detector_workspace(d, rows, cols, (int)std::min<long long>(std::max<long long>(px / 4, 8192), kMaxRawCap));
+    if (rc != SLAMCU_OK) return rc;
+    return detect_common(d, image, rows, cols, stride, kps, nullptr, 0, capacity, n_out, 2);
+}
+
+int slamcu_detect_and_compute(slamcu_detector* d, const uint8_t* image, int rows, int cols, int stride,
+                              slamcu_keypoint* kps, uint8_t* desc, int desc_stride, int capacity, int* n_out) {
+    if (!desc) return SLAMCU_INVALID_ARGUMENT;
+    return detect_common(d, image, rows, cols, stride, kps, desc, desc_stride, capacity, n_out, 1);
+}
+
+int slamcu_compute(slamcu_detector* d, const uint8_t* image, int rows, int cols, int stride, slamcu_keypoint* kps, int n,
+                   uint8_t* desc, int desc_stride) {
+    if (!d) return SLAMCU_INVALID_ARGUMENT;
+    slamcu_context* ctx = d->ctx;
+    if (n < 0) return fail(ctx, SLAMCU_INVALID_ARGUMENT, "negative keypoint count");
+    if (n == 0) return SLAMCU_OK;  // reference: descriptors = DescriptorMatrix(0, 0) (feature_detector.cpp:22-25)
+    if (!kps || !desc) return fail(ctx, SLAMCU_INVALID_ARGUMENT, "null keypoints / descriptors");
+    int rc = check_image(ctx, image, rows, cols, stride);
+    if (rc != SLAMCU_OK) return rc;
+    CU(ctx, cudaSetDevice(ctx->device));
+    rc = detector_workspace(d, rows, cols, n);
+    if (rc != SLAMCU_OK) return rc;
+    slamcu_sequence* s = d->one;
+    rc = slamcu_sequence_upload(s, 0, 1, image, stride);
+    if (rc != SLAMCU_OK) return rc;
+    CU(ctx, cudaMemcpyAsync(s->v.kps, kps, (size_t)n * sizeof(slamcu_keypoint), cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(s->v.n_kp, &n, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaMemsetAsync(s->v.status, 0, sizeof(int), ctx->stream));
+    rc = seq_compute(s, d, 0, 1);
+    if (rc != SLAMCU_OK) return rc;
+    int got = 0;
+    return slamcu_sequence_frame(s, 0, kps, desc, desc_stride, n, &got);
+}
+
+int slamcu_gaussian_blur(slamcu_detector* d, const uint8_t* image, int rows, int cols, int stride, uint8_t* out,
+                         int out_stride) {
+    if (!d || !out) return SLAMCU_INVALID_ARGUMENT;
+    slamcu_context* ctx = d->ctx;
+    int rc = check_image(ctx, image, rows, cols, stride);
+    if (rc != SLAMCU_OK) return rc;
+    if (out_stride < cols) return fail(ctx, SLAMCU_INVALID_ARGUMENT, "out_stride too small");
+    CU(ctx, cudaSetDevice(ctx->device));
+    rc = detector_workspace(d, rows, cols, 0);
+    if (rc != SLAMCU_OK) return rc;
+    slamcu_sequence* s = d->one;
+    rc = slamcu_sequence_upload(s, 0, 1, image, stride);
+    if (rc != SLAMCU_OK) return rc;
+    ctx->launches += launch_blur(s->v, 0, 1, d->p, ctx->stream);
+    rc = check_launch(ctx, "blur kernel");
+    if (rc != SLAMCU_OK) return rc;
+    CU(ctx, cudaMemcpy2DAsync(out, out_stride, s->v.blur, s->v.pitch, cols, rows, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return SLAMCU_OK;
+}
+
+/* ---------------------------------------------------------------------------------------------- */
+/* matcher                                                                                         */
+/* ---------------------------------------------------------------------------------------------- */
+int slamcu_matcher_create(slamcu_context* ctx, const slamcu_matcher_config* cfg, slamcu_matcher** out) {
+    if (!ctx || !cfg || !out) return SLAMCU_INVALID_ARGUMENT;
+    *out = nullptr;
+    // feature_matcher.cpp:25-57
+    if (cfg->distance_type != SLAMCU_DISTANCE_HAMMING && cfg->distance_type != SLAMCU_DISTANCE_L2)
+        return fail(ctx, SLAMCU_INVALID_ARGUMENT, "Invalid distance type. Must be 'HAMMING' or 'L2'.");
+    if (cfg->filter_matches != 0 && cfg->filter_matches != 1)
+        return fail(ctx, SLAMCU_INVALID_ARGUMENT, "FilterMatches must be either 0 (false) or 1 (true).");
+    if (cfg->filter_matches && cfg->good_matches_count <= 0)
+        return fail(ctx, SLAMCU_INVALID_ARGUMENT, "GoodMatchesCount must be positive when filtering is enabled.");
+    if (cfg->use_ratio_test != 0 && cfg->use_ratio_test != 1)
+        return fail(ctx, SLAMCU_INVALID_ARGUMENT, "UseRatioTest must be either 0 (false) or 1 (true).");
+    if (!(cfg->ratio_test_threshold >= 0.0f && cfg->ratio_test_threshold <= 1.0f))
+        return fail(ctx, SLAMCU_INVALID_ARGUMENT, "RatioTestThreshold must be in the range [0, 1].");
+    slamcu_matcher* m = new (std::nothrow) slamcu_matcher();
+    if (!m) return SLAMCU_CUDA_ERROR;
+    m->ctx = ctx;
+    m->distance_type = cfg->distance_type;
+    m->p.filter = cfg->filter_matches;
+    m->p.good = cfg->good_matches_count;
+    m->p.use_ratio = cfg->use_ratio_test;
+    m->p.ratio = cfg->ratio_test_threshold;
+    *out = m;
+    return SLAMCU_OK;
+}
+
+static void matcher_free(slamcu_matcher* m) {
+    void* ptrs[] = {m->d1, m->d2, m->k1, m->k2, m->cand, m->matches, m->keys, m->ors, m->counts};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    m->d1 = m->d2 = nullptr;
+    m->k1 = m->k2 = nullptr;
+    m->cand = nullptr;
+    m->matches = nullptr;
+    m->keys = nullptr;
+    m->ors = nullptr;
+    m->counts = nullptr;
+    m->cap1 = m->cap2 = m->cap_words = 0;
+}
+
+void slamcu_matcher_destroy(slamcu_matcher* m) {
+    if (!m) return;
+    cudaSetDevice(m->ctx->device);
+    cudaStreamSynchronize(m->ctx->stream);
+    matcher_free(m);
+    delete m;
+}
+
+static int matcher_workspace(slamcu_matcher* m, int n1, int n2, int words) {
+    slamcu_context* ctx = m->ctx;
+    if (n1 <= m->cap1 && n2 <= m->cap2 && words <= m->cap_words) return SLAMCU_OK;
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    const int c1 = std::max(n1, m->cap1), c2 = std::max(n2, m->cap2), w = std::max(words, m->cap_words);
+    matcher_free(m);
+    CU(ctx, cudaMalloc(reinterpret_cast<void**>(&m->d1), (size_t)c1 * w * 4));
+    CU(ctx, cudaMalloc(reinterpret_cast<void**>(&m->d2), (size_t)c2 * w * 4));
+    CU(ctx, cudaMalloc(reinterpret_cast<void**>(&m->k1), (size_t)c1 * sizeof(slamcu_keypoint)));
+    CU(ctx, cudaMalloc(reinterpret_cast<void**>(&m->k2), (size_t)c2 * sizeof(slamcu_keypoint)));
+    CU(ctx, cudaMalloc(reinterpret_cast<void**>(&m->cand), (size_t)c1 * sizeof(int4)));
+    CU(ctx, cudaMalloc(reinterpret_cast<void**>(&m->matches), (size_t)c1 * sizeof(slamcu_dmatch)));
+    CU(ctx, cudaMalloc(reinterpret_cast<void**>(&m->keys), (size_t)c1 * sizeof(unsigned long long)));
+    CU(ctx, cudaMalloc(reinterpret_cast<void**>(&m->ors), (size_t)2 * w * 4));
+    CU(ctx, cudaMalloc(reinterpret_cast<void**>(&m->counts), 4 * sizeof(int)));
+    m->cap1 = c1;
+    m->cap2 = c2;
+    m->cap_words = w;
+    return SLAMCU_OK;
+}
+
+static int match_common(slamcu_matcher* m, const uint8_t* d1, int n1, int width1, const uint8_t* d2, int n2, int width2,
+                        const slamcu_keypoint* kp1, int nkp1, const slamcu_keypoint* kp2, int nkp2, bool emit) {
+    slamcu_context* ctx = m->ctx;
+    // validateInputs, feature_matcher.cpp:97-111 (same order of checks)
+    if (n1 <= 0 || n2 <= 0 || !d1 || !d2) return fail(ctx, SLAMCU_EMPTY_INPUT, "Empty descriptors provided.");
+    if (m->distance_type != SLAMCU_DISTANCE_HAMMING)
+        return fail(ctx, SLAMCU_UNSUPPORTED, "DescriptorMatrix (uint8_t) requires HAMMING distance.");
+    if (width1 != width2) return fail(ctx, SLAMCU_SIZE_MISMATCH, "Descriptor dimensions must match.");
+    if (width1 <= 0 || width1 > 256) return fail(ctx, SLAMCU_INVALID_ARGUMENT, "descriptor width %d unsupported", width1);
+    const bool with_kp = kp1 && kp2 && nkp1 > 0 && nkp2 > 0;  // feature_matcher.cpp:150
+    if (with_kp && (nkp1 < n1 || nkp2 < n2))
+        return fail(ctx, SLAMCU_SIZE_MISMATCH, "fewer keypoints than descriptors");
+    CU(ctx, cudaSetDevice(ctx->device));
+    const int words = (width1 + 3) / 4;
+    int rc = matcher_workspace(m, n1, n2, words);
+    if (rc != SLAMCU_OK) return rc;
+    if (width1 & 3) {
+        CU(ctx, cudaMemsetAsync(m->d1, 0, (size_t)n1 * words * 4, ctx->stream));
+        CU(ctx, cudaMemsetAsync(m->d2, 0, (size_t)n2 * words * 4, ctx->stream));
+    }
+    CU(ctx, cudaMemcpy2DAsync(m->d1, words * 4, d1, width1, width1, n1, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaMemcpy2DAsync(m->d2, words * 4, d2, width2, width2, n2, cudaMemcpyHostToDevice, ctx->stream));
+    if (with_kp) {
+        CU(ctx, cudaMemcpyAsync(m->k1, kp1, (size_t)n1 * sizeof(slamcu_keypoint), cudaMemcpyHostToDevice, ctx->stream));
+        CU(ctx, cudaMemcpyAsync(m->k2, kp2, (size_t)n2 * sizeof(slamcu_keypoint), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    const int h_counts[4] = {n1, n2, 0, 0};
+    CU(ctx, cudaMemcpyAsync(m->counts, h_counts, sizeof h_counts, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->launches += launch_desc_or(m->d1, m->counts + 0, words, m->ors, ctx->stream);
+    ctx->launches += launch_desc_or(m->d2, m->counts + 1, words, m->ors + words, ctx->stream);
+    MatchJob j{};
+    j.dq = m->d1;
+    j.dt = m->d2;
+    j.kq = m->k1;
+    j.kt = m->k2;
+    j.nq = m->counts + 0;
+    j.nt = m->counts + 1;
+    j.orq = m->ors;
+    j.ort = m->ors + words;
+    j.cand = m->cand;
+    j.matches = m->matches;
+    j.n_match = m->counts + 2;
+    j.status = m->counts + 3;
+    j.desc_words = words;
+    j.max_q = n1;
+    j.cap_out = n1;
+    ctx->launches += launch_match(j, 1, m->p, emit, with_kp ? 1 : 0, m->keys, ctx->stream);
+    return check_launch(ctx, "match kernels");
+}
+
+int slamcu_match(slamcu_matcher* m, const uint8_t* d1, int n1, int width1, const uint8_t* d2, int n2, int width2,
+                 const slamcu_keypoint* kp1, int nkp1, const slamcu_keypoint* kp2, int nkp2, slamcu_dmatch* matches,
+                 int capacity, int* n_out) {
+    if (!m || !n_out) return SLAMCU_INVALID_ARGUMENT;
+    slamcu_context* ctx = m->ctx;
+    *n_out = 0;
+    int rc = match_common(m, d1, n1, width1, d2, n2, width2, kp1, nkp1, kp2, nkp2, true);
+    if (rc != SLAMCU_OK) return rc;
+    int h[4];
+    CU(ctx, cudaMemcpyAsync(h, m->counts, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    *n_out = h[2];
+    if (h[2] > capacity) return fail(ctx, SLAMCU_CAPACITY, "need room for %d matches, capacity %d", h[2], capacity);
+    if (h[2] > 0) {
+        if (!matches) return fail(ctx, SLAMCU_INVALID_ARGUMENT, "null output");
+        CU(ctx, cudaMemcpyAsync(matches, m->matches, (size_t)h[2] * sizeof(slamcu_dmatch), cudaMemcpyDeviceToHost,
+                                ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return SLAMCU_OK;
+}
+
+int slamcu_knn2_hamming(slamcu_matcher* m, const uint8_t* d1, int n1, const uint8_t* d2, int n2, int width,
+                        slamcu_knn2* out) {
+    if (!m || !out) return SLAMCU_INVALID_ARGUMENT;
+    slamcu_context* ctx = m->ctx;
+    int rc = match_common(m, d1, n1, width, d2, n2, width, nullptr, 0, nullptr, 0, false);
+    if (rc != SLAMCU_OK) return rc;
+    std::vector<int4> h((size_t)n1);
+    CU(ctx, cudaMemcpyAsync(h.data(), m->cand, (size_t)n1 * sizeof(int4), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < n1; i++) {
+        out[i].trainIdx0 = h[i].x;
+        out[i].distance0 = (float)h[i].y;
+        out[i].trainIdx1 = h[i].w;
+        out[i].distance1 = (h[i].w >= 0) ? (float)h[i].z : 0.0f;
+    }
+    return SLAMCU_OK;
+}
+
+/* ---------------------------------------------------------------------------------------------- */
+/* image preparation                                                                               */
+/* ---------------------------------------------------------------------------------------------- */
+int slamcu_bgr_to_gray(slamcu_context* ctx, const uint8_t* bgr, int rows, int cols, int stride, uint8_t* gray,
+                       int gray_stride) {
+    if (!ctx) return SLAMCU_INVALID_ARGUMENT;
+    if (!bgr || !gray || rows <= 0 || cols <= 0 || stride < 3 * cols || gray_stride < cols)
+        return fail(ctx, SLAMCU_INVALID_ARGUMENT, "bad bgr image");
+    CU(ctx, cudaSetDevice(ctx->device));
+    const size_t in_b = (size_t)rows * cols * 3, out_b = (size_t)rows * cols;
+    int rc = ensure_scratch(ctx, in_b + out_b);
+    if (rc != SLAMCU_OK) return rc;
+    uint8_t* d_in = static_cast<uint8_t*>(ctx->scratch);
+    uint8_t* d_out = d_in + in_b;
+    CU(ctx, cudaMemcpy2DAsync(d_in, (size_t)cols * 3, bgr, stride, (size_t)cols * 3, rows, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->launches += launch_bgr2gray(d_in, rows, cols, cols * 3, d_out, cols, ctx->stream);
+    rc = check_launch(ctx, "bgr2gray");
+    if (rc != SLAMCU_OK) return rc;
+    CU(ctx, cudaMemcpy2DAsync(gray, gray_stride, d_out, cols, cols, rows, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return SLAMCU_OK;
+}
+
+int slamcu_undistort(slamcu_context* ctx, const uint8_t* gray, int rows, int cols, int stride, const double* K4,
+                     const double* D4, uint8_t* out_u8, double* out_f64) {
+    if (!ctx) return SLAMCU_INVALID_ARGUMENT;
+    if (!gray || rows <= 0 || cols <= 0) return fail(ctx, SLAMCU_EMPTY_INPUT, "Input image is empty.");  // common.hpp:130-132
+    if (stride < cols || !K4 || !D4 || (!out_u8 && !out_f64)) return fail(ctx, SLAMCU_INVALID_ARGUMENT, "bad arguments");
+    CU(ctx, cudaSetDevice(ctx->device));
+    const size_t px = (size_t)rows * cols;
+    const size_t off_map = (px + 255) / 256 * 256, off_u8 = off_map + px * 4, off_f64 = (off_u8 + px + 255) / 256 * 256;
+    int rc = ensure_scratch(ctx, off_f64 + px * 8);
+    if (rc != SLAMCU_OK) return rc;
+    uint8_t* base = static_cast<uint8_t*>(ctx->scratch);
+    uint8_t* d_in = base;
+    int* d_map = reinterpret_cast<int*>(base + off_map);
+    uint8_t* d_u8 = base + off_u8;
+    double* d_f64 = reinterpret_cast<double*>(base + off_f64);
+    CU(ctx, cudaMemcpy2DAsync(d_in, cols, gray, stride, cols, rows, cudaMemcpyHostToDevice, ctx->stream));
+    CamParams cam{K4[0], K4[1], K4[2], K4[3], D4[0], D4[1], D4[2], D4[3]};
+    ctx->launches += launch_undistort_map(rows, cols, cam, d_map, ctx->stream);
+    ctx->launches += launch_remap(d_in, rows, cols, cols, d_map, out_u8 ? d_u8 : nullptr, out_f64 ? d_f64 : nullptr,
+                                  ctx->stream);
+    rc = check_launch(ctx, "undistort");
+    if (rc != SLAMCU_OK) return rc;
+    if (out_u8) CU(ctx, cudaMemcpyAsync(out_u8, d_u8, px, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_f64) CU(ctx, cudaMemcpyAsync(out_f64, d_f64, px * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return SLAMCU_OK;
+}
+
+/* ---------------------------------------------------------------------------------------------- */
+/* two-view geometry                                                                               */
+/* ---------------------------------------------------------------------------------------------- */
+int slamcu_ransac_score(slamcu_context* ctx, const double* models9, int n_models, const double* x1, const double* x2,
+                        int n, double thr2, int32_t* counts, uint8_t* masks) {
+    if (!ctx) return SLAMCU_INVALID_ARGUMENT;
+    if (!models9 || !x1 || !x2 || !counts || n_models <= 0 || n <= 0) return fail(ctx, SLAMCU_INVALID_ARGUMENT, "bad arguments");
+    CU(ctx, cudaSetDevice(ctx->device));
+    const size_t b_models = (size_t)n_models * 9 * 8, b_pts = (size_t)n * 2 * 8, b_cnt = ((size_t)n_models * 4 + 255) / 256 * 256;
+    const size_t b_mask = masks ? (size_t)n_models * n : 0;
+    int rc = ensure_scratch(ctx, b_models + 2 * b_pts + b_cnt + b_mask + 1024);
+    if (rc != SLAMCU_OK) return rc;
+    uint8_t* base = static_cast<uint8_t*>(ctx->scratch);
+    double* d_models = reinterpret_cast<double*>(base);
+    double* d_x1 = reinterpret_cast<double*>(base + b_models);
+    double* d_x2 = reinterpret_cast<double*>(base + b_models + b_pts);
+    int* d_cnt = reinterpret_cast<int*>(base + b_models + 2 * b_pts);
+    uint8_t* d_mask = masks ? base + b_models + 2 * b_pts + b_cnt : nullptr;
+    CU(ctx, cudaMemcpyAsync(d_models, models9, b_models, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(d_x1, x1, b_pts, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(d_x2, x2, b_pts, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->launches += launch_ransac_score(d_models, n_models, d_x1, d_x2, n, thr2, d_cnt, d_mask, ctx->stream);
+    rc = check_launch(ctx, "ransac_score");
+    if (rc != SLAMCU_OK) return rc;
+    CU(ctx, cudaMemcpyAsync(counts, d_cnt, (size_t)n_models * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (masks) CU(ctx, cudaMemcpyAsync(masks, d_mask, b_mask, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return SLAMCU_OK;
+}
+
+int slamcu_find_essential(slamcu_context* ctx, const float*, const float*, int, const double*, double, double, int,
+                          double*, uint8_t*, int*) {
+    return fail(ctx, SLAMCU_UNSUPPORTED, "slamcu_find_essential: 5-point solver not built yet");
+}
+
+}  // extern "C"

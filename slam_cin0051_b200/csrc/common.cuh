@@ -1,0 +1,95 @@
+// common.cuh -- shared device-side views and launch declarations of the slamcu kernel library (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/slam/cuda/slamcu.h"
+
+namespace slamcu {
+
+constexpr int kKeyIdxBits = 20;                 // sort key = (score << 20) | raster index
+constexpr uint32_t kKeyIdxMask = (1u << kKeyIdxBits) - 1;
+constexpr int kMaxRawCap = 1 << kKeyIdxBits;    // raw-corner capacity per frame
+constexpr int kMaxPattern = 1024;               // BRIEF pairs held in constant memory
+
+// status bits accumulated per frame on the device
+enum : int { kStRawOverflow = 1, kStKpOverflow = 2, kStMatchOverflow = 4 };
+
+// Device-resident layout of a frame sequence (all pointers are HBM; `F` = max_frames).
+struct SeqView {
+    int rows, cols, pitch;   // pitch: bytes per image row, multiple of 128
+    int mwords;              // 32-bit words per row of a 1-bit/pixel mask
+    int cap_raw, cap_kp;     // capacities per frame
+    int desc_bytes;          // bytes per descriptor as seen by the caller
+    int desc_words;          // 32-bit words per descriptor row in HBM (zero padded)
+    int qcap;                // segment-queue capacity (sort)
+    size_t frame_bytes;      // rows * pitch
+    uint8_t* img;            // [F][rows][pitch]     input frames
+    uint8_t* blur;           // [F][rows][pitch]     5x5 gaussian of the frame
+    uint32_t* mask;          // [F][rows][mwords]    FAST corner bitmask
+    uint32_t* raw_xy;        // [F][cap_raw]         (y << 16) | x, raster order
+    uint32_t* keys;          // [F][cap_raw]         (score << 20) | raster index; sorted in place
+    uint32_t* sort_scratch;  // [F][scratch_words]   L/R stop lists, segment queues, boundary bitmap
+    size_t scratch_words;
+    uint32_t* nms_bitmap;    // [F][rows][mwords]    suppression bitmap when it does not fit in smem
+    int* n_raw;              // [F]
+    slamcu_keypoint* kps;    // [F][cap_kp]
+    int* n_kp;               // [F]
+    uint32_t* desc;          // [F][cap_kp][desc_words]
+    uint32_t* desc_or;       // [F][desc_words]      OR of all descriptors of the frame
+    int4* cand;              // [F][cap_kp]          per-query {bestIdx, bestDist, secondDist, secondIdx}
+    slamcu_dmatch* matches;   // [F][cap_kp]          pair (f, f+1)
+    int* n_match;            // [F]
+    int* status;             // [F]
+};
+
+struct DetParams {
+    int thr, arc, nms, window, patch, pairs, n_pattern;
+    double blur_w[25];
+};
+
+struct MatchParams {
+    int filter, good, use_ratio;
+    float ratio;
+};
+
+// ---- launchers (each returns the number of kernels it enqueued) --------------------------------
+int launch_fast_corners(const SeqView& s, int first, int n, const DetParams& p, cudaStream_t st);
+int launch_sort_nms(const SeqView& s, int first, int n, const DetParams& p, int smem_optin, cudaStream_t st);
+int launch_raster_keypoints(const SeqView& s, int first, int n, bool scored, cudaStream_t st);
+int launch_blur(const SeqView& s, int first, int n, const DetParams& p, cudaStream_t st);
+int launch_describe(const SeqView& s, int first, int n, const DetParams& p, const int* d_pattern, cudaStream_t st);
+// generic matcher: nq x nt descriptors, optional keypoints; pair p: query = base + p*stride
+struct MatchJob {
+    const uint32_t* dq; const uint32_t* dt;           // descriptor rows (desc_words words each)
+    const slamcu_keypoint* kq; const slamcu_keypoint* kt;  // may be null
+    const int* nq; const int* nt;                      // device counts (one per pair, strided)
+    const uint32_t* orq; const uint32_t* ort;          // per-set OR masks (may be null)
+    int4* cand; slamcu_dmatch* matches; int* n_match; int* status;
+    size_t desc_pair_stride;   // words between consecutive pairs' descriptor blocks
+    size_t kp_pair_stride;     // keypoints between consecutive pairs
+    int count_stride;          // ints between consecutive pairs' counts
+    size_t cand_pair_stride;   // entries between pairs in cand / matches
+    int or_stride;
+    int desc_words, max_q, cap_out;
+};
+// sort_keys: [n_pairs][cand_pair_stride] 64-bit scratch for the top-K / sort stage
+int launch_match(const MatchJob& job, int n_pairs, const MatchParams& p, bool emit_matches, int with_kp,
+                 unsigned long long* sort_keys, cudaStream_t st);
+
+int launch_bgr2gray(const uint8_t* bgr, int rows, int cols, int stride, uint8_t* gray, int gstride, cudaStream_t st);
+struct CamParams { double fx, fy, cx, cy, k1, k2, p1, p2; };
+int launch_undistort_map(int rows, int cols, const CamParams& cam, int* map, cudaStream_t st);
+int launch_remap(const uint8_t* gray, int rows, int cols, int stride, const int* map, uint8_t* out_u8, double* out_f64,
+                 cudaStream_t st);
+int launch_ransac_score(const double* models9, int n_models, const double* x1, const double* x2, int n, double thr2,
+                        int* counts, uint8_t* masks, cudaStream_t st);
+
+__device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ unsigned lanemask_lt() {
+    unsigned m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+}  // namespace slamcu

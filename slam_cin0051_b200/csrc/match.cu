@@ -1,0 +1,250 @@
+// match.cu -- FeatureMatcher (rows A10-A13 of SURVEY.md section 8a; B9 reuses the k=2 search).
+//
+//   match_kernel    : findBestMatchesHamming's double loop (feature_matcher.cpp:153-173) as a popc-tiled
+//                     all-pairs kernel on the integer pipe: one query per thread held in registers,
+//                     train descriptors (+ keypoint xy) staged through shared memory with 128-bit
+//                     loads and read back as warp-wide broadcasts, running top-2 per thread with the
+//                     reference's strict-< tie rule (lowest train index wins).  calculateHammingDistance
+//                     (common.hpp:40-50, byte table) == sum of __popc over 32-bit words.
+//                     The image-distance penalty (:161-170) uses the same IEEE float ops, no FMA.
+//   finalize_kernel : ratio test (:175-187), emission in query order, then filterAndSortMatches
+//                     (:191-204) with libstdc++'s std::partial_sort / std::sort permutation (exact.cuh).
+#include "common.cuh"
+#include "exact.cuh"
+
+namespace slamcu {
+
+namespace {
+
+constexpr int QT = 128;  // queries per block (one per thread)
+constexpr int TT = 128;  // train descriptors per shared-memory tile
+
+struct Top2 {
+    int best, second, bidx, sidx;
+};
+
+__device__ __forceinline__ void top2_update(Top2& t, int d, int j) {  // feature_matcher.cpp:132-141
+    if (d < t.best) {
+        t.second = t.best;
+        t.sidx = t.bidx;
+        t.best = d;
+        t.bidx = j;
+    } else if (d < t.second) {
+        t.second = d;
+        t.sidx = j;
+    }
+}
+
+__device__ __forceinline__ int penalise(int dist, float qx, float qy, float tx, float ty) {
+    // feature_matcher.cpp:162-169; MAX_JUMP_RADIUS = 500 (feature_matcher.hpp:12)
+    const float dx = qx - tx, dy = qy - ty;
+    const float id = sqrtf(dx * dx + dy * dy);
+    if (id > 500.0f) {
+        const float pen = 1.0f + (id / 500.0f);
+        dist = (int)((float)dist * pen);
+    }
+    return dist;
+}
+
+// W = descriptor words handled by the unrolled path (8 = 256 bits); W = 0 -> generic loop.
+template <int W>
+__global__ void __launch_bounds__(QT) match_kernel(MatchJob job, int with_kp) {
+    extern __shared__ __align__(16) uint32_t smem[];
+    const int pair = blockIdx.y;
+    const int nq = job.nq[(size_t)pair * job.count_stride];
+    const int nt = job.nt[(size_t)pair * job.count_stride];
+    const int q0 = blockIdx.x * QT;
+    if (q0 >= nq || nt <= 0) return;
+    const int dw = job.desc_words;
+    const uint32_t* dq = job.dq + (size_t)pair * job.desc_pair_stride;
+    const uint32_t* dt = job.dt + (size_t)pair * job.desc_pair_stride;
+    const slamcu_keypoint* kq = with_kp ? job.kq + (size_t)pair * job.kp_pair_stride : nullptr;
+    const slamcu_keypoint* kt = with_kp ? job.kt + (size_t)pair * job.kp_pair_stride : nullptr;
+    uint32_t* tile = smem;                                     // [TT][dw]
+    float2* txy = reinterpret_cast<float2*>(smem + TT * dw);   // [TT]
+
+    // words that can be non-zero in either set (XOR of all-zero words contributes nothing)
+    int wmax = dw;
+    if (job.orq && job.ort) {
+        const uint32_t* oq = job.orq + (size_t)pair * job.or_stride;
+        const uint32_t* ot = job.ort + (size_t)pair * job.or_stride;
+        while (wmax > 1 && (oq[wmax - 1] | ot[wmax - 1]) == 0u) wmax--;
+    }
+
+    const int q = q0 + threadIdx.x;
+    const bool qok = q < nq;
+    uint32_t qd[W > 0 ? W : 1];
+    if (W > 0) {
+#pragma unroll
+        for (int w = 0; w < W; w++) qd[w] = qok ? dq[(size_t)q * dw + w] : 0u;
+    }
+    float qx = 0.f, qy = 0.f;
+    if (with_kp && qok) {
+        qx = kq[q].x;
+        qy = kq[q].y;
+    }
+    Top2 t{INT_MAX, INT_MAX, -1, -1};
+
+    for (int t0 = 0; t0 < nt; t0 += TT) {
+        const int cnt = min(TT, nt - t0);
+        __syncthreads();
+        if ((dw & 3) == 0) {
+            const uint4* src = reinterpret_cast<const uint4*>(dt + (size_t)t0 * dw);
+            uint4* dst = reinterpret_cast<uint4*>(tile);
+            for (int v = threadIdx.x; v < cnt * (dw >> 2); v += QT) dst[v] = __ldg(src + v);
+        } else {
+            for (int v = threadIdx.x; v < cnt * dw; v += QT) tile[v] = __ldg(dt + (size_t)t0 * dw + v);
+        }
+        if (with_kp)
+            for (int v = threadIdx.x; v < cnt; v += QT) txy[v] = make_float2(kt[t0 + v].x, kt[t0 + v].y);
+        __syncthreads();
+        if (!qok) continue;
+        if (W == 8 && wmax <= 2) {
+            for (int j = 0; j < cnt; j++) {
+                const uint2 a = *reinterpret_cast<const uint2*>(tile + j * 8);
+                int d = __popc(qd[0] ^ a.x) + __popc(qd[W > 1 ? 1 : 0] ^ a.y);
+                if (with_kp) d = penalise(d, qx, qy, txy[j].x, txy[j].y);
+                top2_update(t, d, t0 + j);
+            }
+        } else if (W == 8) {
+#pragma unroll 2
+            for (int j = 0; j < cnt; j++) {
+                const uint4 a = *reinterpret_cast<const uint4*>(tile + j * 8);
+                const uint4 b = *reinterpret_cast<const uint4*>(tile + j * 8 + 4);
+                int d = __popc(qd[0] ^ a.x) + __popc(qd[W > 1 ? 1 : 0] ^ a.y) + __popc(qd[W > 2 ? 2 : 0] ^ a.z) +
+                        __popc(qd[W > 3 ? 3 : 0] ^ a.w) + __popc(qd[W > 4 ? 4 : 0] ^ b.x) +
+                        __popc(qd[W > 5 ? 5 : 0] ^ b.y) + __popc(qd[W > 6 ? 6 : 0] ^ b.z) +
+                        __popc(qd[W > 7 ? 7 : 0] ^ b.w);
+                if (with_kp) d = penalise(d, qx, qy, txy[j].x, txy[j].y);
+                top2_update(t, d, t0 + j);
+            }
+        } else {
+            for (int j = 0; j < cnt; j++) {
+                int d = 0;
+                for (int w = 0; w < wmax; w++) d += __popc(dq[(size_t)q * dw + w] ^ tile[j * dw + w]);
+                if (with_kp) d = penalise(d, qx, qy, txy[j].x, txy[j].y);
+                top2_update(t, d, t0 + j);
+            }
+        }
+    }
+    if (qok) job.cand[(size_t)pair * job.cand_pair_stride + q] = make_int4(t.bidx, t.best, t.second, t.sidx);
+}
+
+struct MatchLess {  // sortPredicate: a.distance < b.distance (feature_matcher.cpp:192-194); key = dist<<32 | slot
+    __device__ __forceinline__ bool operator()(unsigned long long a, unsigned long long b) const {
+        return (uint32_t)(a >> 32) < (uint32_t)(b >> 32);
+    }
+};
+
+// One block per pair: ratio test, ordered emission, optional top-K / sort with libstdc++ tie order.
+__global__ void __launch_bounds__(256) finalize_kernel(MatchJob job, MatchParams p, unsigned long long* gkeys,
+                                                       int smem_cap) {
+    extern __shared__ __align__(16) unsigned long long skeys[];
+    __shared__ int warp_tot[8];
+    __shared__ int carry;
+    const int pair = blockIdx.x;
+    const int nq = job.nq[(size_t)pair * job.count_stride];
+    const int nt = job.nt[(size_t)pair * job.count_stride];
+    const int4* cand = job.cand + (size_t)pair * job.cand_pair_stride;
+    slamcu_dmatch* out = job.matches + (size_t)pair * job.cand_pair_stride;
+    unsigned long long* keys_g = gkeys + (size_t)pair * job.cand_pair_stride;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) carry = 0;
+    __syncthreads();
+    if (nq <= 0 || nt <= 0) {  // the reference throws std::invalid_argument here; the adapters do too
+        if (tid == 0) job.n_match[(size_t)pair * job.count_stride] = 0;
+        return;
+    }
+    const bool staged = p.filter != 0;  // with filtering, emit into a staging order first
+    for (int base = 0; base < nq; base += 256) {
+        const int q = base + tid;
+        bool good = false;
+        int4 c = make_int4(-1, 0, 0, -1);
+        if (q < nq) {
+            c = cand[q];
+            good = c.x != -1;
+            // Lowe ratio (feature_matcher.cpp:176-182); second == INT_MAX when nt == 1
+            if (p.use_ratio && (float)c.y >= p.ratio * (float)c.z) good = false;
+        }
+        const unsigned b = __ballot_sync(0xffffffffu, good);
+        const int wcount = __popc(b);
+        if (lane == 0) warp_tot[warp] = wcount;
+        __syncthreads();
+        int off = carry;
+        for (int w = 0; w < warp; w++) off += warp_tot[w];
+        const int pos = off + __popc(b & lanemask_lt());
+        if (good && pos < job.cap_out) {
+            if (staged) keys_g[pos] = ((unsigned long long)(uint32_t)c.y << 32) | (uint32_t)q;
+            else {
+                slamcu_dmatch m;
+                m.queryIdx = q;
+                m.trainIdx = c.x;
+                m.distance = (float)c.y;
+                out[pos] = m;
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int tot = 0;
+            for (int w = 0; w < 8; w++) tot += warp_tot[w];
+            carry += tot;
+        }
+        __syncthreads();
+    }
+    int n = carry;
+    if (n > job.cap_out) {
+        if (tid == 0) atomicOr(&job.status[(size_t)pair * job.count_stride], kStMatchOverflow);
+        n = job.cap_out;
+    }
+    if (!staged) {
+        if (tid == 0) job.n_match[(size_t)pair * job.count_stride] = n;
+        return;
+    }
+    // filterAndSortMatches: keys carry (distance, query index); the permutation is what matters.
+    const bool in_smem = n <= smem_cap;
+    unsigned long long* keys = in_smem ? skeys : keys_g;
+    if (in_smem) {
+        for (int i = tid; i < n; i += 256) skeys[i] = keys_g[i];
+    }
+    __syncthreads();
+    int n_out = n;
+    if (tid == 0) {
+        if (n > p.good) {
+            std_partial_sort(keys, p.good, n, MatchLess());
+        } else {
+            std_sort(keys, n, MatchLess());
+        }
+    }
+    if (n > p.good) n_out = p.good;
+    __syncthreads();
+    for (int i = tid; i < n_out; i += 256) {
+        const unsigned long long k = keys[i];
+        const int q = (int)(uint32_t)k;
+        slamcu_dmatch m;
+        m.queryIdx = q;
+        m.trainIdx = cand[q].x;
+        m.distance = (float)(uint32_t)(k >> 32);
+        out[i] = m;
+    }
+    if (tid == 0) job.n_match[(size_t)pair * job.count_stride] = n_out;
+}
+
+}  // namespace
+
+int launch_match(const MatchJob& job, int n_pairs, const MatchParams& p, bool emit_matches, int with_kp,
+                 unsigned long long* sort_keys, cudaStream_t st) {
+    if (n_pairs <= 0) return 0;
+    dim3 grid((job.max_q + QT - 1) / QT, n_pairs);
+    const size_t smem = (size_t)TT * job.desc_words * 4 + TT * sizeof(float2);
+    if (job.desc_words == 8) match_kernel<8><<<grid, QT, smem, st>>>(job, with_kp);
+    else match_kernel<0><<<grid, QT, smem, st>>>(job, with_kp);
+    int launches = 1;
+    if (emit_matches) {
+        const int smem_cap = 4096;
+        finalize_kernel<<<n_pairs, 256, smem_cap * sizeof(unsigned long long), st>>>(job, p, sort_keys, smem_cap);
+        launches++;
+    }
+    return launches;
+}
+
+}  // namespace slamcu

@@ -1,0 +1,69 @@
+// prep.cu -- image preparation (rows P1, P2 of SURVEY.md section 8a).
+//
+//   bgr2gray_kernel      : cv::cvtColor(BGR2GRAY) as called at preprocessor.cpp:136.  OpenCV's 8-bit path is
+//                          fixed point: (3735*B + 19235*G + 9798*R + 16384) >> 15.
+//   undistort_map_kernel : the per-camera part of Camera::undistortImage (common.hpp:146-162): forward
+//                          distortion of every output pixel in FP64 (no FMA), std::round, bounds test
+//                          -> int32 source index (-1 = outside).  Constant per camera, built once.
+//   remap_kernel         : the per-frame part (:159-170): gather; emits the u8 image the detector
+//                          consumes and/or the reference's value/255.0 double image.
+#include "common.cuh"
+
+namespace slamcu {
+namespace {
+
+__global__ void bgr2gray_kernel(const uint8_t* __restrict__ bgr, int rows, int cols, int stride,
+                                uint8_t* __restrict__ gray, int gstride) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= cols || y >= rows) return;
+    const uint8_t* p = bgr + (size_t)y * stride + 3 * x;
+    gray[(size_t)y * gstride + x] = (uint8_t)((3735u * p[0] + 19235u * p[1] + 9798u * p[2] + 16384u) >> 15);
+}
+
+__global__ void undistort_map_kernel(int rows, int cols, CamParams c, int* __restrict__ map) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+    if (j >= cols || i >= rows) return;
+    const double x = ((double)j - c.cx) / c.fx;
+    const double y = ((double)i - c.cy) / c.fy;
+    const double r = sqrt(x * x + y * y);
+    const double r2 = r * r;
+    const double r4 = pow(r, 4.0);
+    const double xd = x * (1 + c.k1 * r2 + c.k2 * r4) + 2 * c.p1 * x * y + c.p2 * (r2 + 2 * (x * x));
+    const double yd = y * (1 + c.k1 * r2 + c.k2 * r4) + 2 * c.p2 * x * y + c.p1 * (r2 + 2 * (y * y));
+    const double ud = c.fx * xd + c.cx;
+    const double vd = c.fy * yd + c.cy;
+    const int u = (int)round(ud), v = (int)round(vd);
+    map[(size_t)i * cols + j] = (u >= 0 && v >= 0 && u < cols && v < rows) ? v * cols + u : -1;
+}
+
+__global__ void remap_kernel(const uint8_t* __restrict__ gray, int rows, int cols, int stride,
+                             const int* __restrict__ map, uint8_t* __restrict__ out_u8, double* __restrict__ out_f64) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+    if (j >= cols || i >= rows) return;
+    const int src = map[(size_t)i * cols + j];
+    uint8_t v = 0;
+    if (src >= 0) v = gray[(size_t)(src / cols) * stride + (src % cols)];
+    if (out_u8) out_u8[(size_t)i * cols + j] = v;
+    if (out_f64) out_f64[(size_t)i * cols + j] = (src >= 0) ? (double)v / 255.0 : 0.0;
+}
+
+}  // namespace
+
+int launch_bgr2gray(const uint8_t* bgr, int rows, int cols, int stride, uint8_t* gray, int gstride, cudaStream_t st) {
+    dim3 grid((cols + 255) / 256, rows);
+    bgr2gray_kernel<<<grid, 256, 0, st>>>(bgr, rows, cols, stride, gray, gstride);
+    return 1;
+}
+int launch_undistort_map(int rows, int cols, const CamParams& cam, int* map, cudaStream_t st) {
+    dim3 grid((cols + 255) / 256, rows);
+    undistort_map_kernel<<<grid, 256, 0, st>>>(rows, cols, cam, map);
+    return 1;
+}
+int launch_remap(const uint8_t* gray, int rows, int cols, int stride, const int* map, uint8_t* out_u8, double* out_f64,
+                 cudaStream_t st) {
+    dim3 grid((cols + 255) / 256, rows);
+    remap_kernel<<<grid, 256, 0, st>>>(gray, rows, cols, stride, map, out_u8, out_f64);
+    return 1;
+}
+
+}  // namespace slamcu

@@ -1,0 +1,97 @@
+"""Device-resident frame sequences: the batched / asynchronous path of the frontend.
+
+A FrameSequence keeps up to `max_frames` frames of one size in HBM with every intermediate of the
+pipeline.  extract() is FeatureDetector::detectAndCompute on a range of frames; match_consecutive() is
+FeatureMatcher::match(frame f, frame f+1) for a range of pairs.  Frames are independent and pairs are
+independent, so a sequence shards across GPUs by contiguous frame range with no data-path collective.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from ._lib import KEYPOINT_DTYPE, MATCH_DTYPE, Context
+from .frontend import FeatureDetector, FeatureMatcher
+
+
+class FrameSequence:
+    def __init__(self, rows: int, cols: int, max_frames: int, desc_bytes: int = 32, max_raw_corners: int = 0,
+                 max_keypoints: int = 0, context: Context | None = None):
+        self.ctx = context or Context.default()
+        h = C.c_void_p()
+        self.ctx.check(self.ctx.lib.slamcu_sequence_create(self.ctx.handle, rows, cols, max_frames, max_raw_corners,
+                                                           max_keypoints, desc_bytes, C.byref(h)))
+        self.handle = h
+        self.rows, self.cols, self.max_frames, self.desc_bytes = rows, cols, max_frames, desc_bytes
+        dptr, pitch, fb = C.c_void_p(), C.c_int(), C.c_int64()
+        self.ctx.check(self.ctx.lib.slamcu_sequence_frames_device(h, C.byref(dptr), C.byref(pitch), C.byref(fb)))
+        self.device_ptr, self.pitch, self.frame_bytes = dptr.value, pitch.value, fb.value
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                self.ctx.lib.slamcu_sequence_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    def upload(self, frames: np.ndarray, first: int = 0):
+        """frames: (n, rows, cols) uint8 host array (pinned memory makes the copy asynchronous)."""
+        a = np.asarray(frames)
+        if a.ndim == 2:
+            a = a[None]
+        if a.dtype != np.uint8 or a.shape[1:] != (self.rows, self.cols) or not a.flags.c_contiguous:
+            raise RuntimeError("frames must be a C-contiguous (n, rows, cols) uint8 array")
+        self.ctx.check(self.ctx.lib.slamcu_sequence_upload(self.handle, first, a.shape[0], a.ctypes.data, self.cols))
+
+    def upload_ptr(self, host_ptr: int, n: int, first: int = 0):
+        self.ctx.check(self.ctx.lib.slamcu_sequence_upload(self.handle, first, n, C.c_void_p(host_ptr), self.cols))
+
+    def extract(self, detector: FeatureDetector, first: int = 0, n: int | None = None):
+        n = self.max_frames - first if n is None else n
+        self.ctx.check(self.ctx.lib.slamcu_sequence_extract(self.handle, detector.handle, first, n))
+
+    def match_consecutive(self, matcher: FeatureMatcher, first: int = 0, n_pairs: int | None = None,
+                          with_keypoints: bool = True):
+        n_pairs = self.max_frames - 1 - first if n_pairs is None else n_pairs
+        self.ctx.check(self.ctx.lib.slamcu_sequence_match(self.handle, matcher.handle, first, n_pairs,
+                                                          1 if with_keypoints else 0))
+
+    def counts(self, first: int = 0, n: int | None = None) -> np.ndarray:
+        """(n, 4) int32: n_keypoints, n_matches (pair f,f+1), n_raw_corners, status.  Synchronises."""
+        n = self.max_frames - first if n is None else n
+        out = np.zeros((n, 4), np.int32)
+        self.ctx.check(self.ctx.lib.slamcu_sequence_counts(self.handle, first, n, out.ctypes.data))
+        return out
+
+    def frame(self, f: int):
+        cap = 4096
+        while True:
+            kps = np.zeros(cap, KEYPOINT_DTYPE)
+            desc = np.zeros((cap, self.desc_bytes), np.uint8)
+            n = C.c_int(0)
+            st = self.ctx.lib.slamcu_sequence_frame(self.handle, f, kps.ctypes.data, desc.ctypes.data, self.desc_bytes,
+                                                    cap, C.byref(n))
+            if st == 4 and n.value > cap:
+                cap = n.value
+                continue
+            self.ctx.check(st)
+            return kps[: n.value].copy(), desc[: n.value].copy()
+
+    def matches(self, f: int) -> np.ndarray:
+        cap = 4096
+        while True:
+            out = np.zeros(cap, MATCH_DTYPE)
+            n = C.c_int(0)
+            st = self.ctx.lib.slamcu_sequence_matches(self.handle, f, out.ctypes.data, cap, C.byref(n))
+            if st == 4 and n.value > cap:
+                cap = n.value
+                continue
+            self.ctx.check(st)
+            return out[: n.value].copy()
+
+    def download_ptrs(self, first, n, kps_ptr=None, desc_ptr=None, matches_ptr=None, counts_ptr=None):
+        self.ctx.check(self.ctx.lib.slamcu_sequence_download(self.handle, first, n, C.c_void_p(kps_ptr or 0),
+                                                             C.c_void_p(desc_ptr or 0), C.c_void_p(matches_ptr or 0),
+                                                             C.c_void_p(counts_ptr or 0)))
