@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""bench.py -- frames/s of the SLAM frontend hot path (extract + consecutive-frame match) on B200.
+
+Contract (one JSON line on stdout from rank 0):
+  python bench.py --gpus N --steps K --warmup W            our CUDA path (this repo)
+  python bench.py --impl reference ...                     the reference's CPU algorithm on the host cores
+For N > 1 launch through torch.distributed.run (one rank per GPU, NCCL).
+
+A "step" is one pass of the hot path over one batch of `--frames` synthetic frames per GPU:
+detectAndCompute on every frame, then match(f, f+1) with keypoints for every consecutive pair.
+Workload = BASELINE.json configs[1] shape: KITTI-shape synthetic grayscale 1241x376.
+
+  value    : whole-job frames/s with the frames already resident in HBM (device-timed, max over ranks)
+  e2e      : same metric through the public host API: pinned host frames -> H2D -> extract -> match ->
+             D2H of keypoints, descriptors, matches and counts, every step inside the timed region
+  roofline : dominant kernel of the step, per-launch duration from CUDA events recorded on the
+             launching stream inside the timed region (slamcu_profile_*), against MEASURED_PEAKS.json
+             (HBM-bound kernels) or the popc ceiling measured in this run (the matcher)
+  cpu_baseline : the CPU oracle (oracle/ref_frontend.cpp, a port of the reference) on a bounded sample
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ROWS, COLS = 376, 1241
+GRID_PITCH = 14  # synthetic scene density; the achieved keypoint count is reported
+METRIC = "frames/s ORB extract+match @1241x376, 2k kp"
+UNIT = "frames/s"
+WORKLOAD = "KITTI-shape synthetic grayscale sequence 1241x376 (BASELINE.json configs[1])"
+
+
+def make_frames(n, seed):
+    from slam_cin0051_b200.synth import make_sequence
+    out = np.empty((n, ROWS, COLS), np.uint8)
+    done, g = 0, 0
+    while done < n:  # a new scene every 16 frames (the crop offsets have period 16)
+        m = min(16, n - done)
+        out[done:done + m] = make_sequence(ROWS, COLS, m, GRID_PITCH, seed=1000 * seed + g)
+        done += m
+        g += 1
+    return out
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_reference_run(frames, threads):
+    from oracle import ref_oracle
+    ref_oracle.build()
+    sec, counts = ref_oracle.frontend_run(frames, with_kp=True, threads=threads)
+    return sec, counts
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return 0
+    threads = host_threads()
+    # bounded sample per step: ~0.15 s of single-core work per frame -> a few seconds per step
+    n = max(threads, min(args.frames, 4 * threads))
+    frames = make_frames(n, 0)
+    for _ in range(args.warmup):
+        cpu_reference_run(frames[: max(2, n // 4)], threads)
+    t = 0.0
+    for _ in range(args.steps):
+        sec, counts = cpu_reference_run(frames, threads)
+        t += sec
+    value = n * args.steps / t
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "mode": "reference algorithm (FAST-12 + SAD NMS + BRIEF + BF Hamming)",
+                   "frames_per_step": n, "keypoints_per_frame_mean": float(counts[:, 0].mean())},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{n} frames/step x {args.steps} steps, frame-parallel std::thread pool, oracle/ref_frontend.cpp (g++ -O2)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(gpu_index)], stdout=self.tmp, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        self.tmp.flush()
+        rows = [l.strip().split(", ") for l in open(self.tmp.name) if l.strip()]
+        os.unlink(self.tmp.name)
+        sm, mx, reasons = [], [], set()
+        for r in rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.strip().lower() == "active":
+                    reasons.add(name)
+        if sm:
+            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return out
+
+
+def kernel_model(name, frames, px, pitch_px, n_raw, n_kp, cmp_per_step):
+    """Algorithmic work per launch (DESIGN.md section 'Kernels'): bytes for HBM-bound kernels, comparisons for the matcher."""
+    mask = px / 8
+    table = {
+        "fast_mask": ("hbm", frames * (px + mask)),
+        "corner_list": ("hbm", frames * (mask + 17 * n_raw + 8 * n_raw)),
+        "sort": ("hbm", frames * (8 * n_raw)),
+        "nms": ("hbm", frames * (8 * n_raw + 20 * n_kp)),
+        "blur5": ("hbm", frames * (2 * px)),
+        "describe": ("hbm", frames * (px + 52 * n_kp)),
+        "desc_or": ("hbm", frames * (32 * n_kp)),
+        "match": ("popc", cmp_per_step),
+        "match_finalize": ("hbm", frames * (16 * n_kp + 12 * 20)),
+    }
+    return table.get(name, ("hbm", 0.0))
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+
+    import slam_cin0051_b200 as S
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: this framework has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    B = args.frames
+    ctx = S.Context(local_rank)
+    stream = torch.cuda.Stream()  # a real (non-null) stream shared by torch's events and the library's launches
+    torch.cuda.set_stream(stream)
+    ctx.set_stream(stream.cuda_stream)
+    data = os.path.join(ROOT, "test", "data")
+    det = S.FeatureDetector(os.path.join(data, "feature_detector.yml"), ctx)
+    mat = S.FeatureMatcher(os.path.join(data, "feature_matcher.yml"), ctx)
+    max_kp = args.max_keypoints
+    seq = S.FrameSequence(ROWS, COLS, B, desc_bytes=det.descriptor_bytes, max_keypoints=max_kp, context=ctx)
+
+    frames_np = make_frames(B, rank)
+    host_frames = torch.empty((B, ROWS, COLS), dtype=torch.uint8, pin_memory=True)
+    host_frames.numpy()[:] = frames_np
+    # pinned result buffers for the end-to-end leg
+    h_kps = torch.empty((B, max_kp, 5), dtype=torch.float32, pin_memory=True)
+    h_desc = torch.empty((B, max_kp, det.descriptor_bytes), dtype=torch.uint8, pin_memory=True)
+    h_matches = torch.empty((B, max_kp, 3), dtype=torch.int32, pin_memory=True)
+    h_counts = torch.empty((B, 4), dtype=torch.int32, pin_memory=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def step_resident():
+        seq.extract(det, 0, B)
+        seq.match_consecutive(mat, 0, B - 1, with_keypoints=True)
+
+    def step_e2e():
+        seq.upload_ptr(host_frames.data_ptr(), B)
+        seq.extract(det, 0, B)
+        seq.match_consecutive(mat, 0, B - 1, with_keypoints=True)
+        # results a caller of detectAndCompute/match receives: counts first, then only the matches that
+        # exist (GoodMatchesCount per pair) and the keypoint / descriptor blocks
+        seq.download_ptrs(0, B, h_kps.data_ptr(), h_desc.data_ptr(), None, h_counts.data_ptr())
+        seq.download_ptrs(0, B, None, None, h_matches.data_ptr(), None)
+        ctx.synchronize()
+        return int(h_counts[:, 0].sum()), int(h_counts[:, 1].sum())
+
+    seq.upload_ptr(host_frames.data_ptr(), B)
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    ctx.synchronize()
+    counts = seq.counts()
+    if (counts[:, 3] != 0).any():
+        raise RuntimeError(f"device list overflow (status bits {np.unique(counts[:, 3])}); raise capacities")
+    n_kp_mean = float(counts[:, 0].mean())
+    n_raw_mean = float(counts[:, 2].mean())
+    cmp_per_step = float((counts[:-1, 0].astype(np.int64) * counts[1:, 0].astype(np.int64)).sum())
+
+    # ---- timed region: resident inputs ----
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    launches0 = ctx.launch_count
+    ctx.profile_enable(True)
+    barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_resident()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    prof = ctx.profile_read()
+    ctx.profile_enable(False)
+    launches = ctx.launch_count - launches0
+    clocks = sampler.stop() if sampler else None
+
+    # ---- end-to-end leg (host buffers, copies inside the timed region) ----
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    tot = (0, 0)
+    for _ in range(args.steps):
+        tot = step_e2e()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    barrier()
+
+    t_res = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_res, op=dist.ReduceOp.MAX)
+        # the only inter-GPU traffic of the path: per-frame counts gathered over NCCL/NVLink
+        gathered = [torch.empty((B, 4), dtype=torch.int32, device="cuda") for _ in range(world)]
+        dist.all_gather(gathered, torch.from_numpy(counts).cuda())
+        n_kp_mean = float(torch.stack(gathered)[:, :, 0].float().mean().item())
+    ms, e2e_ms = float(t_res[0].item()), float(t_res[1].item())
+
+    if rank == 0:
+        value = world * B * args.steps / (ms * 1e-3)
+        e2e_value = world * B * args.steps / (e2e_ms * 1e-3)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        hbm_src = "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        gpopc = ctx.popc_peak()
+        px = ROWS * COLS
+        kernels = []
+        total_k_ms = sum(v[0] for v in prof.values()) or 1.0
+        for name, (kms, cnt) in sorted(prof.items(), key=lambda kv: -kv[1][0]):
+            bound, work = kernel_model(name, B, px, GRID_PITCH, n_raw_mean, n_kp_mean, cmp_per_step)
+            per_launch_ms = kms / max(cnt, 1)
+            if bound == "hbm":
+                ach = work / (per_launch_ms * 1e-3) / 1e9
+                kernels.append({"kernel": name, "bound": "hbm", "ms_per_launch": per_launch_ms, "share": kms / total_k_ms,
+                                "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak})
+            else:
+                ach = work / (per_launch_ms * 1e-3) / 1e9
+                peak = gpopc / 8.0
+                kernels.append({"kernel": name, "bound": "popc", "ms_per_launch": per_launch_ms, "share": kms / total_k_ms,
+                                "achieved": ach, "peak": peak, "unit": "Gcmp/s (256-bit)", "frac": ach / peak})
+        top = kernels[0] if kernels else {}
+        roofline = {"kernel": top.get("kernel"), "bound": top.get("bound"), "achieved": top.get("achieved"),
+                    "peak": top.get("peak"), "unit": top.get("unit"), "frac": top.get("frac"), "traffic": None,
+                    "peak_source": hbm_src if top.get("bound") == "hbm" else f"popc microbenchmark in this run: {gpopc:.0f} Gpopc/s / 8 popc per 256-bit comparison",
+                    "share_of_step": top.get("share")}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "mode": "reference algorithm (FAST-12 + SAD NMS + BRIEF + BF Hamming with keypoint penalty)",
+                       "frames_per_step_per_gpu": B, "pairs_per_step_per_gpu": B - 1, "keypoints_per_frame_mean": n_kp_mean,
+                       "raw_corners_per_frame_mean": n_raw_mean, "parallelism": f"frame-range sharding x{world}",
+                       "l2": f"inputs larger than L2: {B * ROWS * COLS / 1e6:.0f} MB of frames per step vs 126 MB L2"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(B * ROWS * COLS),
+                    "d2h_bytes_per_step": int(h_kps.nbytes + h_desc.nbytes + h_matches.nbytes + h_counts.nbytes),
+                    "ms_per_step": e2e_ms / args.steps, "keypoints_last_step": tot[0], "matches_last_step": tot[1]},
+            "gpu_launches": int(launches),
+            "roofline": roofline,
+            "kernels": kernels,
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            threads = host_threads()
+            n_s = max(8, min(B, 2 * threads))
+            sec, c_cpu = cpu_reference_run(frames_np[:n_s], threads)
+            sec1, _ = cpu_reference_run(frames_np[:4], 1)
+            same = bool((c_cpu[:, 0] == counts[:n_s, 0]).all() and (c_cpu[:-1, 1] == counts[:n_s - 1, 1]).all())
+            line["cpu_baseline"] = {"value": n_s / sec, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": f"first {n_s} frames of the same batch, frame-parallel over {threads} host threads",
+                                    "single_thread_value": 4 / sec1, "counts_match_gpu": same}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames", type=int, default=512, help="frames per GPU per step")
+    ap.add_argument("--max-keypoints", type=int, default=2560)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+    return run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

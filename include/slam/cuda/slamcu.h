@@ -109,6 +109,13 @@ void* slamcu_get_stream(slamcu_context* ctx);
 int slamcu_synchronize(slamcu_context* ctx);
 /* number of kernels this library launched on the context since creation (bench.py gpu_launches) */
 int64_t slamcu_launch_count(const slamcu_context* ctx);
+/* Per-kernel device timing: when enabled, every kernel launch on the context is bracketed by CUDA
+ * events on the launching stream.  slamcu_profile_read(index) synchronises and returns the accumulated
+ * milliseconds and launch count of the index-th kernel name (SLAMCU_INVALID_ARGUMENT past the end). */
+/* Measured POPC issue ceiling of the device (G popc/s): the matcher's roofline denominator. */
+int slamcu_popc_peak(slamcu_context* ctx, double* gpopc_per_s);
+int slamcu_profile_enable(slamcu_context* ctx, int on);
+int slamcu_profile_read(slamcu_context* ctx, int index, char* name, int name_cap, double* total_ms, int64_t* launches);
 
 /* ---- FeatureDetector (feature_detector.hpp:53,114-135) ---------------------------------------- */
 /* Constructor-time host tables, produced with the same host-library calls as the reference:

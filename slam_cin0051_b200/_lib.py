@@ -47,6 +47,9 @@ SYMBOLS = {
     "slamcu_get_stream": (_vp, [_vp]),
     "slamcu_synchronize": (_i, [_vp]),
     "slamcu_launch_count": (C.c_int64, [_vp]),
+    "slamcu_popc_peak": (_i, [_vp, C.POINTER(C.c_double)]),
+    "slamcu_profile_enable": (_i, [_vp, _i]),
+    "slamcu_profile_read": (_i, [_vp, _i, C.c_char_p, _i, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "slamcu_default_brief_pattern": (_i, [_i, _i, _vp, _i, _ip]),
     "slamcu_default_blur_weights": (_i, [_vp]),
     "slamcu_detector_create": (_i, [_vp, C.POINTER(DetectorConfig), C.POINTER(_vp)]),
@@ -153,6 +156,26 @@ class Context:
     @property
     def launch_count(self) -> int:
         return int(self.lib.slamcu_launch_count(self.handle))
+
+    def popc_peak(self) -> float:
+        v = C.c_double(0)
+        raise_for(self.lib.slamcu_popc_peak(self.handle, C.byref(v)), self.handle)
+        return v.value
+
+    def profile_enable(self, on: bool = True):
+        raise_for(self.lib.slamcu_profile_enable(self.handle, 1 if on else 0), self.handle)
+
+    def profile_read(self) -> dict:
+        """{kernel name: (total_ms, launches)} accumulated since profile_enable()."""
+        out, i = {}, 0
+        while True:
+            name = C.create_string_buffer(64)
+            ms, cnt = C.c_double(0), C.c_int64(0)
+            if self.lib.slamcu_profile_read(self.handle, i, name, 64, C.byref(ms), C.byref(cnt)) != OK:
+                break
+            out[name.value.decode()] = (ms.value, cnt.value)
+            i += 1
+        return out
 
     def check(self, status, what=""):
         raise_for(status, self.handle, what)

@@ -16,9 +16,52 @@ using namespace slamcu;
 namespace slamcu {
 void init_sortnms_attributes(int smem_optin);
 int launch_desc_or(const uint32_t* desc, const int* n_dev, int desc_words, uint32_t* out, cudaStream_t st);
+long long launch_popc_peak(unsigned* scratch, int blocks, int iters, cudaStream_t st);
 }
 
+namespace slamcu {
+thread_local Profiler* g_prof = nullptr;
+}
+
+namespace {
+struct EventProfiler : Profiler {
+    struct Rec { const char* name; cudaEvent_t a, b; };
+    struct Acc { const char* name; double ms; long long count; };
+    std::vector<Rec> pending;
+    std::vector<cudaEvent_t> pool;
+    std::vector<Acc> acc;
+    cudaEvent_t cur_a = nullptr;
+    const char* cur_name = nullptr;
+    cudaEvent_t get() {
+        if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+        cudaEvent_t e; cudaEventCreate(&e); return e;
+    }
+    void begin(const char* name, cudaStream_t st) override {
+        cur_a = get(); cur_name = name; cudaEventRecord(cur_a, st);
+    }
+    void end(cudaStream_t st) override {
+        cudaEvent_t b = get(); cudaEventRecord(b, st);
+        pending.push_back({cur_name, cur_a, b});
+    }
+    void collect() {  // caller has synchronised the stream
+        for (auto& r : pending) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, r.a, r.b);
+            bool found = false;
+            for (auto& a : acc) if (!strcmp(a.name, r.name)) { a.ms += ms; a.count++; found = true; break; }
+            if (!found) acc.push_back({r.name, ms, 1});
+            pool.push_back(r.a); pool.push_back(r.b);
+        }
+        pending.clear();
+    }
+    void reset() { collect(); acc.clear(); }
+    ~EventProfiler() { for (auto e : pool) cudaEventDestroy(e); }
+};
+}  // namespace
+
 struct slamcu_context {
+    EventProfiler prof;
+    bool profiling = false;
     int device = 0;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
@@ -188,6 +231,53 @@ int slamcu_synchronize(slamcu_context* ctx) {
 }
 int64_t slamcu_launch_count(const slamcu_context* ctx) { return ctx ? ctx->launches : 0; }
 
+int slamcu_popc_peak(slamcu_context* ctx, double* gpopc_per_s) {
+    if (!ctx || !gpopc_per_s) return SLAMCU_INVALID_ARGUMENT;
+    CU(ctx, cudaSetDevice(ctx->device));
+    int rc = ensure_scratch(ctx, 4096);
+    if (rc != SLAMCU_OK) return rc;
+    int sms = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+    cudaEvent_t a, b;
+    CU(ctx, cudaEventCreate(&a));
+    CU(ctx, cudaEventCreate(&b));
+    double best = 0.0;
+    for (int rep = 0; rep < 5; rep++) {
+        CU(ctx, cudaEventRecord(a, ctx->stream));
+        const long long ops = launch_popc_peak(static_cast<unsigned*>(ctx->scratch), sms * 8, 1 << 14, ctx->stream);
+        ctx->launches++;
+        CU(ctx, cudaEventRecord(b, ctx->stream));
+        CU(ctx, cudaEventSynchronize(b));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, a, b);
+        if (ms > 0.f) best = std::max(best, (double)ops / (ms * 1e-3) / 1e9);
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    *gpopc_per_s = best;
+    return check_launch(ctx, "popc_peak");
+}
+
+int slamcu_profile_enable(slamcu_context* ctx, int on) {
+    if (!ctx) return SLAMCU_INVALID_ARGUMENT;
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->prof.reset();
+    ctx->profiling = on != 0;
+    return SLAMCU_OK;
+}
+
+int slamcu_profile_read(slamcu_context* ctx, int index, char* name, int name_cap, double* total_ms, int64_t* launches) {
+    if (!ctx) return SLAMCU_INVALID_ARGUMENT;
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->prof.collect();
+    if (index < 0 || index >= (int)ctx->prof.acc.size()) return SLAMCU_INVALID_ARGUMENT;  // end of list
+    const auto& a = ctx->prof.acc[index];
+    if (name && name_cap > 0) { strncpy(name, a.name, name_cap - 1); name[name_cap - 1] = 0; }
+    if (total_ms) *total_ms = a.ms;
+    if (launches) *launches = a.count;
+    return SLAMCU_OK;
+}
+
 /* ---------------------------------------------------------------------------------------------- */
 /* sequences                                                                                       */
 /* ---------------------------------------------------------------------------------------------- */
@@ -210,15 +300,16 @@ int slamcu_sequence_create(slamcu_context* ctx, int rows, int cols, int max_fram
     v.mwords = (cols + 31) / 32;
     const long long px = (long long)rows * cols;
     if (max_raw <= 0) max_raw = (int)std::min<long long>(std::max<long long>(px / 20, 8192), kMaxRawCap);
+    max_raw = round_up(max_raw, 32);  // keeps every per-frame sub-array 16-byte aligned
     if (max_raw > kMaxRawCap) max_raw = kMaxRawCap;
     if (max_kp <= 0) max_kp = (int)std::min<long long>(std::max<long long>(px / 100, 1024), 65536);
     v.cap_raw = max_raw;
     v.cap_kp = max_kp;
     v.desc_bytes = desc_bytes;
     v.desc_words = (desc_bytes + 3) / 4;
-    v.qcap = max_raw / 16 + 2;
+    v.qcap = round_up(max_raw / 16 + 2, 4);
     v.frame_bytes = (size_t)rows * v.pitch;
-    v.scratch_words = 2 * (size_t)max_raw + 4 * (size_t)v.qcap + (size_t)max_raw / 32 + 2;
+    v.scratch_words = (2 * (size_t)max_raw + 4 * (size_t)v.qcap + (size_t)max_raw / 32 + 2 + 3) / 4 * 4;
     const size_t F = (size_t)max_frames;
     int rc = SLAMCU_OK;
     auto A = [&](auto** p, size_t count, bool zero) {
@@ -280,8 +371,14 @@ int slamcu_sequence_frames_device(slamcu_sequence* s, void** dptr, int* pitch, i
     return SLAMCU_OK;
 }
 
+struct ProfGuard {
+    explicit ProfGuard(slamcu_context* ctx) { slamcu::g_prof = ctx->profiling ? &ctx->prof : nullptr; }
+    ~ProfGuard() { slamcu::g_prof = nullptr; }
+};
+
 static int seq_detect(slamcu_sequence* s, slamcu_detector* det, int first, int n, bool raw_probe) {
     slamcu_context* ctx = s->ctx;
+    ProfGuard pg(ctx);
     ctx->launches += launch_fast_corners(s->v, first, n, det->p, ctx->stream);
     if (raw_probe) ctx->launches += launch_raster_keypoints(s->v, first, n, true, ctx->stream);
     else if (det->p.nms) ctx->launches += launch_sort_nms(s->v, first, n, det->p, ctx->smem_optin, ctx->stream);
@@ -291,6 +388,7 @@ static int seq_detect(slamcu_sequence* s, slamcu_detector* det, int first, int n
 
 static int seq_compute(slamcu_sequence* s, slamcu_detector* det, int first, int n) {
     slamcu_context* ctx = s->ctx;
+    ProfGuard pg(ctx);
     ctx->launches += launch_blur(s->v, first, n, det->p, ctx->stream);
     ctx->launches += launch_describe(s->v, first, n, det->p, det->d_pattern, ctx->stream);
     return check_launch(ctx, "compute kernels");
@@ -317,6 +415,7 @@ int slamcu_sequence_match(slamcu_sequence* s, slamcu_matcher* m, int first, int 
     if (m->distance_type != SLAMCU_DISTANCE_HAMMING)
         return fail(ctx, SLAMCU_UNSUPPORTED, "L2 distance requires float descriptors. Use the float overload.");
     if (n_pairs == 0) return SLAMCU_OK;
+    ProfGuard pg(ctx);
     const SeqView& v = s->v;
     MatchJob j{};
     const size_t dstride = (size_t)v.cap_kp * v.desc_words;
@@ -734,6 +833,7 @@ static int match_common(slamcu_matcher* m, const uint8_t* d1, int n1, int width1
     if (with_kp && (nkp1 < n1 || nkp2 < n2))
         return fail(ctx, SLAMCU_SIZE_MISMATCH, "fewer keypoints than descriptors");
     CU(ctx, cudaSetDevice(ctx->device));
+    ProfGuard pg(ctx);
     const int words = (width1 + 3) / 4;
     int rc = matcher_workspace(m, n1, n2, words);
     if (rc != SLAMCU_OK) return rc;

@@ -85,6 +85,19 @@ int launch_remap(const uint8_t* gray, int rows, int cols, int stride, const int*
 int launch_ransac_score(const double* models9, int n_models, const double* x1, const double* x2, int n, double thr2,
                         int* counts, uint8_t* masks, cudaStream_t st);
 
+// ---- optional per-kernel timing (CUDA events on the launching stream; bench.py's roofline input) ----
+struct Profiler {
+    virtual void begin(const char* name, cudaStream_t st) = 0;
+    virtual void end(cudaStream_t st) = 0;
+};
+extern thread_local Profiler* g_prof;  // set by the API entry points while profiling is enabled
+#define SLAM_KERNEL(name, st, ...)              \
+    do {                                         \
+        if (slamcu::g_prof) slamcu::g_prof->begin(name, st); \
+        __VA_ARGS__;                             \
+        if (slamcu::g_prof) slamcu::g_prof->end(st);         \
+    } while (0)
+
 __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31; }
 __device__ __forceinline__ unsigned lanemask_lt() {
     unsigned m;

@@ -180,15 +180,17 @@ int launch_blur(const SeqView& s, int first, int n, const DetParams& p, cudaStre
     BlurW bw;
     for (int i = 0; i < 25; i++) bw.w[i] = p.blur_w[i];
     dim3 grid((s.cols + BW - 1) / BW, (s.rows + BH - 1) / BH, n);
-    blur5_kernel<<<grid, 256, 0, st>>>(s, first, bw);
+    SLAM_KERNEL("blur5", st, blur5_kernel<<<grid, 256, 0, st>>>(s, first, bw));
     return 1;
 }
 
 int launch_describe(const SeqView& s, int first, int n, const DetParams& p, const int* d_pattern, cudaStream_t st) {
     dim3 grid((s.cap_kp + 3) / 4, n);
-    describe_kernel<<<grid, 128, 0, st>>>(s, first, p.patch, p.n_pattern, d_pattern);
-    desc_or_kernel<<<n, 256, 0, st>>>(s.desc + (size_t)first * s.cap_kp * s.desc_words, (size_t)s.cap_kp * s.desc_words,
-                                      s.n_kp + first, s.desc_words, s.desc_or + (size_t)first * s.desc_words);
+    SLAM_KERNEL("describe", st, describe_kernel<<<grid, 128, 0, st>>>(s, first, p.patch, p.n_pattern, d_pattern));
+    SLAM_KERNEL("desc_or", st,
+                desc_or_kernel<<<n, 256, 0, st>>>(s.desc + (size_t)first * s.cap_kp * s.desc_words,
+                                                  (size_t)s.cap_kp * s.desc_words, s.n_kp + first, s.desc_words,
+                                                  s.desc_or + (size_t)first * s.desc_words));
     return 2;
 }
 

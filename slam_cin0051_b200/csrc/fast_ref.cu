@@ -205,14 +205,14 @@ __global__ void raster_keypoints_kernel(SeqView s, int first, int scored) {
 
 int launch_fast_corners(const SeqView& s, int first, int n, const DetParams& p, cudaStream_t st) {
     dim3 grid((s.cols + TW - 1) / TW, (s.rows + TH - 1) / TH, n);
-    fast_mask_kernel<<<grid, 256, 0, st>>>(s, first, p.thr, p.arc);
-    corner_list_kernel<<<n, 256, (s.rows + 1) * sizeof(int), st>>>(s, first);
+    SLAM_KERNEL("fast_mask", st, fast_mask_kernel<<<grid, 256, 0, st>>>(s, first, p.thr, p.arc));
+    SLAM_KERNEL("corner_list", st, corner_list_kernel<<<n, 256, (s.rows + 1) * sizeof(int), st>>>(s, first));
     return 2;
 }
 
 int launch_raster_keypoints(const SeqView& s, int first, int n, bool scored, cudaStream_t st) {
     dim3 grid((s.cap_kp + 255) / 256, n);
-    raster_keypoints_kernel<<<grid, 256, 0, st>>>(s, first, scored ? 1 : 0);
+    SLAM_KERNEL("raster_keypoints", st, raster_keypoints_kernel<<<grid, 256, 0, st>>>(s, first, scored ? 1 : 0));
     return 1;
 }
 

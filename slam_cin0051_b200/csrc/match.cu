@@ -236,12 +236,12 @@ int launch_match(const MatchJob& job, int n_pairs, const MatchParams& p, bool em
     if (n_pairs <= 0) return 0;
     dim3 grid((job.max_q + QT - 1) / QT, n_pairs);
     const size_t smem = (size_t)TT * job.desc_words * 4 + TT * sizeof(float2);
-    if (job.desc_words == 8) match_kernel<8><<<grid, QT, smem, st>>>(job, with_kp);
-    else match_kernel<0><<<grid, QT, smem, st>>>(job, with_kp);
+    if (job.desc_words == 8) SLAM_KERNEL("match", st, match_kernel<8><<<grid, QT, smem, st>>>(job, with_kp));
+    else SLAM_KERNEL("match", st, match_kernel<0><<<grid, QT, smem, st>>>(job, with_kp));
     int launches = 1;
     if (emit_matches) {
         const int smem_cap = 4096;
-        finalize_kernel<<<n_pairs, 256, smem_cap * sizeof(unsigned long long), st>>>(job, p, sort_keys, smem_cap);
+        SLAM_KERNEL("match_finalize", st, finalize_kernel<<<n_pairs, 256, smem_cap * sizeof(unsigned long long), st>>>(job, p, sort_keys, smem_cap));
         launches++;
     }
     return launches;

@@ -312,10 +312,10 @@ int launch_sort_nms(const SeqView& s, int first, int n, const DetParams& p, int 
     // keys in shared memory when the frame's raw-corner count fits; else the same code runs on HBM
     int smem_keys = min(s.cap_raw, (smem_optin - 1024) / 4);
     size_t sort_smem = (size_t)smem_keys * 4;
-    sort_kernel<<<n, 256, sort_smem, st>>>(s, first, smem_keys);
+    SLAM_KERNEL("sort", st, sort_kernel<<<n, 256, sort_smem, st>>>(s, first, smem_keys));
     const size_t bm_bytes = (size_t)s.rows * s.mwords * 4;
     const int use_smem = bm_bytes <= (size_t)(smem_optin - 1024);
-    nms_kernel<<<n, 32, use_smem ? bm_bytes : 0, st>>>(s, first, p.window, use_smem);
+    SLAM_KERNEL("nms", st, nms_kernel<<<n, 32, use_smem ? bm_bytes : 0, st>>>(s, first, p.window, use_smem));
     return 2;
 }
 
