@@ -143,6 +143,16 @@ int slamcu_detect_and_compute(slamcu_detector* det, const uint8_t* image, int ro
  * raster-order FAST corners with their SAD score in `response` (feature_detector.cpp:56-68,190-203) */
 int slamcu_fast_corners(slamcu_detector* det, const uint8_t* image, int rows, int cols, int stride,
                         slamcu_keypoint* keypoints, int capacity, int* n_out);
+/* ORB mode only: pyramid level (cv::KeyPoint::octave) of every keypoint of the last single-frame call. */
+int slamcu_detector_last_octaves(slamcu_detector* det, int32_t* octaves, int capacity);
+/* ORB mode stage probes (parity tests): lists of the last single-frame call at one pyramid level.
+ * stage 0 = FAST-9 + 3x3 NMS + border filter survivors (value = FAST score), 1 = after retainBest(2*quota)
+ * (value = Harris response), 2 = after retainBest(quota).  xy[i] = (y << 16) | x in level coordinates. */
+int slamcu_orb_stage(slamcu_detector* det, int stage, int level, uint32_t* xy, float* value, int capacity, int* n_out);
+/* ORB mode: pyramid level `level` of the last single-frame call (blurred != 0: the 7x7 sigma=2 blurred copy the
+ * descriptors sample).  out may be NULL to query the size only. */
+int slamcu_orb_level_image(slamcu_detector* det, int level, int blurred, uint8_t* out, int out_stride, int* rows,
+                           int* cols);
 /* FeatureDetector::gaussianBlur(image, 5, 1.0) (feature_detector.cpp:315-364) */
 int slamcu_gaussian_blur(slamcu_detector* det, const uint8_t* image, int rows, int cols, int stride, uint8_t* out,
                          int out_stride);
@@ -182,6 +192,8 @@ int slamcu_sequence_counts(slamcu_sequence* seq, int first, int n, int32_t* coun
 /* D2H of one frame's keypoints + descriptors / one pair's matches; synchronises. */
 int slamcu_sequence_frame(slamcu_sequence* seq, int f, slamcu_keypoint* keypoints, uint8_t* descriptors,
                           int desc_stride, int capacity, int* n_out);
+/* ORB mode only: octaves of frame f's keypoints. */
+int slamcu_sequence_octaves(slamcu_sequence* seq, int f, int32_t* octaves, int capacity);
 int slamcu_sequence_matches(slamcu_sequence* seq, int f, slamcu_dmatch* matches, int capacity, int* n_out);
 /* Bulk asynchronous D2H of everything a consumer needs for frames [first, first+n): keypoints
  * [n][max_keypoints], descriptors [n][max_keypoints][desc_bytes], matches [n][max_keypoints],

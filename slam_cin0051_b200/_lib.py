@@ -58,6 +58,10 @@ SYMBOLS = {
     "slamcu_compute": (_i, [_vp, _u8p, _i, _i, _i, _vp, _i, _u8p, _i]),
     "slamcu_detect_and_compute": (_i, [_vp, _u8p, _i, _i, _i, _vp, _u8p, _i, _i, _ip]),
     "slamcu_fast_corners": (_i, [_vp, _u8p, _i, _i, _i, _vp, _i, _ip]),
+    "slamcu_detector_last_octaves": (_i, [_vp, _vp, _i]),
+    "slamcu_orb_stage": (_i, [_vp, _i, _i, _vp, _vp, _i, _ip]),
+    "slamcu_orb_level_image": (_i, [_vp, _i, _i, _u8p, _i, _ip, _ip]),
+    "slamcu_sequence_octaves": (_i, [_vp, _i, _vp, _i]),
     "slamcu_gaussian_blur": (_i, [_vp, _u8p, _i, _i, _i, _u8p, _i]),
     "slamcu_matcher_create": (_i, [_vp, C.POINTER(MatcherConfig), C.POINTER(_vp)]),
     "slamcu_matcher_destroy": (None, [_vp]),

@@ -10,13 +10,16 @@
 #include <vector>
 
 #include "common.cuh"
+#include "orb.cuh"
 
 using namespace slamcu;
 
 namespace slamcu {
 void init_sortnms_attributes(int smem_optin);
-int launch_desc_or(const uint32_t* desc, const int* n_dev, int desc_words, uint32_t* out, cudaStream_t st);
+int launch_desc_or(const uint32_t* desc, const int* n_dev, int desc_words, uint32_t* out, cudaStream_t st, int sets = 1,
+                   size_t set_stride = 0);
 long long launch_popc_peak(unsigned* scratch, int blocks, int iters, cudaStream_t st);
+void init_orb_attributes(int smem_optin);
 }
 
 namespace slamcu {
@@ -133,12 +136,21 @@ struct slamcu_sequence {
     unsigned long long* sort_keys = nullptr;  // [F][cap_kp]
     int* h_counts = nullptr;                  // pinned [F][4]
     std::vector<void*> owned;
+    // ORB-mode working set, allocated on first use and keyed by the detector parameters
+    bool has_orb = false;
+    OrbView orb{};
+    int orb_levels = 0, orb_features = 0, orb_fast = 0;
+    float orb_scale = 0.f;
+    std::vector<void*> orb_owned;
 };
 
 struct slamcu_detector {
     slamcu_context* ctx = nullptr;
     DetParams p{};
     int mode = 0;
+    int n_levels = 8, max_features = 2000, fast_threshold = 20;
+    float scale_factor = 1.2f;
+    int8_t* d_orb_pattern = nullptr;  // [512][2]
     int* d_pattern = nullptr;
     slamcu_sequence* one = nullptr;  // cached single-frame workspace
 };
@@ -202,6 +214,7 @@ int slamcu_create(int device_id, slamcu_context** out) {
     ctx->stream = ctx->own_stream;
     cudaDeviceGetAttribute(&ctx->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device_id);
     init_sortnms_attributes(ctx->smem_optin);
+    init_orb_attributes(ctx->smem_optin);
     *out = ctx;
     return SLAMCU_OK;
 }
@@ -348,6 +361,7 @@ void slamcu_sequence_destroy(slamcu_sequence* s) {
     cudaSetDevice(s->ctx->device);
     cudaStreamSynchronize(s->ctx->stream);
     for (void* p : s->owned) cudaFree(p);
+    for (void* p : s->orb_owned) cudaFree(p);
     if (s->h_counts) cudaFreeHost(s->h_counts);
     delete s;
 }
@@ -394,10 +408,153 @@ static int seq_compute(slamcu_sequence* s, slamcu_detector* det, int first, int 
     return check_launch(ctx, "compute kernels");
 }
 
+// INTER_LINEAR_EXACT coefficient tables (OpenCV resize.cpp bit-exact path): source index pair and the
+// 8.8 fixed-point weight of the second tap, computed in double exactly like OpenCV, per destination index.
+static void resize_tables(int dst, int src, std::vector<int>& i0, std::vector<int>& i1, std::vector<int>& a) {
+    i0.resize(dst);
+    i1.resize(dst);
+    a.resize(dst);
+    const double scale = 1.0 / ((double)dst / (double)src);
+    for (int d = 0; d < dst; d++) {
+        const double f = scale * (d + 0.5) - 0.5;
+        int i = (int)std::floor(f);
+        int w = (int)std::nearbyint((f - i) * 256.0);  // cvRound: half to even
+        int j = i + 1;
+        if (i < 0) { i = 0; j = 0; w = 0; }
+        if (i >= src - 1) { i = src - 1; j = src - 1; w = 0; }
+        i0[d] = i;
+        i1[d] = j;
+        a[d] = w;
+    }
+}
+
+static int seq_ensure_orb(slamcu_sequence* s, slamcu_detector* det) {
+    slamcu_context* ctx = s->ctx;
+    if (s->has_orb && s->orb_levels == det->n_levels && s->orb_features == det->max_features &&
+        s->orb_scale == det->scale_factor) {
+        s->orb.fast_threshold = det->fast_threshold;
+        s->orb.pattern = det->d_orb_pattern;
+        return SLAMCU_OK;
+    }
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    for (void* p : s->orb_owned) cudaFree(p);
+    s->orb_owned.clear();
+    s->has_orb = false;
+    OrbView& o = s->orb;
+    o = OrbView{};
+    const SeqView& v = s->v;
+    const int L = det->n_levels;
+    o.nlevels = L;
+    o.fast_threshold = det->fast_threshold;
+    o.pattern = det->d_orb_pattern;
+    // ORB_Impl: scale = (float)pow(scaleFactor, level); size = cvRound(dim / scale); quotas by geometric series
+    const double sf = (double)det->scale_factor;
+    const float factor = (float)(1.0 / sf);
+    float ndesired = det->max_features * (1 - factor) / (1 - (float)std::pow((double)factor, (double)L));
+    int sum = 0;
+    size_t pyr = 0, mw = 0, ct = 0;
+    for (int l = 0; l < L; l++) {
+        OrbLevel& lv = o.lv[l];
+        lv.scale = (float)std::pow(sf, (double)l);
+        lv.cols = (int)std::lrintf((float)v.cols / lv.scale);
+        lv.rows = (int)std::lrintf((float)v.rows / lv.scale);
+        if (lv.rows < 8 || lv.cols < 8) return fail(ctx, SLAMCU_INVALID_ARGUMENT, "pyramid level %d is %dx%d: too small", l, lv.cols, lv.rows);
+        lv.pitch = round_up(lv.cols, 128);
+        lv.mwords = (lv.cols + 31) / 32;
+        if (l == 0) lv.off = 0;
+        else { lv.off = pyr; pyr += (size_t)lv.rows * lv.pitch; }
+        lv.moff = mw;
+        mw += (size_t)lv.rows * lv.mwords;
+        if (l < L - 1) { lv.quota = (int)std::lrintf(ndesired); sum += lv.quota; ndesired *= factor; }
+        else lv.quota = std::max(det->max_features - sum, 0);
+        lv.capc = round_up(std::max(2048, lv.rows * lv.cols / 16), 32);
+        lv.coff = ct;
+        ct += lv.capc;
+    }
+    o.pyr_bytes = std::max<size_t>(pyr, 16);
+    o.mask_words = mw;
+    o.cand_total = ct;
+    const size_t F = (size_t)s->max_frames;
+    int rc = SLAMCU_OK;
+    auto A = [&](auto** p, size_t count, bool zero) {
+        if (rc == SLAMCU_OK) rc = dev_alloc(ctx, p, count, s->orb_owned, zero);
+    };
+    A(&o.pyr, F * o.pyr_bytes, true);
+    A(&o.pyrb, F * o.pyr_bytes, true);
+    A(&o.mask, F * o.mask_words, false);
+    A(&o.cxy, F * ct, false);
+    A(&o.cscore, F * ct, false);
+    A(&o.sxy, F * ct, false);
+    A(&o.sresp, F * ct, false);
+    A(&o.fxy, F * ct, false);
+    A(&o.fresp, F * ct, false);
+    A(&o.n_cand, F * kMaxLevels, true);
+    A(&o.n_sel, F * kMaxLevels, true);
+    A(&o.n_fin, F * kMaxLevels, true);
+    A(&o.octave, F * v.cap_kp, true);
+    A(&o.lxy, F * v.cap_kp, true);
+    for (int l = 1; l < L && rc == SLAMCU_OK; l++) {
+        std::vector<int> t[6];
+        resize_tables(o.lv[l].cols, o.lv[l - 1].cols, t[0], t[1], t[2]);
+        resize_tables(o.lv[l].rows, o.lv[l - 1].rows, t[3], t[4], t[5]);
+        int* d[6];
+        for (int k = 0; k < 6 && rc == SLAMCU_OK; k++) {
+            A(&d[k], t[k].size(), false);
+            if (rc == SLAMCU_OK && cudaMemcpy(d[k], t[k].data(), t[k].size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess)
+                rc = fail(ctx, SLAMCU_CUDA_ERROR, "table upload failed");
+        }
+        if (rc == SLAMCU_OK) {
+            o.lv[l].x0 = d[0]; o.lv[l].x1 = d[1]; o.lv[l].ax = d[2];
+            o.lv[l].y0 = d[3]; o.lv[l].y1 = d[4]; o.lv[l].ay = d[5];
+        }
+    }
+    if (rc != SLAMCU_OK) return rc;
+    s->has_orb = true;
+    s->orb_levels = L;
+    s->orb_features = det->max_features;
+    s->orb_scale = det->scale_factor;
+    return SLAMCU_OK;
+}
+
+static int seq_extract_orb(slamcu_sequence* s, slamcu_detector* det, int first, int n) {
+    slamcu_context* ctx = s->ctx;
+    if (s->v.desc_bytes != 32) return fail(ctx, SLAMCU_SIZE_MISMATCH, "ORB mode needs 32-byte descriptors");
+    int rc = seq_ensure_orb(s, det);
+    if (rc != SLAMCU_OK) return rc;
+    ProfGuard pg(ctx);
+    CU(ctx, cudaMemsetAsync(s->v.status + first, 0, (size_t)n * sizeof(int), ctx->stream));
+    ctx->launches += launch_orb_extract(s->v, s->orb, first, n, ctx->stream);
+    {
+        const SeqView& v = s->v;
+        ctx->launches += launch_desc_or(v.desc + (size_t)first * v.cap_kp * v.desc_words, v.n_kp + first, v.desc_words,
+                                        v.desc_or + (size_t)first * v.desc_words, ctx->stream, n,
+                                        (size_t)v.cap_kp * v.desc_words);
+    }
+    return check_launch(ctx, "orb kernels");
+}
+
+int slamcu_sequence_octaves(slamcu_sequence* s, int f, int32_t* octaves, int capacity) {
+    if (!s || !octaves) return SLAMCU_INVALID_ARGUMENT;
+    slamcu_context* ctx = s->ctx;
+    if (!s->has_orb) return fail(ctx, SLAMCU_UNSUPPORTED, "sequence was not extracted in ORB mode");
+    if (f < 0 || f >= s->max_frames) return fail(ctx, SLAMCU_INVALID_ARGUMENT, "bad frame index");
+    int32_t c[4];
+    int rc = slamcu_sequence_counts(s, f, 1, c);
+    if (rc != SLAMCU_OK) return rc;
+    if (c[0] > capacity) return fail(ctx, SLAMCU_CAPACITY, "need room for %d octaves", c[0]);
+    if (c[0] > 0) {
+        CU(ctx, cudaMemcpyAsync(octaves, s->orb.octave + (size_t)f * s->v.cap_kp, (size_t)c[0] * sizeof(int),
+                                cudaMemcpyDeviceToHost, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return SLAMCU_OK;
+}
+
 int slamcu_sequence_extract(slamcu_sequence* s, slamcu_detector* det, int first, int n) {
     if (!s || !det || s->ctx != det->ctx) return SLAMCU_INVALID_ARGUMENT;
     slamcu_context* ctx = s->ctx;
     if (first < 0 || n < 0 || first + n > s->max_frames) return fail(ctx, SLAMCU_INVALID_ARGUMENT, "bad frame range");
+    if (det->mode == SLAMCU_MODE_ORB) return n == 0 ? SLAMCU_OK : seq_extract_orb(s, det, first, n);
     if (det->p.pairs / 8 != s->v.desc_bytes)
         return fail(ctx, SLAMCU_SIZE_MISMATCH, "sequence desc_bytes %d != NumBRIEFPairs/8 = %d", s->v.desc_bytes,
                     det->p.pairs / 8);
@@ -601,7 +758,15 @@ int slamcu_detector_create(slamcu_context* ctx, const slamcu_detector_config* cf
     if (cfg->n_pattern < 0 || cfg->n_pattern > cfg->num_brief_pairs || (cfg->n_pattern > 0 && !cfg->pattern))
         return fail(ctx, SLAMCU_INVALID_ARGUMENT, "BRIEF pattern missing or longer than NumBRIEFPairs");
     if (!cfg->blur_weights) return fail(ctx, SLAMCU_INVALID_ARGUMENT, "blur weights missing");
-    if (cfg->mode != SLAMCU_MODE_REFERENCE) return fail(ctx, SLAMCU_UNSUPPORTED, "detector mode %d not built", cfg->mode);
+    if (cfg->mode != SLAMCU_MODE_REFERENCE && cfg->mode != SLAMCU_MODE_ORB)
+        return fail(ctx, SLAMCU_UNSUPPORTED, "detector mode %d unknown", cfg->mode);
+    if (cfg->mode == SLAMCU_MODE_ORB) {
+        if (cfg->n_levels < 1 || cfg->n_levels > kMaxLevels) return fail(ctx, SLAMCU_INVALID_ARGUMENT, "NumLevels must be in [1, %d]", kMaxLevels);
+        if (!(cfg->scale_factor > 1.0f)) return fail(ctx, SLAMCU_INVALID_ARGUMENT, "ScaleFactor must be > 1");
+        if (cfg->max_features <= 0) return fail(ctx, SLAMCU_INVALID_ARGUMENT, "MaxFeatures must be positive");
+        if (!cfg->orb_pattern) return fail(ctx, SLAMCU_INVALID_ARGUMENT, "ORB mode needs the 256x4 rBRIEF pattern");
+        if (cfg->num_brief_pairs != 256) return fail(ctx, SLAMCU_INVALID_ARGUMENT, "ORB mode descriptors are 256 bits");
+    }
     CU(ctx, cudaSetDevice(ctx->device));
     slamcu_detector* d = new (std::nothrow) slamcu_detector();
     if (!d) return SLAMCU_CUDA_ERROR;
@@ -615,6 +780,19 @@ int slamcu_detector_create(slamcu_context* ctx, const slamcu_detector_config* cf
     d->p.pairs = cfg->num_brief_pairs;
     d->p.n_pattern = cfg->n_pattern;
     for (int i = 0; i < 25; i++) d->p.blur_w[i] = cfg->blur_weights[i];
+    if (cfg->mode == SLAMCU_MODE_ORB) {
+        d->n_levels = cfg->n_levels;
+        d->scale_factor = cfg->scale_factor;
+        d->max_features = cfg->max_features;
+        d->fast_threshold = cfg->fast_threshold > 0 ? cfg->fast_threshold : cfg->intensity_threshold;
+        int8_t h[1024];
+        for (int i = 0; i < 1024; i++) h[i] = (int8_t)cfg->orb_pattern[i];
+        if (cudaMalloc(reinterpret_cast<void**>(&d->d_orb_pattern), 1024) != cudaSuccess ||
+            cudaMemcpy(d->d_orb_pattern, h, 1024, cudaMemcpyHostToDevice) != cudaSuccess) {
+            delete d;
+            return fail(ctx, SLAMCU_CUDA_ERROR, "cudaMalloc(orb pattern) failed");
+        }
+    }
     const size_t pbytes = (size_t)std::max(cfg->n_pattern, 1) * 4 * sizeof(int);
     if (cudaMalloc(reinterpret_cast<void**>(&d->d_pattern), pbytes) != cudaSuccess) {
         delete d;
@@ -633,6 +811,7 @@ void slamcu_detector_destroy(slamcu_detector* d) {
     cudaSetDevice(d->ctx->device);
     if (d->one) slamcu_sequence_destroy(d->one);
     if (d->d_pattern) cudaFree(d->d_pattern);
+    if (d->d_orb_pattern) cudaFree(d->d_orb_pattern);
     delete d;
 }
 
@@ -649,6 +828,7 @@ static int detector_workspace(slamcu_detector* d, int rows, int cols, int min_kp
     // single calls favour safety over footprint: room for one corner per 4 pixels
     int cap_raw = (int)std::min<long long>(std::max<long long>(px / 4, 8192), kMaxRawCap);
     int cap_kp = d->p.nms ? (int)std::min<long long>(std::max<long long>(px / 16, 4096), kMaxRawCap) : cap_raw;
+    if (d->mode == SLAMCU_MODE_ORB) { cap_raw = 8192; cap_kp = std::max(4096, 2 * d->max_features); }
     cap_kp = std::max(cap_kp, min_kp);
     return slamcu_sequence_create(ctx, rows, cols, 1, cap_raw, cap_kp, desc_bytes, &d->one);
 }
@@ -670,6 +850,12 @@ static int detect_common(slamcu_detector* d, const uint8_t* image, int rows, int
     slamcu_sequence* s = d->one;
     rc = slamcu_sequence_upload(s, 0, 1, image, stride);
     if (rc != SLAMCU_OK) return rc;
+    if (d->mode == SLAMCU_MODE_ORB) {
+        if (what == 2) return fail(ctx, SLAMCU_UNSUPPORTED, "raw-corner probe is a reference-mode stage");
+        rc = seq_extract_orb(s, d, 0, 1);
+        if (rc != SLAMCU_OK) return rc;
+        return slamcu_sequence_frame(s, 0, kps, what == 1 ? desc : nullptr, desc_stride, capacity, n_out);
+    }
     rc = seq_detect(s, d, 0, 1, what == 2);
     if (rc != SLAMCU_OK) return rc;
     if (what == 1) {
@@ -725,6 +911,64 @@ int slamcu_compute(slamcu_detector* d, const uint8_t* image, int rows, int cols,
     if (rc != SLAMCU_OK) return rc;
     int got = 0;
     return slamcu_sequence_frame(s, 0, kps, desc, desc_stride, n, &got);
+}
+
+int slamcu_detector_last_octaves(slamcu_detector* d, int32_t* octaves, int capacity) {
+    if (!d || !d->one) return SLAMCU_INVALID_ARGUMENT;
+    return slamcu_sequence_octaves(d->one, 0, octaves, capacity);
+}
+
+int slamcu_orb_stage(slamcu_detector* d, int stage, int level, uint32_t* xy, float* value, int capacity, int* n_out) {
+    if (!d || !n_out) return SLAMCU_INVALID_ARGUMENT;
+    slamcu_context* ctx = d->ctx;
+    if (d->mode != SLAMCU_MODE_ORB || !d->one || !d->one->has_orb)
+        return fail(ctx, SLAMCU_UNSUPPORTED, "no ORB-mode single-frame call to probe");
+    const OrbView& o = d->one->orb;
+    if (stage < 0 || stage > 2 || level < 0 || level >= o.nlevels) return fail(ctx, SLAMCU_INVALID_ARGUMENT, "bad stage / level");
+    CU(ctx, cudaSetDevice(ctx->device));
+    const int* counts = stage == 0 ? o.n_cand : stage == 1 ? o.n_sel : o.n_fin;
+    int n = 0;
+    CU(ctx, cudaMemcpyAsync(&n, counts + level, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    *n_out = n;
+    if (n > capacity) return fail(ctx, SLAMCU_CAPACITY, "need room for %d entries", n);
+    if (n == 0) return SLAMCU_OK;
+    const size_t off = o.lv[level].coff;
+    const uint32_t* sxy = stage == 0 ? o.cxy : stage == 1 ? o.sxy : o.fxy;
+    if (xy) CU(ctx, cudaMemcpyAsync(xy, sxy + off, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (value) {
+        if (stage == 0) {
+            std::vector<int> tmp((size_t)n);
+            CU(ctx, cudaMemcpyAsync(tmp.data(), o.cscore + off, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            CU(ctx, cudaStreamSynchronize(ctx->stream));
+            for (int i = 0; i < n; i++) value[i] = (float)tmp[i];
+        } else {
+            CU(ctx, cudaMemcpyAsync(value, (stage == 1 ? o.sresp : o.fresp) + off, (size_t)n * 4, cudaMemcpyDeviceToHost,
+                                    ctx->stream));
+        }
+    }
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return SLAMCU_OK;
+}
+
+int slamcu_orb_level_image(slamcu_detector* d, int level, int blurred, uint8_t* out, int out_stride, int* rows, int* cols) {
+    if (!d) return SLAMCU_INVALID_ARGUMENT;
+    slamcu_context* ctx = d->ctx;
+    if (d->mode != SLAMCU_MODE_ORB || !d->one || !d->one->has_orb)
+        return fail(ctx, SLAMCU_UNSUPPORTED, "no ORB-mode single-frame call to probe");
+    const OrbView& o = d->one->orb;
+    const SeqView& v = d->one->v;
+    if (level < 0 || level >= o.nlevels) return fail(ctx, SLAMCU_INVALID_ARGUMENT, "bad level");
+    const OrbLevel& L = o.lv[level];
+    if (rows) *rows = L.rows;
+    if (cols) *cols = L.cols;
+    if (!out) return SLAMCU_OK;
+    if (out_stride < L.cols) return fail(ctx, SLAMCU_INVALID_ARGUMENT, "out_stride too small");
+    CU(ctx, cudaSetDevice(ctx->device));
+    const uint8_t* src = level == 0 ? (blurred ? v.blur : v.img) : (blurred ? o.pyrb : o.pyr) + L.off;
+    CU(ctx, cudaMemcpy2DAsync(out, out_stride, src, L.pitch, L.cols, L.rows, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return SLAMCU_OK;
 }
 
 int slamcu_gaussian_blur(slamcu_detector* d, const uint8_t* image, int rows, int cols, int stride, uint8_t* out,

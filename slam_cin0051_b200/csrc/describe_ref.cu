@@ -194,8 +194,9 @@ int launch_describe(const SeqView& s, int first, int n, const DetParams& p, cons
     return 2;
 }
 
-int launch_desc_or(const uint32_t* desc, const int* n_dev, int desc_words, uint32_t* out, cudaStream_t st) {
-    desc_or_kernel<<<1, 256, 0, st>>>(desc, 0, n_dev, desc_words, out);
+int launch_desc_or(const uint32_t* desc, const int* n_dev, int desc_words, uint32_t* out, cudaStream_t st, int sets,
+                   size_t set_stride) {
+    SLAM_KERNEL("desc_or", st, desc_or_kernel<<<sets, 256, 0, st>>>(desc, set_stride, n_dev, desc_words, out));
     return 1;
 }
 

@@ -1,0 +1,51 @@
+// orb.cuh -- device view of the ORB-compatible ("mode B") extractor's working set.
+#pragma once
+#include "common.cuh"
+
+namespace slamcu {
+
+constexpr int kMaxLevels = 12;
+constexpr int kOrbEdge = 31;        // edgeThreshold
+constexpr int kOrbPatch = 31;       // patchSize
+constexpr int kOrbHalfPatch = 15;
+
+struct OrbLevel {
+    int rows, cols, pitch, mwords;
+    size_t off;      // byte offset of this level inside a frame's pyramid block (level 0 lives in SeqView::img)
+    size_t moff;     // word offset of this level's corner mask inside a frame's mask block
+    size_t coff;     // element offset of this level's candidate lists inside a frame's candidate block
+    int capc;        // candidate capacity
+    int quota;       // nfeaturesPerLevel
+    float scale;     // (float)pow(scaleFactor, level)
+    // INTER_LINEAR_EXACT tables for producing this level from level-1 (device pointers; unused for level 0)
+    const int* x0; const int* x1; const int* ax;
+    const int* y0; const int* y1; const int* ay;
+};
+
+struct OrbView {
+    int nlevels;
+    int fast_threshold;
+    OrbLevel lv[kMaxLevels];
+    size_t pyr_bytes;     // per frame, levels 1..L-1
+    size_t mask_words;    // per frame
+    size_t cand_total;    // per frame
+    uint8_t* pyr;         // [F][pyr_bytes]
+    uint8_t* pyrb;        // [F][pyr_bytes]   blurred levels 1..L-1 (level 0 -> SeqView::blur)
+    uint32_t* mask;       // [F][mask_words]  FAST-9 + 3x3 NMS + border-filter survivors, 1 bit / pixel
+    uint32_t* cxy;        // [F][cand_total]  candidates, raster order per level: (y << 16) | x
+    int* cscore;          // [F][cand_total]  FAST score
+    uint32_t* sxy;        // [F][cand_total]  after retainBest(2*quota)
+    float* sresp;         // [F][cand_total]  Harris response
+    uint32_t* fxy;        // [F][cand_total]  after retainBest(quota)
+    float* fresp;         // [F][cand_total]
+    int* n_cand;          // [F][kMaxLevels]
+    int* n_sel;           // [F][kMaxLevels]
+    int* n_fin;           // [F][kMaxLevels]
+    int* octave;          // [F][cap_kp]
+    uint32_t* lxy;        // [F][cap_kp]      level coordinates of the final keypoints
+    const int8_t* pattern;  // [512][2] rBRIEF sampling points
+};
+
+int launch_orb_extract(const SeqView& s, const OrbView& o, int first, int n, cudaStream_t st);
+
+}  // namespace slamcu

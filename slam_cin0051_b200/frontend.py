@@ -79,7 +79,23 @@ class FeatureDetector:
         c.n_pattern = len(self.brief_pattern)
         c.pattern = self.brief_pattern.ctypes.data_as(C.POINTER(C.c_int32))
         c.blur_weights = self.blur_weights.ctypes.data_as(C.POINTER(C.c_double))
+        # Opt-in OpenCV-ORB-compatible mode: present only when the YAML carries keys the reference does not have.
+        self.orb_mode = any(k in cfg for k in ("NumLevels", "MaxFeatures", "ScaleFactor"))
         c.mode = 0
+        if self.orb_mode:
+            self.num_levels = get_int(cfg, "NumLevels") or 8
+            self.scale_factor = float(np.float32(get_float(cfg, "ScaleFactor") or 1.2))
+            self.max_features = get_int(cfg, "MaxFeatures") or 2000
+            if self.patch_size != 31 or self.num_brief_pairs != 256:
+                raise RuntimeError("ORB mode requires PatchSize 31 and NumBRIEFPairs 256.")
+            self.orb_pattern = np.ascontiguousarray(
+                np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "orb_bit_pattern_31.npy")), np.int32)
+            c.mode = 1
+            c.n_levels = self.num_levels
+            c.scale_factor = self.scale_factor
+            c.max_features = self.max_features
+            c.fast_threshold = get_int(cfg, "FastThreshold") or self.intensity_threshold
+            c.orb_pattern = self.orb_pattern.ctypes.data_as(C.POINTER(C.c_int32))
         h = C.c_void_p()
         self.ctx.check(lib.slamcu_detector_create(self.ctx.handle, C.byref(c), C.byref(h)))
         self.handle = h
@@ -116,6 +132,35 @@ class FeatureDetector:
                 continue
             self.ctx.check(st)
             return (kps[: n.value].copy(), desc[: n.value].copy()) if with_desc else kps[: n.value].copy()
+
+    def last_octaves(self, n: int) -> np.ndarray:
+        """ORB mode: cv::KeyPoint::octave of the n keypoints returned by the last single-frame call."""
+        out = np.zeros(max(n, 1), np.int32)
+        self.ctx.check(self.ctx.lib.slamcu_detector_last_octaves(self.handle, out.ctypes.data, len(out)))
+        return out[:n].copy()
+
+    def orb_stage(self, stage: int, level: int):
+        """ORB mode stage probe of the last single-frame call: (x, y, value) arrays in level coordinates."""
+        n = C.c_int(0)
+        lib = self.ctx.lib
+        st = lib.slamcu_orb_stage(self.handle, stage, level, None, None, 0, C.byref(n))
+        if st not in (_lib.OK, _lib.CAPACITY):
+            self.ctx.check(st)
+        xy = np.zeros(max(n.value, 1), np.uint32)
+        val = np.zeros(max(n.value, 1), np.float32)
+        self.ctx.check(lib.slamcu_orb_stage(self.handle, stage, level, xy.ctypes.data, val.ctypes.data, len(xy), C.byref(n)))
+        xy, val = xy[: n.value], val[: n.value]
+        return (xy & 0xFFFF).astype(np.int32), (xy >> 16).astype(np.int32), val.copy()
+
+    def orb_level_image(self, level: int, blurred: bool = False) -> np.ndarray:
+        """ORB mode: pyramid level (optionally its 7x7 blurred copy) of the last single-frame call."""
+        r, c = C.c_int(0), C.c_int(0)
+        lib = self.ctx.lib
+        self.ctx.check(lib.slamcu_orb_level_image(self.handle, level, int(blurred), None, 0, C.byref(r), C.byref(c)))
+        out = np.zeros((r.value, c.value), np.uint8)
+        self.ctx.check(lib.slamcu_orb_level_image(self.handle, level, int(blurred), out.ctypes.data, out.strides[0],
+                                                  C.byref(r), C.byref(c)))
+        return out
 
     def detect(self, image) -> np.ndarray:
         """FeatureDetector::detect (feature_detector.cpp:8-18)."""

@@ -79,6 +79,11 @@ class FrameSequence:
             self.ctx.check(st)
             return kps[: n.value].copy(), desc[: n.value].copy()
 
+    def octaves(self, f: int, n: int) -> np.ndarray:
+        out = np.zeros(max(n, 1), np.int32)
+        self.ctx.check(self.ctx.lib.slamcu_sequence_octaves(self.handle, f, out.ctypes.data, len(out)))
+        return out[:n].copy()
+
     def matches(self, f: int) -> np.ndarray:
         cap = 4096
         while True:
