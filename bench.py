@@ -67,28 +67,70 @@ def cpu_reference_run(frames, threads):
     return sec, counts
 
 
+def cpu_orb_run(frames, threads, nfeatures=2000, ratio=0.75):
+    """OpenCV's own ORB + BFMatcher(k=2) + ratio test on the host cores, frame-parallel (cv2 releases the GIL).
+    Returns (seconds, counts[n, 2] = keypoints, matches(f, f+1))."""
+    import concurrent.futures as cf
+
+    import cv2
+    cv2.setNumThreads(1)
+    n = len(frames)
+
+    def extract(i):
+        orb = cv2.ORB_create(nfeatures=nfeatures, scaleFactor=1.2, nlevels=8, edgeThreshold=31, firstLevel=0, WTA_K=2,
+                             scoreType=cv2.ORB_HARRIS_SCORE, patchSize=31, fastThreshold=20)
+        k, d = orb.detectAndCompute(frames[i], None)
+        return d if d is not None else np.zeros((0, 32), np.uint8)
+
+    def match(i):
+        if len(desc[i]) == 0 or len(desc[i + 1]) < 2:
+            return 0
+        m = cv2.BFMatcher(cv2.NORM_HAMMING).knnMatch(desc[i], desc[i + 1], k=2)
+        return sum(1 for a, b in m if not (a.distance >= np.float32(ratio) * np.float32(b.distance)))
+
+    t0 = time.perf_counter()
+    with cf.ThreadPoolExecutor(max_workers=threads) as ex:
+        desc = list(ex.map(extract, range(n)))
+        nm = list(ex.map(match, range(n - 1))) + [0]
+    sec = time.perf_counter() - t0
+    return sec, np.array([[len(d), m] for d, m in zip(desc, nm)], np.int64)
+
+
+MODE_TEXT = {
+    "orb": "OpenCV-ORB-compatible: 8-level pyramid, FAST-9 + Harris, 2000-keypoint budget, rBRIEF-256, BF Hamming kNN k=2 + ratio 0.75",
+    "reference": "reference algorithm (FAST-12 + SAD NMS + BRIEF + BF Hamming with keypoint penalty)",
+}
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return 0
     threads = host_threads()
-    # bounded sample per step: ~0.15 s of single-core work per frame -> a few seconds per step
+    orb = args.mode == "orb"
+    # bounded sample per step: ~0.1-0.15 s of single-core work per frame -> a few seconds per step
     n = max(threads, min(args.frames, 4 * threads))
     frames = make_frames(n, 0)
+    run = cpu_orb_run if orb else cpu_reference_run
     for _ in range(args.warmup):
-        cpu_reference_run(frames[: max(2, n // 4)], threads)
+        run(frames[: max(2, n // 4)], threads)
     t = 0.0
     for _ in range(args.steps):
-        sec, counts = cpu_reference_run(frames, threads)
+        sec, counts = run(frames, threads)
         t += sec
     value = n * args.steps / t
+    if orb:
+        import cv2
+        kind, how = "reference", f"cv2 {cv2.__version__} ORB_create(2000).detectAndCompute + BFMatcher(NORM_HAMMING).knnMatch(k=2) + ratio 0.75, frame-parallel thread pool, cv2.setNumThreads(1) per call"
+    else:
+        kind, how = "port", "frame-parallel std::thread pool, oracle/ref_frontend.cpp (g++ -O2)"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "mode": "reference algorithm (FAST-12 + SAD NMS + BRIEF + BF Hamming)",
+        "config": {"workload": WORKLOAD, "mode": MODE_TEXT[args.mode],
                    "frames_per_step": n, "keypoints_per_frame_mean": float(counts[:, 0].mean())},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{n} frames/step x {args.steps} steps, frame-parallel std::thread pool, oracle/ref_frontend.cpp (g++ -O2)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind,
+                         "sample": f"{n} frames/step x {args.steps} steps, {how}"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -138,9 +180,36 @@ class ClockSampler:
         return out
 
 
-def kernel_model(name, frames, px, pitch_px, n_raw, n_kp, cmp_per_step):
-    """Algorithmic work per launch (DESIGN.md section 'Kernels'): bytes for HBM-bound kernels, comparisons for the matcher."""
+def orb_level_pixels(rows, cols, nlevels=8, sf=1.2):
+    out = []
+    for l in range(nlevels):
+        s = np.float32(np.power(np.float64(np.float32(sf)), float(l)))
+        out.append(int(np.rint(np.float32(rows) / s)) * int(np.rint(np.float32(cols) / s)))
+    return out
+
+
+def kernel_model(name, frames, px, pitch_px, n_raw, n_kp, cmp_per_step, orb_stats=None):
+    """Algorithmic work per STEP (DESIGN.md section 'Kernels'): bytes for HBM-bound kernels, comparisons for the
+    matcher.  Kernels launched once per pyramid level are summed over the levels."""
     mask = px / 8
+    if orb_stats is not None:
+        lp = orb_level_pixels(ROWS, COLS)
+        P = float(sum(lp))
+        n_cand, n_sel = orb_stats
+        table = {
+            "pyr_down": ("hbm", frames * float(sum(lp[l - 1] + lp[l] for l in range(1, len(lp))))),
+            "fast9_mask": ("hbm", frames * (P + P / 8)),
+            "orb_select": ("hbm", frames * (P / 8 + 12 * n_cand + 16 * n_cand + 4 * n_sel)),
+            "harris": ("hbm", frames * (81 * n_sel + 8 * n_sel)),
+            "orb_retain": ("hbm", frames * (8 * n_sel + 8 * n_kp)),
+            "orb_assemble": ("hbm", frames * (8 * n_kp + 28 * n_kp)),
+            "blur7": ("hbm", frames * (2 * P)),
+            "orb_describe": ("hbm", frames * ((709 + 512) * n_kp + 44 * n_kp)),
+            "desc_or": ("hbm", frames * (32 * n_kp)),
+            "match": ("popc", cmp_per_step),
+            "match_finalize": ("hbm", frames * (16 * n_kp + 12 * n_kp)),
+        }
+        return table.get(name, ("hbm", 0.0))
     table = {
         "fast_mask": ("hbm", frames * (px + mask)),
         "corner_list": ("hbm", frames * (mask + 17 * n_raw + 8 * n_raw)),
@@ -172,8 +241,11 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
     data = os.path.join(ROOT, "test", "data")
-    det = S.FeatureDetector(os.path.join(data, "feature_detector.yml"), ctx)
-    mat = S.FeatureMatcher(os.path.join(data, "feature_matcher.yml"), ctx)
+    orb = args.mode == "orb"
+    sfx = "_orb" if orb else ""
+    with_kp = not orb  # the reference's matcher applies its image-distance penalty; BFMatcher has none
+    det = S.FeatureDetector(os.path.join(data, f"feature_detector{sfx}.yml"), ctx)
+    mat = S.FeatureMatcher(os.path.join(data, f"feature_matcher{sfx}.yml"), ctx)
     max_kp = args.max_keypoints
     seq = S.FrameSequence(ROWS, COLS, B, desc_bytes=det.descriptor_bytes, max_keypoints=max_kp, context=ctx)
 
@@ -192,12 +264,12 @@ def run_ours(args, rank, world, local_rank):
 
     def step_resident():
         seq.extract(det, 0, B)
-        seq.match_consecutive(mat, 0, B - 1, with_keypoints=True)
+        seq.match_consecutive(mat, 0, B - 1, with_keypoints=with_kp)
 
     def step_e2e():
         seq.upload_ptr(host_frames.data_ptr(), B)
         seq.extract(det, 0, B)
-        seq.match_consecutive(mat, 0, B - 1, with_keypoints=True)
+        seq.match_consecutive(mat, 0, B - 1, with_keypoints=with_kp)
         # results a caller of detectAndCompute/match receives: counts first, then only the matches that
         # exist (GoodMatchesCount per pair) and the keypoint / descriptor blocks
         seq.download_ptrs(0, B, h_kps.data_ptr(), h_desc.data_ptr(), None, h_counts.data_ptr())
@@ -272,17 +344,18 @@ def run_ours(args, rank, world, local_rank):
         kernels = []
         total_k_ms = sum(v[0] for v in prof.values()) or 1.0
         for name, (kms, cnt) in sorted(prof.items(), key=lambda kv: -kv[1][0]):
-            bound, work = kernel_model(name, B, px, GRID_PITCH, n_raw_mean, n_kp_mean, cmp_per_step)
+            bound, work = kernel_model(name, B, px, GRID_PITCH, n_raw_mean, n_kp_mean, cmp_per_step,
+                                       (n_raw_mean, 2.0 * n_kp_mean) if orb else None)
             per_launch_ms = kms / max(cnt, 1)
+            ms_step = kms / args.steps  # all launches of this kernel in one step (one per pyramid level for some)
+            ach = work / (ms_step * 1e-3) / 1e9
+            common = {"kernel": name, "ms_per_launch": per_launch_ms, "launches_per_step": cnt / args.steps,
+                      "ms_per_step": ms_step, "share": kms / total_k_ms, "achieved": ach}
             if bound == "hbm":
-                ach = work / (per_launch_ms * 1e-3) / 1e9
-                kernels.append({"kernel": name, "bound": "hbm", "ms_per_launch": per_launch_ms, "share": kms / total_k_ms,
-                                "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak})
+                kernels.append({**common, "bound": "hbm", "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak})
             else:
-                ach = work / (per_launch_ms * 1e-3) / 1e9
                 peak = gpopc / 8.0
-                kernels.append({"kernel": name, "bound": "popc", "ms_per_launch": per_launch_ms, "share": kms / total_k_ms,
-                                "achieved": ach, "peak": peak, "unit": "Gcmp/s (256-bit)", "frac": ach / peak})
+                kernels.append({**common, "bound": "popc", "peak": peak, "unit": "Gcmp/s (256-bit)", "frac": ach / peak})
         top = kernels[0] if kernels else {}
         roofline = {"kernel": top.get("kernel"), "bound": top.get("bound"), "achieved": top.get("achieved"),
                     "peak": top.get("peak"), "unit": top.get("unit"), "frac": top.get("frac"), "traffic": None,
@@ -292,7 +365,7 @@ def run_ours(args, rank, world, local_rank):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "mode": "reference algorithm (FAST-12 + SAD NMS + BRIEF + BF Hamming with keypoint penalty)",
+            "config": {"workload": WORKLOAD, "mode": MODE_TEXT[args.mode],
                        "frames_per_step_per_gpu": B, "pairs_per_step_per_gpu": B - 1, "keypoints_per_frame_mean": n_kp_mean,
                        "raw_corners_per_frame_mean": n_raw_mean, "parallelism": f"frame-range sharding x{world}",
                        "l2": f"inputs larger than L2: {B * ROWS * COLS / 1e6:.0f} MB of frames per step vs 126 MB L2"},
@@ -306,12 +379,20 @@ def run_ours(args, rank, world, local_rank):
         }
         if world == 1 and not args.no_cpu_baseline:
             threads = host_threads()
-            n_s = max(8, min(B, 2 * threads))
-            sec, c_cpu = cpu_reference_run(frames_np[:n_s], threads)
-            sec1, _ = cpu_reference_run(frames_np[:4], 1)
+            n_s = max(8, min(B, 4 * threads))
+            run = cpu_orb_run if orb else cpu_reference_run
+            run(frames_np[:4], threads)  # warm
+            sec, c_cpu = run(frames_np[:n_s], threads)
+            sec1, _ = run(frames_np[:4], 1)
             same = bool((c_cpu[:, 0] == counts[:n_s, 0]).all() and (c_cpu[:-1, 1] == counts[:n_s - 1, 1]).all())
-            line["cpu_baseline"] = {"value": n_s / sec, "unit": UNIT, "cores": threads, "kind": "port",
-                                    "sample": f"first {n_s} frames of the same batch, frame-parallel over {threads} host threads",
+            if orb:
+                import cv2
+                kind = "reference"
+                what = f"cv2 {cv2.__version__} ORB_create(2000) + BFMatcher.knnMatch(k=2) + ratio 0.75 (the OpenCV path BASELINE.json names)"
+            else:
+                kind, what = "port", "oracle/ref_frontend.cpp (port of the reference's src/frontend, g++ -O2)"
+            line["cpu_baseline"] = {"value": n_s / sec, "unit": UNIT, "cores": threads, "kind": kind,
+                                    "sample": f"first {n_s} frames of the same batch, frame-parallel over {threads} host threads; {what}",
                                     "single_thread_value": 4 / sec1, "counts_match_gpu": same}
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -325,6 +406,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default="orb", choices=["orb", "reference"],
+                    help="orb: the OpenCV-ORB-compatible path BASELINE.json's headline config names; "
+                         "reference: the reference repo's own hand-written detector/matcher")
     ap.add_argument("--frames", type=int, default=512, help="frames per GPU per step")
     ap.add_argument("--max-keypoints", type=int, default=2560)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -151,6 +151,7 @@ struct slamcu_detector {
     int n_levels = 8, max_features = 2000, fast_threshold = 20;
     float scale_factor = 1.2f;
     int8_t* d_orb_pattern = nullptr;  // [512][2]
+    float2* d_orb_patf = nullptr;     // [512] (x, y) as floats
     int* d_pattern = nullptr;
     slamcu_sequence* one = nullptr;  // cached single-frame workspace
 };
@@ -408,23 +409,19 @@ static int seq_compute(slamcu_sequence* s, slamcu_detector* det, int first, int 
     return check_launch(ctx, "compute kernels");
 }
 
-// INTER_LINEAR_EXACT coefficient tables (OpenCV resize.cpp bit-exact path): source index pair and the
-// 8.8 fixed-point weight of the second tap, computed in double exactly like OpenCV, per destination index.
-static void resize_tables(int dst, int src, std::vector<int>& i0, std::vector<int>& i1, std::vector<int>& a) {
-    i0.resize(dst);
-    i1.resize(dst);
-    a.resize(dst);
+// INTER_LINEAR_EXACT coefficient tables (OpenCV resize.cpp bit-exact path): first source index and the 8.8
+// fixed-point weight of the second tap, computed in double exactly like OpenCV, packed (index << 8) | weight.
+static void resize_table(int dst, int src, std::vector<uint32_t>& tab) {
+    tab.resize(dst);
     const double scale = 1.0 / ((double)dst / (double)src);
     for (int d = 0; d < dst; d++) {
         const double f = scale * (d + 0.5) - 0.5;
         int i = (int)std::floor(f);
         int w = (int)std::nearbyint((f - i) * 256.0);  // cvRound: half to even
-        int j = i + 1;
-        if (i < 0) { i = 0; j = 0; w = 0; }
-        if (i >= src - 1) { i = src - 1; j = src - 1; w = 0; }
-        i0[d] = i;
-        i1[d] = j;
-        a[d] = w;
+        if (i < 0) { i = 0; w = 0; }
+        if (i >= src - 1) { i = src - 1; w = 0; }
+        if (w == 256) { i += 1; w = 0; }  // (256 - 256) * s[i] + 256 * s[i + 1]  ==  256 * s[i + 1] + 0 * s[i + 2]
+        tab[d] = ((uint32_t)i << 8) | (uint32_t)w;
     }
 }
 
@@ -434,6 +431,7 @@ static int seq_ensure_orb(slamcu_sequence* s, slamcu_detector* det) {
         s->orb_scale == det->scale_factor) {
         s->orb.fast_threshold = det->fast_threshold;
         s->orb.pattern = det->d_orb_pattern;
+        s->orb.patf = det->d_orb_patf;
         return SLAMCU_OK;
     }
     CU(ctx, cudaStreamSynchronize(ctx->stream));
@@ -447,6 +445,7 @@ static int seq_ensure_orb(slamcu_sequence* s, slamcu_detector* det) {
     o.nlevels = L;
     o.fast_threshold = det->fast_threshold;
     o.pattern = det->d_orb_pattern;
+    o.patf = det->d_orb_patf;
     // ORB_Impl: scale = (float)pow(scaleFactor, level); size = cvRound(dim / scale); quotas by geometric series
     const double sf = (double)det->scale_factor;
     const float factor = (float)(1.0 / sf);
@@ -494,19 +493,17 @@ static int seq_ensure_orb(slamcu_sequence* s, slamcu_detector* det) {
     A(&o.octave, F * v.cap_kp, true);
     A(&o.lxy, F * v.cap_kp, true);
     for (int l = 1; l < L && rc == SLAMCU_OK; l++) {
-        std::vector<int> t[6];
-        resize_tables(o.lv[l].cols, o.lv[l - 1].cols, t[0], t[1], t[2]);
-        resize_tables(o.lv[l].rows, o.lv[l - 1].rows, t[3], t[4], t[5]);
-        int* d[6];
-        for (int k = 0; k < 6 && rc == SLAMCU_OK; k++) {
-            A(&d[k], t[k].size(), false);
-            if (rc == SLAMCU_OK && cudaMemcpy(d[k], t[k].data(), t[k].size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess)
-                rc = fail(ctx, SLAMCU_CUDA_ERROR, "table upload failed");
-        }
-        if (rc == SLAMCU_OK) {
-            o.lv[l].x0 = d[0]; o.lv[l].x1 = d[1]; o.lv[l].ax = d[2];
-            o.lv[l].y0 = d[3]; o.lv[l].y1 = d[4]; o.lv[l].ay = d[5];
-        }
+        std::vector<uint32_t> tx, ty;
+        resize_table(o.lv[l].cols, o.lv[l - 1].cols, tx);
+        resize_table(o.lv[l].rows, o.lv[l - 1].rows, ty);
+        uint32_t *dx = nullptr, *dy = nullptr;
+        A(&dx, tx.size(), false);
+        A(&dy, ty.size(), false);
+        if (rc == SLAMCU_OK && (cudaMemcpy(dx, tx.data(), tx.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
+                                cudaMemcpy(dy, ty.data(), ty.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess))
+            rc = fail(ctx, SLAMCU_CUDA_ERROR, "table upload failed");
+        o.lv[l].xt = dx;
+        o.lv[l].yt = dy;
     }
     if (rc != SLAMCU_OK) return rc;
     s->has_orb = true;
@@ -787,8 +784,12 @@ int slamcu_detector_create(slamcu_context* ctx, const slamcu_detector_config* cf
         d->fast_threshold = cfg->fast_threshold > 0 ? cfg->fast_threshold : cfg->intensity_threshold;
         int8_t h[1024];
         for (int i = 0; i < 1024; i++) h[i] = (int8_t)cfg->orb_pattern[i];
+        float hf[1024];
+        for (int i = 0; i < 1024; i++) hf[i] = (float)cfg->orb_pattern[i];
         if (cudaMalloc(reinterpret_cast<void**>(&d->d_orb_pattern), 1024) != cudaSuccess ||
-            cudaMemcpy(d->d_orb_pattern, h, 1024, cudaMemcpyHostToDevice) != cudaSuccess) {
+            cudaMemcpy(d->d_orb_pattern, h, 1024, cudaMemcpyHostToDevice) != cudaSuccess ||
+            cudaMalloc(reinterpret_cast<void**>(&d->d_orb_patf), sizeof hf) != cudaSuccess ||
+            cudaMemcpy(d->d_orb_patf, hf, sizeof hf, cudaMemcpyHostToDevice) != cudaSuccess) {
             delete d;
             return fail(ctx, SLAMCU_CUDA_ERROR, "cudaMalloc(orb pattern) failed");
         }
@@ -812,6 +813,7 @@ void slamcu_detector_destroy(slamcu_detector* d) {
     if (d->one) slamcu_sequence_destroy(d->one);
     if (d->d_pattern) cudaFree(d->d_pattern);
     if (d->d_orb_pattern) cudaFree(d->d_orb_pattern);
+    if (d->d_orb_patf) cudaFree(d->d_orb_patf);
     delete d;
 }
 

@@ -32,44 +32,67 @@ __device__ __forceinline__ uint8_t* blur_ptr(const SeqView& s, const OrbView& o,
 }
 
 // ---- B1 ------------------------------------------------------------------------------------------
+// INTER_LINEAR_EXACT: out = ((256-ay) * ((256-ax) s00 + ax s01) + ay * ((256-ax) s10 + ax s11) + 32768) >> 16,
+// written as a + w (b - a) on 8.8 / 16.16 integers (identical values: everything is exact in int32).
 __global__ void __launch_bounds__(256) pyr_down_kernel(SeqView s, OrbView o, int first, int l) {
     const int f = first + blockIdx.z;
     const OrbLevel& d = o.lv[l];
     const OrbLevel& p = o.lv[l - 1];
-    const int x = blockIdx.x * 64 + (threadIdx.x & 15) * 4;  // 4 pixels per thread -> one 32-bit store
-    const int y = blockIdx.y * 16 + (threadIdx.x >> 4);
+    const int x = blockIdx.x * 128 + (threadIdx.x & 31) * 4;  // 4 pixels per thread -> one 32-bit store
+    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
     if (y >= d.rows || x >= d.pitch) return;
     const uint8_t* src = level_ptr(s, o, f, l - 1);
     uint8_t* dst = level_ptr_w(s, o, f, l);
-    const int y0 = d.y0[y], y1 = d.y1[y], ay = d.ay[y];
-    const uint8_t* r0 = src + (size_t)y0 * p.pitch;
-    const uint8_t* r1 = src + (size_t)y1 * p.pitch;
+    const uint32_t ty = __ldg(d.yt + y);
+    const int sy0 = ty >> 8, ay = ty & 255, sy1 = min(sy0 + 1, p.rows - 1);
+    const uint8_t* r0 = src + (size_t)sy0 * p.pitch;
+    const uint8_t* r1 = src + (size_t)sy1 * p.pitch;
     uint32_t packed = 0;
+    if (x + 3 < d.cols) {
+        const uint4 tx = __ldg(reinterpret_cast<const uint4*>(d.xt + x));
+        const uint32_t t4[4] = {tx.x, tx.y, tx.z, tx.w};
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-        const int xx = x + k;
-        uint32_t v = 0;
-        if (xx < d.cols) {
-            const int x0 = d.x0[xx], x1 = d.x1[xx], ax = d.ax[xx];
-            const int h0 = (256 - ax) * r0[x0] + ax * r0[x1];
-            const int h1 = (256 - ax) * r1[x0] + ax * r1[x1];
-            v = (uint32_t)(((256 - ay) * h0 + ay * h1 + 32768) >> 16);
+        for (int k = 0; k < 4; k++) {
+            const int sx0 = t4[k] >> 8, ax = t4[k] & 255, sx1 = min(sx0 + 1, p.cols - 1);
+            const int a0 = r0[sx0], b0 = r0[sx1], a1 = r1[sx0], b1 = r1[sx1];
+            const int h0 = (a0 << 8) + ax * (b0 - a0);
+            const int h1 = (a1 << 8) + ax * (b1 - a1);
+            packed |= (uint32_t)(((h0 << 8) + ay * (h1 - h0) + 32768) >> 16) << (8 * k);
         }
-        packed |= v << (8 * k);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (x + k >= d.cols) break;
+            const uint32_t t1 = __ldg(d.xt + x + k);
+            const int sx0 = t1 >> 8, ax = t1 & 255, sx1 = min(sx0 + 1, p.cols - 1);
+            const int a0 = r0[sx0], b0 = r0[sx1], a1 = r1[sx0], b1 = r1[sx1];
+            const int h0 = (a0 << 8) + ax * (b0 - a0);
+            const int h1 = (a1 << 8) + ax * (b1 - a1);
+            packed |= (uint32_t)(((h0 << 8) + ay * (h1 - h0) + 32768) >> 16) << (8 * k);
+        }
     }
     *reinterpret_cast<uint32_t*>(dst + (size_t)y * d.pitch + x) = packed;
 }
 
 // ---- B2 ------------------------------------------------------------------------------------------
-constexpr int FTW = 128, FTH = 32, FHX = 16, FSW = FTW + 2 * FHX, FSH = FTH + 8;  // pixel tile with 4-row halo
-constexpr int SCW = FTW + 2, SCH = FTH + 2;                                      // score tile with 1-px halo
+// FAST-9/16 + cornerScore + 3x3 NMS + border filter, one 128x32 output tile per block, in compacting phases so
+// that every phase runs with full warps (the one-thread-per-pixel form spent half its issue slots diverged):
+//   0  stage the tile (+16 px / 4 row halo) in shared memory with aligned 128-bit loads; clear the score grid
+//   1  SWAR pre-test, 4 pixels per thread on packed bytes: a 9-arc contains two ring pixels 90 degrees apart
+//      (one of N/S and one of E/W) that differ from the centre by more than t -> survivors to list 1
+//   2  segment test on list 1 (16-bit brighter / darker ring masks, run of 9 by shift-AND) -> corners to list 2
+//   3  cornerScore for list 2 -> dense score grid (1 px ring around the tile for the NMS)
+//   4  3x3 strict NMS + edgeThreshold border filter for the list-2 entries inside the tile -> bit mask
+constexpr int FTW = 128, FTH = 32, FHX = 16, FSW = FTW + 2 * FHX, FSH = FTH + 8;  // pixel tile with halo
+constexpr int SCW = FTW + 8, SCH = FTH + 2;  // score grid: x0-4 .. x0+131 (4-px groups), y0-1 .. y0+32
+constexpr int SCG = SCW / 4;
 
-// cornerScore of cv::FAST (9/16): max over the 16 arcs of 9 ring pixels of min |v - p| (one sign), minus 1.
-// With d = v - p:  min over an arc of d = v - max(p),  min of -d = min(p) - v, so the score needs the
-// sliding-window (length 9, circular) min and max of the raw ring pixels: doubling steps 2, 4, 8, then +1.
-// The subtraction from v is applied AFTER the min/max network on purpose: nvcc 12.9 folds
-// max(a, -b) chains into VIMNMX3 for sm_100a and loses the negation ("toolchain findings").
 __device__ __forceinline__ int fast9_ring_score(int v, const int (&p)[16], int thr) {
+    // cornerScore of cv::FAST (9/16): max over the 16 arcs of 9 ring pixels of min |v - p| (one sign), minus 1.
+    // With d = v - p:  min over an arc of d = v - max(p),  min of -d = min(p) - v, so the score needs the
+    // sliding-window (length 9, circular) min and max of the raw ring pixels: doubling steps 2, 4, 8, then +1.
+    // The subtraction from v is applied AFTER the min/max network on purpose: nvcc 12.9 folds
+    // max(a, -b) chains into VIMNMX3 for sm_100a and loses the negation ("toolchain findings").
     int n2[16], x2[16], n4[16], x4[16];
 #pragma unroll
     for (int i = 0; i < 16; i++) {
@@ -94,23 +117,18 @@ __device__ __forceinline__ int fast9_ring_score(int v, const int (&p)[16], int t
 }
 
 // ring of radius 3, OpenCV order; only the set of arcs matters
-__device__ __forceinline__ int fast9_score(const uint8_t* t, int thr) {
+__device__ __forceinline__ void fast9_load_ring(const uint8_t* t, int stride, int (&p)[16]) {
     constexpr int dxs[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1};
     constexpr int dys[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3};
-    const int v = t[0];
+#pragma unroll
+    for (int k = 0; k < 16; k++) p[k] = t[dys[k] * stride + dxs[k]];
+}
+
+__device__ __forceinline__ bool fast9_is_corner(int v, const int (&p)[16], int thr) {
     const int up = v + thr, dn = v - thr;
-    // opposite-pixel rejection: a 9-arc contains one pixel of every antipodal pair
-    {
-        const int a = t[3 * FSW], b = t[-3 * FSW];
-        if (!((a > up) | (b > up) | (a < dn) | (b < dn))) return 0;
-        const int c = t[3], e = t[-3];
-        if (!((c > up) | (e > up) | (c < dn) | (e < dn))) return 0;
-    }
-    int p[16];
     unsigned mh = 0, ml = 0;
 #pragma unroll
     for (int k = 0; k < 16; k++) {
-        p[k] = t[dys[k] * FSW + dxs[k]];
         mh |= (unsigned)(p[k] > up) << k;
         ml |= (unsigned)(p[k] < dn) << k;
     }
@@ -123,17 +141,29 @@ __device__ __forceinline__ int fast9_score(const uint8_t* t, int thr) {
     rl &= rl >> 4;            // runs of 8
     rh &= mh >> 8;
     rl &= ml >> 8;            // runs of 9
-    if ((rh | rl) == 0) return 0;
-    return fast9_ring_score(v, p, thr);
+    return (rh | rl) != 0;
+}
+
+// bytes of |a - b| that exceed thr -> bit 7 of the byte (SWAR; thr in [0, 255])
+__device__ __forceinline__ unsigned swar_absdiff_gt(unsigned a, unsigned b, unsigned k7, bool big) {
+    const unsigned d = __vabsdiffu4(a, b);
+    const unsigned s = (d & 0x7f7f7f7fu) + k7;  // no carry between bytes: both addends are <= 127
+    return big ? (s & d) : (s | d);             // thr >= 128: needs bit 7 of d as well; else bit 7 of d suffices
 }
 
 __global__ void __launch_bounds__(256) fast9_mask_kernel(SeqView s, OrbView o, int first, int l) {
     __shared__ __align__(16) uint8_t tile[FSH * FSW];
-    __shared__ uint8_t sc[SCH * SCW];
+    __shared__ __align__(16) uint8_t sc[SCH * SCW];
+    __shared__ uint16_t list1[SCH * SCW];
+    __shared__ uint16_t list2[SCH * SCW];
+    __shared__ unsigned mw[FTH * (FTW / 32)];
+    __shared__ int n1, n2;
     const int f = first + blockIdx.z;
     const OrbLevel& L = o.lv[l];
     const int x0 = blockIdx.x * FTW, y0 = blockIdx.y * FTH;
+    const int thr = o.fast_threshold;
     const uint8_t* img = level_ptr(s, o, f, l);
+    // ---- phase 0
     constexpr int VPR = FSW / 16;
     for (int v = threadIdx.x; v < FSH * VPR; v += blockDim.x) {
         const int r = v / VPR, cv = v - r * VPR;
@@ -143,46 +173,91 @@ __global__ void __launch_bounds__(256) fast9_mask_kernel(SeqView s, OrbView o, i
             val = __ldg(reinterpret_cast<const uint4*>(img + (size_t)gy * L.pitch + gx));
         *reinterpret_cast<uint4*>(tile + r * FSW + cv * 16) = val;
     }
+    for (int v = threadIdx.x; v < SCH * SCW / 16; v += blockDim.x) reinterpret_cast<uint4*>(sc)[v] = make_uint4(0, 0, 0, 0);
+    if (threadIdx.x < FTH * (FTW / 32)) mw[threadIdx.x] = 0;
+    if (threadIdx.x == 0) { n1 = 0; n2 = 0; }
     __syncthreads();
-    // scores on the output tile plus a 1-pixel ring (needed by the 3x3 NMS)
-    for (int i = threadIdx.x; i < SCH * SCW; i += blockDim.x) {
-        const int ry = i / SCW, rx = i - ry * SCW;
-        const int gx = x0 - 1 + rx, gy = y0 - 1 + ry;
-        int v = 0;
-        if (gx >= 3 && gx < L.cols - 3 && gy >= 3 && gy < L.rows - 3)
-            v = fast9_score(tile + (ry + 3) * FSW + (FHX - 1) + rx, o.fast_threshold);
-        sc[i] = (uint8_t)v;
+    // ---- phase 1: 4 pixels per thread
+    {
+        const bool big = thr >= 128;
+        const unsigned k7 = (unsigned)(big ? 255 - thr : 127 - thr) * 0x01010101u;
+        // valid score-grid columns: the FAST domain [3, cols-3) intersected with [x0-1, x0+129)
+        const int lo = max(3, x0 - 1), hi = min(L.cols - 3, x0 + FTW + 1);
+        for (int g = threadIdx.x; g < SCH * SCG; g += blockDim.x) {
+            const int ry = g / SCG, gc = g - ry * SCG;
+            const int gy = y0 - 1 + ry;
+            if ((unsigned)(gy - 3) >= (unsigned)(L.rows - 6)) continue;
+            const uint32_t* row = reinterpret_cast<const uint32_t*>(tile + (ry + 3) * FSW) + 3 + gc;
+            const unsigned w0 = row[0], wm = row[-1], wp = row[1];
+            const unsigned wn = row[-3 * (FSW / 4)], ws = row[3 * (FSW / 4)];
+            const unsigned we = __funnelshift_r(w0, wp, 24);  // pixels x+3 .. x+6
+            const unsigned ww = __funnelshift_r(wm, w0, 8);   // pixels x-3 .. x
+            unsigned m = (swar_absdiff_gt(wn, w0, k7, big) | swar_absdiff_gt(ws, w0, k7, big)) &
+                         (swar_absdiff_gt(we, w0, k7, big) | swar_absdiff_gt(ww, w0, k7, big)) & 0x80808080u;
+            if (m == 0) continue;
+            const int gxb = x0 - 4 + 4 * gc;
+            if (gxb < lo || gxb + 4 > hi) {
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if ((unsigned)(gxb + k - lo) >= (unsigned)(hi - lo)) m &= ~(0x80u << (8 * k));
+                if (m == 0) continue;
+            }
+            int pos = atomicAdd(&n1, __popc(m));
+            const int base = ry * SCW + 4 * gc;
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if (m & (0x80u << (8 * k))) list1[pos++] = (uint16_t)(base + k);
+        }
     }
     __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint32_t* mask = o.mask + (size_t)f * o.mask_words + L.moff;
-    for (int r = warp; r < FTH; r += 8) {
-        const int gy = y0 + r;
-        if (gy >= L.rows) break;
-#pragma unroll
-        for (int wx = 0; wx < FTW / 32; wx++) {
-            const int lx = wx * 32 + lane;
-            const int gx = x0 + lx;
-            const uint8_t* c = sc + (r + 1) * SCW + lx + 1;
-            const int v = c[0];
-            bool keep = v > 0 && gx >= kOrbEdge && gx < L.cols - kOrbEdge && gy >= kOrbEdge && gy < L.rows - kOrbEdge;
-            if (keep)
-                keep = v > c[-1] && v > c[1] && v > c[-SCW - 1] && v > c[-SCW] && v > c[-SCW + 1] && v > c[SCW - 1] &&
-                       v > c[SCW] && v > c[SCW + 1];
-            const unsigned word = __ballot_sync(0xffffffffu, keep);
-            const int wi = (x0 >> 5) + wx;
-            if (lane == 0 && wi < L.mwords) mask[(size_t)gy * L.mwords + wi] = word;
-        }
+    // ---- phase 2: segment test
+    const int c1 = n1;
+    for (int e = threadIdx.x; e < c1; e += blockDim.x) {
+        const int idx = list1[e];
+        const int ry = idx / SCW, cx = idx - ry * SCW;
+        const uint8_t* t = tile + (ry + 3) * FSW + (FHX - 4) + cx;
+        int p[16];
+        fast9_load_ring(t, FSW, p);
+        if (fast9_is_corner(t[0], p, thr)) list2[atomicAdd(&n2, 1)] = (uint16_t)idx;
+    }
+    __syncthreads();
+    // ---- phase 3: scores
+    const int c2 = n2;
+    for (int e = threadIdx.x; e < c2; e += blockDim.x) {
+        const int idx = list2[e];
+        const int ry = idx / SCW, cx = idx - ry * SCW;
+        const uint8_t* t = tile + (ry + 3) * FSW + (FHX - 4) + cx;
+        int p[16];
+        fast9_load_ring(t, FSW, p);
+        sc[idx] = (uint8_t)fast9_ring_score(t[0], p, thr);
+    }
+    __syncthreads();
+    // ---- phase 4: NMS + border filter
+    for (int e = threadIdx.x; e < c2; e += blockDim.x) {
+        const int idx = list2[e];
+        const int ry = idx / SCW, cx = idx - ry * SCW;
+        const int r = ry - 1, lx = cx - 4;
+        if ((unsigned)r >= (unsigned)FTH || (unsigned)lx >= (unsigned)FTW) continue;
+        const int gx = x0 + lx, gy = y0 + r;
+        if (gx < kOrbEdge || gx >= L.cols - kOrbEdge || gy < kOrbEdge || gy >= L.rows - kOrbEdge) continue;
+        const uint8_t* c = sc + idx;
+        const int v = c[0];
+        if (v > c[-1] && v > c[1] && v > c[-SCW - 1] && v > c[-SCW] && v > c[-SCW + 1] && v > c[SCW - 1] && v > c[SCW] &&
+            v > c[SCW + 1])
+            atomicOr(&mw[r * (FTW / 32) + (lx >> 5)], 1u << (lx & 31));
+    }
+    __syncthreads();
+    if (threadIdx.x < FTH * (FTW / 32)) {
+        const int gy = y0 + (threadIdx.x >> 2), wi = (x0 >> 5) + (threadIdx.x & 3);
+        if (gy < L.rows && wi < L.mwords)
+            (o.mask + (size_t)f * o.mask_words + L.moff)[(size_t)gy * L.mwords + wi] = mw[threadIdx.x];
     }
 }
 
 // global-memory version of the score for the list kernel (same arithmetic, pitch-strided)
 __device__ int fast9_score_global(const uint8_t* c, int pitch, int thr) {
-    constexpr int dxs[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1};
-    constexpr int dys[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3};
     int p[16];
-#pragma unroll
-    for (int k = 0; k < 16; k++) p[k] = c[dys[k] * pitch + dxs[k]];
+    fast9_load_ring(c, pitch, p);
     return fast9_ring_score(c[0], p, thr);
 }
 
@@ -302,41 +377,49 @@ __global__ void __launch_bounds__(256) orb_select_kernel(SeqView s, OrbView o, i
     if (threadIdx.x == 0) o.n_sel[f * kMaxLevels + l] = carry;
 }
 
-// ---- B4: warp per candidate ---------------------------------------------------------------------------
+// ---- B4: thread per candidate ---------------------------------------------------------------------------
+// HarrisResponses (orb.cpp): over the 7x7 block, Ix / Iy are 3x3 Sobel sums; a = sum Ix^2, b = sum Iy^2, c = sum IxIy
+// in int, then the float formula without FMA.  One thread walks its own 9x9 patch with a three-row sliding
+// window held in registers: per row the horizontal differences dx[c] = p[c+1] - p[c-1] and the smoothed values
+// sx[c] = p[c-1] + 2 p[c] + p[c+1], so Ix = dx(r-1) + 2 dx(r) + dx(r+1) and Iy = sx(r+1) - sx(r-1).
 __global__ void __launch_bounds__(128) harris_kernel(SeqView s, OrbView o, int first) {
     const int l = blockIdx.y, f = first + blockIdx.z;
     const OrbLevel& L = o.lv[l];
     const int n = o.n_sel[f * kMaxLevels + l];
-    const unsigned lane = lane_id();
     const uint8_t* img = level_ptr(s, o, f, l);
-    for (int i = blockIdx.x * 4 + (threadIdx.x >> 5); i < n; i += gridDim.x * 4) {
-    const uint32_t p = o.sxy[(size_t)f * o.cand_total + L.coff + i];
-    const int x = p & 0xffff, y = p >> 16;
-    int a = 0, b = 0, c = 0;
-    for (int k = lane; k < 49; k += 32) {
-        const int dy = k / 7 - 3, dx = k - (k / 7) * 7 - 3;
-        const uint8_t* q = img + (size_t)(y + dy) * L.pitch + (x + dx);
-        const int st = L.pitch;
-        const int Ix = ((int)q[1] - (int)q[-1]) * 2 + ((int)q[-st + 1] - (int)q[-st - 1]) + ((int)q[st + 1] - (int)q[st - 1]);
-        const int Iy = ((int)q[st] - (int)q[-st]) * 2 + ((int)q[st - 1] - (int)q[-st - 1]) + ((int)q[st + 1] - (int)q[-st + 1]);
-        a += Ix * Ix;
-        b += Iy * Iy;
-        c += Ix * Iy;
-    }
+    const float scale = 1.f / ((1 << 2) * 7 * 255.f);
+    const float scale4 = scale * scale * scale * scale;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t p = o.sxy[(size_t)f * o.cand_total + L.coff + i];
+        const int x = p & 0xffff, y = p >> 16;
+        const uint8_t* q = img + (size_t)(y - 4) * L.pitch + (x - 4);
+        int dx[3][7], sx[3][7];
+        int a = 0, b = 0, c = 0;
 #pragma unroll
-    for (int q = 16; q; q >>= 1) {
-        a += __shfl_xor_sync(0xffffffffu, a, q);
-        b += __shfl_xor_sync(0xffffffffu, b, q);
-        c += __shfl_xor_sync(0xffffffffu, c, q);
-    }
-    if (lane == 0) {
-        const float scale = 1.f / ((1 << 2) * 7 * 255.f);
-        const float scale4 = scale * scale * scale * scale;
+        for (int r = 0; r < 9; r++) {
+            int px[9];
+#pragma unroll
+            for (int k = 0; k < 9; k++) px[k] = q[k];
+            q += L.pitch;
+#pragma unroll
+            for (int k = 0; k < 7; k++) {
+                dx[r % 3][k] = px[k + 2] - px[k];
+                sx[r % 3][k] = px[k] + 2 * px[k + 1] + px[k + 2];
+            }
+            if (r >= 2) {  // rows r-2, r-1, r are complete: emit the block row centred on r-1
+#pragma unroll
+                for (int k = 0; k < 7; k++) {
+                    const int Ix = dx[(r - 2) % 3][k] + 2 * dx[(r - 1) % 3][k] + dx[r % 3][k];
+                    const int Iy = sx[r % 3][k] - sx[(r - 2) % 3][k];
+                    a += Ix * Ix;
+                    b += Iy * Iy;
+                    c += Ix * Iy;
+                }
+            }
+        }
         const float fa = (float)a, fb = (float)b, fc = (float)c;
         // ((float)a * b - (float)c * c - harris_k * ((float)a + b) * ((float)a + b)) * scale_sq_sq   (no FMA)
-        const float r = ((fa * fb - fc * fc) - (0.04f * (fa + fb)) * (fa + fb)) * scale4;
-        o.sresp[(size_t)f * o.cand_total + L.coff + i] = r;
-    }
+        o.sresp[(size_t)f * o.cand_total + L.coff + i] = ((fa * fb - fc * fc) - (0.04f * (fa + fb)) * (fa + fb)) * scale4;
     }
 }
 
@@ -438,16 +521,23 @@ __global__ void __launch_bounds__(256) orb_assemble_kernel(SeqView s, OrbView o,
 }
 
 // ---- B7 ----------------------------------------------------------------------------------------------------
-constexpr int GW = 64, GH = 16;
+// 7x7 sigma=2 separable float blur with OpenCV's rounding: row pass s = k0*S0, s = fma(k_j, S_j, s) (j = 1..6),
+// column pass s = k3*R0, s = fma(k_{3+j}, R_{+j} + R_{-j}, s) (j = 1..3), cvRound (half to even), saturate.
+// 64x32 output tile per block; bytes are staged once in shared memory, the row pass converts them with a
+// PRMT + FADD (0x4B000000 | byte is the float 2^23 + byte), four outputs per thread in both passes.
+constexpr int GW = 64, GH = 32, GIW = GW + 8, GIH = GH + 6;
 __device__ __forceinline__ int reflect101(int i, int n) {
     if (i < 0) i = -i;
     if (i >= n) i = 2 * n - 2 - i;
     return min(max(i, 0), n - 1);
 }
+__device__ __forceinline__ float byte_to_float(unsigned w, unsigned sel) {
+    return __uint_as_float(__byte_perm(w, 0x4B000000u, sel)) - 8388608.0f;
+}
 
 __global__ void __launch_bounds__(256) blur7_kernel(SeqView s, OrbView o, int first, int l) {
-    __shared__ uint8_t tin[(GH + 6) * (GW + 8)];
-    __shared__ float trow[(GH + 6) * GW];
+    __shared__ __align__(16) uint8_t tin[GIH * GIW];      // pixels x0-4 .. x0+GW+3, rows y0-3 .. y0+GH+2
+    __shared__ __align__(16) float trow[GIH * GW];
     const int f = first + blockIdx.z;
     const OrbLevel& L = o.lv[l];
     const uint8_t* img = level_ptr(s, o, f, l);
@@ -456,42 +546,76 @@ __global__ void __launch_bounds__(256) blur7_kernel(SeqView s, OrbView o, int fi
     // getGaussianKernel(7, 2, CV_32F) (bit patterns of the cv2 result; OpenCV computes exp(-x^2/8) normalised)
     const float k0 = __uint_as_float(0x3d8fafb1u), k1 = __uint_as_float(0x3e06387eu), k2 = __uint_as_float(0x3e434a39u),
                 k3 = __uint_as_float(0x3e5d4ae0u);
-    for (int i = threadIdx.x; i < (GH + 6) * (GW + 6); i += blockDim.x) {
-        const int r = i / (GW + 6), c = i - r * (GW + 6);
-        const int gy = reflect101(y0 - 3 + r, L.rows), gx = reflect101(x0 - 3 + c, L.cols);
-        tin[r * (GW + 8) + c] = img[(size_t)gy * L.pitch + gx];
+    const bool interior = x0 >= 4 && x0 + GW + 3 <= L.cols;  // no horizontal reflection inside the staged span
+    if (interior) {
+        for (int i = threadIdx.x; i < GIH * (GIW / 4); i += blockDim.x) {
+            const int r = i / (GIW / 4), c = i - r * (GIW / 4);
+            const int gy = reflect101(y0 - 3 + r, L.rows);
+            reinterpret_cast<uint32_t*>(tin)[i] =
+                __ldg(reinterpret_cast<const uint32_t*>(img + (size_t)gy * L.pitch + x0 - 4) + c);
+        }
+    } else {
+        for (int i = threadIdx.x; i < GIH * GIW; i += blockDim.x) {
+            const int r = i / GIW, c = i - r * GIW;
+            const int gy = reflect101(y0 - 3 + r, L.rows), gx = reflect101(x0 - 4 + c, L.cols);
+            tin[i] = img[(size_t)gy * L.pitch + gx];
+        }
     }
     __syncthreads();
-    // row pass: s = k0*S0; s = fma(k_j, S_j, s), j = 1..6
-    for (int i = threadIdx.x; i < (GH + 6) * GW; i += blockDim.x) {
-        const int r = i / GW, c = i - r * GW;
-        const uint8_t* p = tin + r * (GW + 8) + c;
-        float acc = k0 * (float)p[0];
-        acc = fmaf(k1, (float)p[1], acc);
-        acc = fmaf(k2, (float)p[2], acc);
-        acc = fmaf(k3, (float)p[3], acc);
-        acc = fmaf(k2, (float)p[4], acc);
-        acc = fmaf(k1, (float)p[5], acc);
-        acc = fmaf(k0, (float)p[6], acc);
-        trow[i] = acc;
-    }
-    __syncthreads();
-    // column pass: s = k3*R0; s = fma(k_{3+j}, R_{+j} + R_{-j}, s), j = 1..3; cvRound, saturate
-    const int tx = (threadIdx.x & 15) * 4, ty = threadIdx.x >> 4;
-    const int gy = y0 + ty;
-    if (gy >= L.rows) return;
-    uint32_t packed = 0;
+    for (int i = threadIdx.x; i < GIH * (GW / 4); i += blockDim.x) {
+        const int r = i / (GW / 4), c = i - r * (GW / 4);
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(tin + r * GIW) + c;  // pixels x-4 .. x+7 of 4 outputs at x
+        const unsigned w0 = w[0], w1 = w[1], w2 = w[2];
+        float p[10];  // pixels x-3 .. x+6
+        p[0] = byte_to_float(w0, 0x7441u);
+        p[1] = byte_to_float(w0, 0x7442u);
+        p[2] = byte_to_float(w0, 0x7443u);
+        p[3] = byte_to_float(w1, 0x7440u);
+        p[4] = byte_to_float(w1, 0x7441u);
+        p[5] = byte_to_float(w1, 0x7442u);
+        p[6] = byte_to_float(w1, 0x7443u);
+        p[7] = byte_to_float(w2, 0x7440u);
+        p[8] = byte_to_float(w2, 0x7441u);
+        p[9] = byte_to_float(w2, 0x7442u);
+        float4 acc;
+        float* a = &acc.x;
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-        const float* q = trow + (ty + 3) * GW + tx + k;
-        float acc = k3 * q[0];
-        acc = fmaf(k2, q[GW] + q[-GW], acc);
-        acc = fmaf(k1, q[2 * GW] + q[-2 * GW], acc);
-        acc = fmaf(k0, q[3 * GW] + q[-3 * GW], acc);
-        const int v = min(max(__float2int_rn(acc), 0), 255);
-        packed |= (uint32_t)v << (8 * k);
+        for (int k = 0; k < 4; k++) {
+            float v = k0 * p[k];
+            v = fmaf(k1, p[k + 1], v);
+            v = fmaf(k2, p[k + 2], v);
+            v = fmaf(k3, p[k + 3], v);
+            v = fmaf(k2, p[k + 4], v);
+            v = fmaf(k1, p[k + 5], v);
+            v = fmaf(k0, p[k + 6], v);
+            a[k] = v;
+        }
+        reinterpret_cast<float4*>(trow)[i] = acc;
     }
-    if (x0 + tx < L.pitch) *reinterpret_cast<uint32_t*>(out + (size_t)gy * L.pitch + x0 + tx) = packed;
+    __syncthreads();
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+#pragma unroll
+    for (int pass = 0; pass < GH / 16; pass++) {
+        const int r = ty + 16 * pass;
+        const int gy = y0 + r;
+        if (gy >= L.rows) break;
+        const float4* q = reinterpret_cast<const float4*>(trow) + (r + 3) * (GW / 4) + tx;
+        const float4 c0 = q[0], a1 = q[GW / 4], b1 = q[-(GW / 4)], a2 = q[2 * (GW / 4)], b2 = q[-2 * (GW / 4)],
+                     a3 = q[3 * (GW / 4)], b3 = q[-3 * (GW / 4)];
+        const float* pc = &c0.x;
+        const float *pa1 = &a1.x, *pb1 = &b1.x, *pa2 = &a2.x, *pb2 = &b2.x, *pa3 = &a3.x, *pb3 = &b3.x;
+        uint32_t packed = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            float acc = k3 * pc[k];
+            acc = fmaf(k2, pa1[k] + pb1[k], acc);
+            acc = fmaf(k1, pa2[k] + pb2[k], acc);
+            acc = fmaf(k0, pa3[k] + pb3[k], acc);
+            const int v = min(max(__float2int_rn(acc), 0), 255);
+            packed |= (uint32_t)v << (8 * k);
+        }
+        if (x0 + tx * 4 < L.pitch) *reinterpret_cast<uint32_t*>(out + (size_t)gy * L.pitch + x0 + tx * 4) = packed;
+    }
 }
 
 // ---- B6 + B8: warp per keypoint ----------------------------------------------------------------------------
@@ -515,31 +639,42 @@ __device__ __forceinline__ float cv_fast_atan2(float y, float x) {
     return a;
 }
 
-__global__ void __launch_bounds__(128) orb_describe_kernel(SeqView s, OrbView o, int first) {
+// One warp owns 32 consecutive keypoints of a frame.  Phase A: per keypoint, the 31 lanes of a disc row set sum
+// their column of the unblurred level (integer moments, any order is exact) and lane j keeps keypoint j's angle.
+// Phase B: every lane does the double-precision cos / sin of ITS keypoint (once per keypoint instead of 32
+// redundant copies).  Phase C: per keypoint, lane k builds descriptor byte k from 8 rotated pattern pairs.
+__global__ void __launch_bounds__(128) orb_describe_kernel(SeqView s, OrbView o, int first, const float2* __restrict__ patf) {
     const int f = first + blockIdx.y;
     const int n = s.n_kp[f];
-    const int kpi = blockIdx.x * 4 + (threadIdx.x >> 5);
-    if (kpi >= n) return;
-    const unsigned lane = lane_id();
-    const int l = o.octave[(size_t)f * s.cap_kp + kpi];
-    const uint32_t p = o.lxy[(size_t)f * s.cap_kp + kpi];
-    const int x = p & 0xffff, y = p >> 16;
-    const OrbLevel& L = o.lv[l];
-    const uint8_t* img = level_ptr(s, o, f, l);
-    const uint8_t* bl = blur_ptr(s, o, f, l);
+    const int base = (blockIdx.x * 4 + (threadIdx.x >> 5)) * 32;
+    if (base >= n) return;
+    const int lane = lane_id();
+    const int mine = base + lane;
+    const bool have = mine < n;
+    const size_t kbase = (size_t)f * s.cap_kp;
+    const int my_l = have ? o.octave[kbase + mine] : 0;
+    const uint32_t my_p = have ? o.lxy[kbase + mine] : 0u;
+    const int cnt = min(32, n - base);
     // IC_Angle on the unblurred level: umax-limited disc of radius 15
     constexpr int umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
-    int m01 = 0, m10 = 0;
-    {
-        const int u = (int)lane - kOrbHalfPatch;  // lanes 0..30 -> u = -15..15
+    float my_angle = 0.f;
+    const int u = lane - kOrbHalfPatch;  // lanes 0..30 -> u = -15..15
+    const int au = abs(u);
+    for (int j = 0; j < cnt; j++) {
+        const int l = __shfl_sync(0xffffffffu, my_l, j);
+        const uint32_t p = __shfl_sync(0xffffffffu, my_p, j);
+        const int x = p & 0xffff, y = p >> 16;
+        const int pitch = o.lv[l].pitch;
+        const uint8_t* img = level_ptr(s, o, f, l);
+        int m01 = 0, m10 = 0;
         if (u <= kOrbHalfPatch) {
-            const uint8_t* c = img + (size_t)y * L.pitch + x + u;
+            const uint8_t* c = img + (size_t)y * pitch + x + u;
             int col = c[0];  // v = 0 row
             int vsum = 0;
 #pragma unroll
             for (int v = 1; v <= kOrbHalfPatch; v++) {
-                if (abs(u) <= umax[v]) {
-                    const int below = c[v * L.pitch], above = c[-v * L.pitch];
+                if (au <= umax[v]) {
+                    const int below = c[v * pitch], above = c[-v * pitch];
                     col += below + above;
                     vsum += v * (below - above);
                 }
@@ -547,34 +682,46 @@ __global__ void __launch_bounds__(128) orb_describe_kernel(SeqView s, OrbView o,
             m10 = u * col;
             m01 = vsum;
         }
-    }
 #pragma unroll
-    for (int q = 16; q; q >>= 1) {
-        m01 += __shfl_xor_sync(0xffffffffu, m01, q);
-        m10 += __shfl_xor_sync(0xffffffffu, m10, q);
+        for (int q = 16; q; q >>= 1) {
+            m01 += __shfl_xor_sync(0xffffffffu, m01, q);
+            m10 += __shfl_xor_sync(0xffffffffu, m10, q);
+        }
+        if (lane == j) my_angle = cv_fast_atan2((float)m01, (float)m10);
     }
-    const float angle = cv_fast_atan2((float)m01, (float)m10);
-    if (lane == 0) s.kps[(size_t)f * s.cap_kp + kpi].angle = angle;
     // rBRIEF: a = (float)cos(angle_rad), b = (float)sin(angle_rad) in double, narrowed
-    const float ar = angle * (float)(3.14159265358979323846 / 180.f);
-    const float a = (float)cos((double)ar), b = (float)sin((double)ar);
-    const uint8_t* cb = bl + (size_t)y * L.pitch + x;
-    const int8_t* pat = o.pattern + lane * 32;  // 16 points (x, y) per lane
-    unsigned byte = 0;
-#pragma unroll
-    for (int k = 0; k < 8; k++) {
-        const float x0 = (float)pat[4 * k + 0], y0 = (float)pat[4 * k + 1];
-        const float x1 = (float)pat[4 * k + 2], y1 = (float)pat[4 * k + 3];
-        const int ix0 = __float2int_rn(x0 * a - y0 * b), iy0 = __float2int_rn(x0 * b + y0 * a);
-        const int ix1 = __float2int_rn(x1 * a - y1 * b), iy1 = __float2int_rn(x1 * b + y1 * a);
-        const int t0 = cb[iy0 * L.pitch + ix0], t1 = cb[iy1 * L.pitch + ix1];
-        byte |= (unsigned)(t0 < t1) << k;
+    float my_a = 1.f, my_b = 0.f;
+    if (have) {
+        s.kps[kbase + mine].angle = my_angle;
+        const float ar = my_angle * (float)(3.14159265358979323846 / 180.f);
+        my_a = (float)cos((double)ar);
+        my_b = (float)sin((double)ar);
     }
-    // pack 4 lanes' bytes into one 32-bit word
-    unsigned w = byte << (8 * (lane & 3));
-    w |= __shfl_xor_sync(0xffffffffu, w, 1);
-    w |= __shfl_xor_sync(0xffffffffu, w, 2);
-    if ((lane & 3) == 0) s.desc[((size_t)f * s.cap_kp + kpi) * s.desc_words + (lane >> 2)] = w;
+    float2 pp[16];  // this lane's 16 pattern points (8 pairs -> descriptor byte `lane`), the same for every keypoint
+#pragma unroll
+    for (int k = 0; k < 16; k++) pp[k] = __ldg(patf + lane * 16 + k);
+    for (int j = 0; j < cnt; j++) {
+        const int l = __shfl_sync(0xffffffffu, my_l, j);
+        const uint32_t p = __shfl_sync(0xffffffffu, my_p, j);
+        const float a = __shfl_sync(0xffffffffu, my_a, j), b = __shfl_sync(0xffffffffu, my_b, j);
+        const int x = p & 0xffff, y = p >> 16;
+        const int pitch = o.lv[l].pitch;
+        const uint8_t* cb = blur_ptr(s, o, f, l) + (size_t)y * pitch + x;
+        unsigned byte = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const float2 p0 = pp[2 * k], p1 = pp[2 * k + 1];
+            const int ix0 = __float2int_rn(p0.x * a - p0.y * b), iy0 = __float2int_rn(p0.x * b + p0.y * a);
+            const int ix1 = __float2int_rn(p1.x * a - p1.y * b), iy1 = __float2int_rn(p1.x * b + p1.y * a);
+            const int t0 = cb[iy0 * pitch + ix0], t1 = cb[iy1 * pitch + ix1];
+            byte |= (unsigned)(t0 < t1) << k;
+        }
+        // pack 4 lanes' bytes into one 32-bit word
+        unsigned w = byte << (8 * (lane & 3));
+        w |= __shfl_xor_sync(0xffffffffu, w, 1);
+        w |= __shfl_xor_sync(0xffffffffu, w, 2);
+        if ((lane & 3) == 0) s.desc[(kbase + base + j) * s.desc_words + (lane >> 2)] = w;
+    }
 }
 
 }  // namespace
@@ -592,7 +739,7 @@ int launch_orb_extract(const SeqView& s, const OrbView& o, int first, int n, cud
         max_capc = max(max_capc, o.lv[l].capc);
     }
     for (int l = 1; l < o.nlevels; l++) {
-        dim3 grid((o.lv[l].pitch + 63) / 64, (o.lv[l].rows + 15) / 16, n);
+        dim3 grid((o.lv[l].pitch + 127) / 128, (o.lv[l].rows + 7) / 8, n);
         SLAM_KERNEL("pyr_down", st, pyr_down_kernel<<<grid, 256, 0, st>>>(s, o, first, l));
         launches++;
     }
@@ -605,7 +752,7 @@ int launch_orb_extract(const SeqView& s, const OrbView& o, int first, int n, cud
                 orb_select_kernel<<<dim3(o.nlevels, n), 256, (max_rows + 1) * sizeof(int), st>>>(s, o, first));
     int max_quota = 1;
     for (int l = 0; l < o.nlevels; l++) max_quota = max(max_quota, o.lv[l].quota);
-    SLAM_KERNEL("harris", st, harris_kernel<<<dim3((2 * max_quota + 3) / 4, o.nlevels, n), 128, 0, st>>>(s, o, first));
+    SLAM_KERNEL("harris", st, harris_kernel<<<dim3((2 * max_quota + 127) / 128, o.nlevels, n), 128, 0, st>>>(s, o, first));
     const int retain_cap = 12 * 1024;
     SLAM_KERNEL("orb_retain", st,
                 orb_retain_kernel<<<dim3(o.nlevels, n), 256, retain_cap * sizeof(float), st>>>(s, o, first, retain_cap));
@@ -616,7 +763,8 @@ int launch_orb_extract(const SeqView& s, const OrbView& o, int first, int n, cud
         SLAM_KERNEL("blur7", st, blur7_kernel<<<grid, 256, 0, st>>>(s, o, first, l));
         launches++;
     }
-    SLAM_KERNEL("orb_describe", st, orb_describe_kernel<<<dim3((s.cap_kp + 3) / 4, n), 128, 0, st>>>(s, o, first));
+    SLAM_KERNEL("orb_describe", st,
+                orb_describe_kernel<<<dim3((s.cap_kp + 127) / 128, n), 128, 0, st>>>(s, o, first, o.patf));
     launches++;
     return launches;
 }

@@ -17,9 +17,10 @@ struct OrbLevel {
     int capc;        // candidate capacity
     int quota;       // nfeaturesPerLevel
     float scale;     // (float)pow(scaleFactor, level)
-    // INTER_LINEAR_EXACT tables for producing this level from level-1 (device pointers; unused for level 0)
-    const int* x0; const int* x1; const int* ax;
-    const int* y0; const int* y1; const int* ay;
+    // INTER_LINEAR_EXACT tables for producing this level from level-1 (device pointers; unused for level 0):
+    // per destination column / row, (first source index << 8) | 8.8 weight of the second tap.  The second tap
+    // is index + 1 (clamped); at the clamped ends OpenCV's weight is 0, so the clamp never changes a result.
+    const uint32_t* xt; const uint32_t* yt;
 };
 
 struct OrbView {
@@ -44,6 +45,7 @@ struct OrbView {
     int* octave;          // [F][cap_kp]
     uint32_t* lxy;        // [F][cap_kp]      level coordinates of the final keypoints
     const int8_t* pattern;  // [512][2] rBRIEF sampling points
+    const float2* patf;     // the same points as float2 (x, y)
 };
 
 int launch_orb_extract(const SeqView& s, const OrbView& o, int first, int n, cudaStream_t st);
