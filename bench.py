@@ -267,13 +267,11 @@ def run_ours(args, rank, world, local_rank):
         seq.match_consecutive(mat, 0, B - 1, with_keypoints=with_kp)
 
     def step_e2e():
-        seq.upload_ptr(host_frames.data_ptr(), B)
-        seq.extract(det, 0, B)
-        seq.match_consecutive(mat, 0, B - 1, with_keypoints=with_kp)
-        # results a caller of detectAndCompute/match receives: counts first, then only the matches that
-        # exist (GoodMatchesCount per pair) and the keypoint / descriptor blocks
-        seq.download_ptrs(0, B, h_kps.data_ptr(), h_desc.data_ptr(), None, h_counts.data_ptr())
-        seq.download_ptrs(0, B, None, None, h_matches.data_ptr(), None)
+        # the public host-side call: pinned host frames in, keypoints / descriptors / matches / counts out
+        # (upload, extract, match and download pipelined in chunks over the copy engines)
+        seq.process_ptrs(det, mat, host_frames.data_ptr(), B, chunk=args.chunk, with_keypoints=with_kp,
+                         kps_ptr=h_kps.data_ptr(), desc_ptr=h_desc.data_ptr(), matches_ptr=h_matches.data_ptr(),
+                         counts_ptr=h_counts.data_ptr())
         ctx.synchronize()
         return int(h_counts[:, 0].sum()), int(h_counts[:, 1].sum())
 
@@ -371,7 +369,8 @@ def run_ours(args, rank, world, local_rank):
                        "l2": f"inputs larger than L2: {B * ROWS * COLS / 1e6:.0f} MB of frames per step vs 126 MB L2"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(B * ROWS * COLS),
                     "d2h_bytes_per_step": int(h_kps.nbytes + h_desc.nbytes + h_matches.nbytes + h_counts.nbytes),
-                    "ms_per_step": e2e_ms / args.steps, "keypoints_last_step": tot[0], "matches_last_step": tot[1]},
+                    "ms_per_step": e2e_ms / args.steps, "keypoints_last_step": tot[0], "matches_last_step": tot[1],
+                    "pipeline_chunk_frames": args.chunk},
             "gpu_launches": int(launches),
             "roofline": roofline,
             "kernels": kernels,
@@ -411,6 +410,7 @@ def main():
                          "reference: the reference repo's own hand-written detector/matcher")
     ap.add_argument("--frames", type=int, default=512, help="frames per GPU per step")
     ap.add_argument("--max-keypoints", type=int, default=2560)
+    ap.add_argument("--chunk", type=int, default=128, help="frames per pipeline stage of the end-to-end leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -201,6 +201,15 @@ int slamcu_sequence_matches(slamcu_sequence* seq, int f, slamcu_dmatch* matches,
 int slamcu_sequence_download(slamcu_sequence* seq, int first, int n, slamcu_keypoint* keypoints, uint8_t* descriptors,
                              slamcu_dmatch* matches, int32_t* counts4);
 
+/* The whole per-frame loop for n host frames (the SLAMModel wiring the reference sketches at
+ * include/slam/model/model.hpp:20-27): upload -> detectAndCompute -> match(f, f+1) -> download, software-pipelined
+ * in chunks of `chunk` frames (<= 0: 64) over separate H2D / compute / D2H streams.  host_frames: n frames of
+ * rows x stride bytes (pinned for overlap); outputs as in slamcu_sequence_download (any may be NULL; pinned).
+ * Asynchronous: slamcu_synchronize() waits for the downloads too. */
+int slamcu_sequence_process(slamcu_sequence* seq, slamcu_detector* det, slamcu_matcher* m, const uint8_t* host_frames,
+                            int stride, int n, int chunk, int with_keypoints, slamcu_keypoint* keypoints,
+                            uint8_t* descriptors, slamcu_dmatch* matches, int32_t* counts4);
+
 /* ---- image preparation (src/preprocessing) ---------------------------------------------------- */
 /* cv::cvtColor(BGR2GRAY) (preprocessor.cpp:136): gray = (3735 B + 19235 G + 9798 R + 16384) >> 15. */
 int slamcu_bgr_to_gray(slamcu_context* ctx, const uint8_t* bgr, int rows, int cols, int stride, uint8_t* gray,

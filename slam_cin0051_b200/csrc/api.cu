@@ -74,6 +74,9 @@ struct slamcu_context {
     // scratch reused by the preparation / ransac entry points
     void* scratch = nullptr;
     size_t scratch_bytes = 0;
+    // copy engines of the pipelined sequence path: H2D and D2H run on their own streams
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    std::vector<cudaEvent_t> events;
 };
 
 namespace {
@@ -129,12 +132,18 @@ int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
 }  // namespace
 
+struct ProfGuard {
+    explicit ProfGuard(slamcu_context* ctx) { slamcu::g_prof = ctx->profiling ? &ctx->prof : nullptr; }
+    ~ProfGuard() { slamcu::g_prof = nullptr; }
+};
+
 struct slamcu_sequence {
     slamcu_context* ctx = nullptr;
     SeqView v{};
     int max_frames = 0;
     unsigned long long* sort_keys = nullptr;  // [F][cap_kp]
     int* h_counts = nullptr;                  // pinned [F][4]
+    uint8_t* stage = nullptr;                 // [F][rows][cols] dense landing zone of linear H2D copies (lazy)
     std::vector<void*> owned;
     // ORB-mode working set, allocated on first use and keyed by the detector parameters
     bool has_orb = false;
@@ -225,6 +234,9 @@ void slamcu_destroy(slamcu_context* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->scratch) cudaFree(ctx->scratch);
+    if (ctx->s_in) { cudaStreamSynchronize(ctx->s_in); cudaStreamDestroy(ctx->s_in); }
+    if (ctx->s_out) { cudaStreamSynchronize(ctx->s_out); cudaStreamDestroy(ctx->s_out); }
+    for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -363,8 +375,40 @@ void slamcu_sequence_destroy(slamcu_sequence* s) {
     cudaStreamSynchronize(s->ctx->stream);
     for (void* p : s->owned) cudaFree(p);
     for (void* p : s->orb_owned) cudaFree(p);
+    if (s->stage) cudaFree(s->stage);
     if (s->h_counts) cudaFreeHost(s->h_counts);
     delete s;
+}
+
+// Host frames -> the pitched frame store.  Dense frames (stride == cols) take one linear copy into a staging
+// block plus a re-pitch kernel; a strided cudaMemcpy2D is kept only for other strides.  `copy_stream` carries
+// the copy, `kernel_stream` the re-pitch kernel (the caller orders the two).
+static int seq_upload_async(slamcu_sequence* s, int first, int n, const uint8_t* host, int stride, cudaStream_t copy_stream,
+                            bool* needs_repitch) {
+    slamcu_context* ctx = s->ctx;
+    const SeqView& v = s->v;
+    *needs_repitch = false;
+    if (stride == v.pitch) {
+        CU(ctx, cudaMemcpyAsync(v.img + (size_t)first * v.frame_bytes, host, (size_t)n * v.frame_bytes, cudaMemcpyHostToDevice,
+                                copy_stream));
+        return SLAMCU_OK;
+    }
+    if (stride == v.cols) {
+        if (!s->stage) CU(ctx, cudaMalloc(reinterpret_cast<void**>(&s->stage), (size_t)s->max_frames * v.rows * v.cols));
+        const size_t fb = (size_t)v.rows * v.cols;
+        CU(ctx, cudaMemcpyAsync(s->stage + (size_t)first * fb, host, (size_t)n * fb, cudaMemcpyHostToDevice, copy_stream));
+        *needs_repitch = true;
+        return SLAMCU_OK;
+    }
+    CU(ctx, cudaMemcpy2DAsync(v.img + (size_t)first * v.frame_bytes, v.pitch, host, stride, v.cols, (size_t)v.rows * n,
+                              cudaMemcpyHostToDevice, copy_stream));
+    return SLAMCU_OK;
+}
+
+static void seq_repitch(slamcu_sequence* s, int first, int n, cudaStream_t st) {
+    const SeqView& v = s->v;
+    s->ctx->launches += launch_repitch(s->stage + (size_t)first * v.rows * v.cols, v.cols, v.img + (size_t)first * v.frame_bytes,
+                                       v.pitch, v.cols, (long long)n * v.rows, st);
 }
 
 int slamcu_sequence_upload(slamcu_sequence* s, int first, int n, const uint8_t* host, int stride) {
@@ -373,8 +417,15 @@ int slamcu_sequence_upload(slamcu_sequence* s, int first, int n, const uint8_t* 
     if (first < 0 || n < 0 || first + n > s->max_frames || stride < s->v.cols)
         return fail(ctx, SLAMCU_INVALID_ARGUMENT, "upload range [%d,%d) / stride %d invalid", first, first + n, stride);
     if (n == 0) return SLAMCU_OK;
-    CU(ctx, cudaMemcpy2DAsync(s->v.img + (size_t)first * s->v.frame_bytes, s->v.pitch, host, stride, s->v.cols,
-                              (size_t)s->v.rows * n, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaSetDevice(ctx->device));
+    bool rp = false;
+    int rc = seq_upload_async(s, first, n, host, stride, ctx->stream, &rp);
+    if (rc != SLAMCU_OK) return rc;
+    if (rp) {
+        ProfGuard pg(ctx);
+        seq_repitch(s, first, n, ctx->stream);
+        return check_launch(ctx, "repitch");
+    }
     return SLAMCU_OK;
 }
 
@@ -385,11 +436,6 @@ int slamcu_sequence_frames_device(slamcu_sequence* s, void** dptr, int* pitch, i
     if (frame_bytes) *frame_bytes = (int64_t)s->v.frame_bytes;
     return SLAMCU_OK;
 }
-
-struct ProfGuard {
-    explicit ProfGuard(slamcu_context* ctx) { slamcu::g_prof = ctx->profiling ? &ctx->prof : nullptr; }
-    ~ProfGuard() { slamcu::g_prof = nullptr; }
-};
 
 static int seq_detect(slamcu_sequence* s, slamcu_detector* det, int first, int n, bool raw_probe) {
     slamcu_context* ctx = s->ctx;
@@ -664,6 +710,20 @@ int slamcu_sequence_matches(slamcu_sequence* s, int f, slamcu_dmatch* matches, i
     return SLAMCU_OK;
 }
 
+// descriptor block of frames [first, first+n) -> host [n][cap_kp][desc_bytes]; one linear copy when the HBM rows
+// are not padded (a 2-D copy of 32-byte rows runs at less than half the link rate)
+static int seq_download_desc(slamcu_sequence* s, int first, int n, uint8_t* desc, cudaStream_t st) {
+    slamcu_context* ctx = s->ctx;
+    const SeqView& v = s->v;
+    const uint32_t* src = v.desc + (size_t)first * v.cap_kp * v.desc_words;
+    if (v.desc_bytes == v.desc_words * 4)
+        CU(ctx, cudaMemcpyAsync(desc, src, (size_t)n * v.cap_kp * v.desc_bytes, cudaMemcpyDeviceToHost, st));
+    else
+        CU(ctx, cudaMemcpy2DAsync(desc, v.desc_bytes, src, v.desc_words * 4, v.desc_bytes, (size_t)n * v.cap_kp,
+                                  cudaMemcpyDeviceToHost, st));
+    return SLAMCU_OK;
+}
+
 int slamcu_sequence_download(slamcu_sequence* s, int first, int n, slamcu_keypoint* kps, uint8_t* desc, slamcu_dmatch* matches,
                              int32_t* counts4) {
     if (!s) return SLAMCU_INVALID_ARGUMENT;
@@ -674,9 +734,10 @@ int slamcu_sequence_download(slamcu_sequence* s, int first, int n, slamcu_keypoi
     if (kps)
         CU(ctx, cudaMemcpyAsync(kps, v.kps + (size_t)first * v.cap_kp, (size_t)n * v.cap_kp * sizeof(slamcu_keypoint),
                                 cudaMemcpyDeviceToHost, ctx->stream));
-    if (desc)
-        CU(ctx, cudaMemcpy2DAsync(desc, v.desc_bytes, v.desc + (size_t)first * v.cap_kp * v.desc_words, v.desc_words * 4,
-                                  v.desc_bytes, (size_t)n * v.cap_kp, cudaMemcpyDeviceToHost, ctx->stream));
+    if (desc) {
+        int rc = seq_download_desc(s, first, n, desc, ctx->stream);
+        if (rc != SLAMCU_OK) return rc;
+    }
     if (matches)
         CU(ctx, cudaMemcpyAsync(matches, v.matches + (size_t)first * v.cap_kp, (size_t)n * v.cap_kp * sizeof(slamcu_dmatch),
                                 cudaMemcpyDeviceToHost, ctx->stream));
@@ -687,6 +748,86 @@ int slamcu_sequence_download(slamcu_sequence* s, int first, int n, slamcu_keypoi
         CU(ctx, cudaMemcpy2DAsync(counts4 + 2, 16, v.n_raw + first, 4, 4, n, cudaMemcpyDeviceToHost, ctx->stream));
         CU(ctx, cudaMemcpy2DAsync(counts4 + 3, 16, v.status + first, 4, 4, n, cudaMemcpyDeviceToHost, ctx->stream));
     }
+    return SLAMCU_OK;
+}
+
+static int ctx_pipeline_resources(slamcu_context* ctx, size_t n_events) {
+    if (!ctx->s_in) CU(ctx, cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
+    if (!ctx->s_out) CU(ctx, cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
+    while (ctx->events.size() < n_events) {
+        cudaEvent_t e;
+        CU(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->events.push_back(e);
+    }
+    return SLAMCU_OK;
+}
+
+// The intended SLAMModel loop of the reference (include/slam/model/model.hpp:20-27: Preprocessor -> FeatureDetector
+// -> FeatureMatcher), for n frames held in host memory: upload, detectAndCompute, match(f, f+1), download --
+// software-pipelined by chunks of `chunk` frames over three streams (H2D copy engine, compute, D2H copy engine) so
+// the PCIe transfers hide behind the kernels.
+int slamcu_sequence_process(slamcu_sequence* s, slamcu_detector* det, slamcu_matcher* m, const uint8_t* host_frames,
+                            int stride, int n, int chunk, int with_keypoints, slamcu_keypoint* kps, uint8_t* desc,
+                            slamcu_dmatch* matches, int32_t* counts4) {
+    if (!s || !det || !m || !host_frames || s->ctx != det->ctx || s->ctx != m->ctx) return SLAMCU_INVALID_ARGUMENT;
+    slamcu_context* ctx = s->ctx;
+    if (n < 0 || n > s->max_frames || stride < s->v.cols) return fail(ctx, SLAMCU_INVALID_ARGUMENT, "bad frame count / stride");
+    if (m->distance_type != SLAMCU_DISTANCE_HAMMING)
+        return fail(ctx, SLAMCU_UNSUPPORTED, "L2 distance requires float descriptors. Use the float overload.");
+    if (n == 0) return SLAMCU_OK;
+    if (chunk <= 0) chunk = 64;
+    CU(ctx, cudaSetDevice(ctx->device));
+    const int n_chunks = (n + chunk - 1) / chunk;
+    int rc = ctx_pipeline_resources(ctx, (size_t)2 * n_chunks + 2);
+    if (rc != SLAMCU_OK) return rc;
+    const SeqView& v = s->v;
+    cudaStream_t cs = ctx->stream;
+    // everything already queued on the compute stream (e.g. the previous call) precedes the first copy
+    cudaEvent_t ev_start = ctx->events[2 * n_chunks];
+    CU(ctx, cudaEventRecord(ev_start, cs));
+    CU(ctx, cudaStreamWaitEvent(ctx->s_in, ev_start, 0));
+    CU(ctx, cudaStreamWaitEvent(ctx->s_out, ev_start, 0));
+    for (int c = 0; c < n_chunks; c++) {
+        const int f0 = c * chunk, cnt = std::min(chunk, n - f0);
+        bool rp = false;
+        rc = seq_upload_async(s, f0, cnt, host_frames + (size_t)f0 * v.rows * stride, stride, ctx->s_in, &rp);
+        if (rc != SLAMCU_OK) return rc;
+        CU(ctx, cudaEventRecord(ctx->events[2 * c], ctx->s_in));
+        CU(ctx, cudaStreamWaitEvent(cs, ctx->events[2 * c], 0));
+        if (rp) {
+            ProfGuard pg(ctx);
+            seq_repitch(s, f0, cnt, cs);
+        }
+        rc = slamcu_sequence_extract(s, det, f0, cnt);
+        if (rc != SLAMCU_OK) return rc;
+        const int p0 = std::max(f0 - 1, 0), np = f0 + cnt - 1 - p0;  // pairs (p, p+1) completed by this chunk
+        if (np > 0) {
+            rc = slamcu_sequence_match(s, m, p0, np, with_keypoints);
+            if (rc != SLAMCU_OK) return rc;
+        }
+        CU(ctx, cudaEventRecord(ctx->events[2 * c + 1], cs));
+        CU(ctx, cudaStreamWaitEvent(ctx->s_out, ctx->events[2 * c + 1], 0));
+        if (kps)
+            CU(ctx, cudaMemcpyAsync(kps + (size_t)f0 * v.cap_kp, v.kps + (size_t)f0 * v.cap_kp,
+                                    (size_t)cnt * v.cap_kp * sizeof(slamcu_keypoint), cudaMemcpyDeviceToHost, ctx->s_out));
+        if (desc) {
+            rc = seq_download_desc(s, f0, cnt, desc + (size_t)f0 * v.cap_kp * v.desc_bytes, ctx->s_out);
+            if (rc != SLAMCU_OK) return rc;
+        }
+        if (matches && np > 0)
+            CU(ctx, cudaMemcpyAsync(matches + (size_t)p0 * v.cap_kp, v.matches + (size_t)p0 * v.cap_kp,
+                                    (size_t)np * v.cap_kp * sizeof(slamcu_dmatch), cudaMemcpyDeviceToHost, ctx->s_out));
+    }
+    if (counts4) {
+        CU(ctx, cudaMemcpy2DAsync(counts4 + 0, 16, v.n_kp, 4, 4, n, cudaMemcpyDeviceToHost, ctx->s_out));
+        CU(ctx, cudaMemcpy2DAsync(counts4 + 1, 16, v.n_match, 4, 4, n, cudaMemcpyDeviceToHost, ctx->s_out));
+        CU(ctx, cudaMemcpy2DAsync(counts4 + 2, 16, v.n_raw, 4, 4, n, cudaMemcpyDeviceToHost, ctx->s_out));
+        CU(ctx, cudaMemcpy2DAsync(counts4 + 3, 16, v.status, 4, 4, n, cudaMemcpyDeviceToHost, ctx->s_out));
+    }
+    // join: slamcu_synchronize() on the context now also covers the downloads
+    cudaEvent_t ev_end = ctx->events[2 * n_chunks + 1];
+    CU(ctx, cudaEventRecord(ev_end, ctx->s_out));
+    CU(ctx, cudaStreamWaitEvent(cs, ev_end, 0));
     return SLAMCU_OK;
 }
 

@@ -35,6 +35,29 @@ __device__ __forceinline__ void top2_update(Top2& t, int d, int j) {  // feature
     }
 }
 
+// Packed running top-2 for the penalty-free paths: key = (distance << 20) | train index, so integer order on the
+// key is the reference's (distance, lowest index first) order; a tie with the best lands in second, exactly
+// like the strict-< updateBestMatches (feature_matcher.cpp:132-141).  Needs nt <= 2^20 and distance < 2^11.
+constexpr int kKeyShift = 20;
+__device__ __forceinline__ void top2_update_key(uint32_t& best, uint32_t& second, uint32_t key) {
+    second = min(second, max(best, key));
+    best = min(best, key);
+}
+
+// 256-bit Hamming distance with a carry-save adder tree (Harley-Seal): seven of the eight XOR words are
+// compressed to ones / twos / fours bit-planes by four full adders (two LOP3 each), so a comparison costs
+// 4 POPC instead of 8.  POPC issues at a quarter of the LOP3 rate on sm_100, which makes the popc pipe the
+// limiter of the plain form (ncu: sm__inst_executed_pipe_xu 89 %).
+__device__ __forceinline__ int hamming256_csa(const uint32_t (&q)[8], const uint4& a, const uint4& b) {
+    const uint32_t x0 = q[0] ^ a.x, x1 = q[1] ^ a.y, x2 = q[2] ^ a.z, x3 = q[3] ^ a.w;
+    const uint32_t x4 = q[4] ^ b.x, x5 = q[5] ^ b.y, x6 = q[6] ^ b.z, x7 = q[7] ^ b.w;
+    const uint32_t s1 = x0 ^ x1 ^ x2, c1 = (x0 & x1) | (x2 & (x0 | x1));
+    const uint32_t s2 = x3 ^ x4 ^ x5, c2 = (x3 & x4) | (x5 & (x3 | x4));
+    const uint32_t ones = s1 ^ s2 ^ x6, c3 = (s1 & s2) | (x6 & (s1 | s2));
+    const uint32_t twos = c1 ^ c2 ^ c3, fours = (c1 & c2) | (c3 & (c1 | c2));
+    return __popc(ones) + __popc(x7) + 2 * __popc(twos) + 4 * __popc(fours);
+}
+
 __device__ __forceinline__ int penalise(int dist, float qx, float qy, float tx, float ty) {
     // feature_matcher.cpp:162-169; MAX_JUMP_RADIUS = 500 (feature_matcher.hpp:12)
     const float dx = qx - tx, dy = qy - ty;
@@ -84,6 +107,9 @@ __global__ void __launch_bounds__(QT) match_kernel(MatchJob job, int with_kp) {
         qy = kq[q].y;
     }
     Top2 t{INT_MAX, INT_MAX, -1, -1};
+    // penalty-free, full-width 256-bit case: packed keys + carry-save popcount
+    const bool packed = W == 8 && !with_kp && wmax > 2 && nt <= (1 << kKeyShift);
+    uint32_t kbest = 0xffffffffu, ksecond = 0xffffffffu;
 
     for (int t0 = 0; t0 < nt; t0 += TT) {
         const int cnt = min(TT, nt - t0);
@@ -99,7 +125,18 @@ __global__ void __launch_bounds__(QT) match_kernel(MatchJob job, int with_kp) {
             for (int v = threadIdx.x; v < cnt; v += QT) txy[v] = make_float2(kt[t0 + v].x, kt[t0 + v].y);
         __syncthreads();
         if (!qok) continue;
-        if (W == 8 && wmax <= 2) {
+        if (W == 8 && packed) {
+            uint32_t qq[8];
+#pragma unroll
+            for (int w = 0; w < 8; w++) qq[w] = qd[W > 0 ? (w < W ? w : 0) : 0];
+#pragma unroll 4
+            for (int j = 0; j < cnt; j++) {
+                const uint4 a = *reinterpret_cast<const uint4*>(tile + j * 8);
+                const uint4 b = *reinterpret_cast<const uint4*>(tile + j * 8 + 4);
+                const int d = hamming256_csa(qq, a, b);
+                top2_update_key(kbest, ksecond, ((uint32_t)d << kKeyShift) + (uint32_t)(t0 + j));
+            }
+        } else if (W == 8 && wmax <= 2) {
             for (int j = 0; j < cnt; j++) {
                 const uint2 a = *reinterpret_cast<const uint2*>(tile + j * 8);
                 int d = __popc(qd[0] ^ a.x) + __popc(qd[W > 1 ? 1 : 0] ^ a.y);
@@ -126,6 +163,10 @@ __global__ void __launch_bounds__(QT) match_kernel(MatchJob job, int with_kp) {
                 top2_update(t, d, t0 + j);
             }
         }
+    }
+    if (packed) {
+        if (kbest != 0xffffffffu) { t.best = (int)(kbest >> kKeyShift); t.bidx = (int)(kbest & ((1u << kKeyShift) - 1)); }
+        if (ksecond != 0xffffffffu) { t.second = (int)(ksecond >> kKeyShift); t.sidx = (int)(ksecond & ((1u << kKeyShift) - 1)); }
     }
     if (qok) job.cand[(size_t)pair * job.cand_pair_stride + q] = make_int4(t.bidx, t.best, t.second, t.sidx);
 }

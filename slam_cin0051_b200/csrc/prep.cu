@@ -47,7 +47,31 @@ __global__ void remap_kernel(const uint8_t* __restrict__ gray, int rows, int col
     if (out_f64) out_f64[(size_t)i * cols + j] = (src >= 0) ? (double)v / 255.0 : 0.0;
 }
 
+// dense host-layout frames (stride bytes per row) -> the pitched frame store; 4 output bytes per thread.
+// (A strided cudaMemcpy2D of 1241-byte rows runs at ~10 GB/s over PCIe 5; one linear copy + this kernel runs
+// at the link rate, tools/xfer_probe.py.)
+__global__ void __launch_bounds__(256) repitch_kernel(const uint8_t* __restrict__ src, int stride, uint8_t* __restrict__ dst,
+                                                      int pitch, int cols, long long rows_total) {
+    const long long row = (long long)blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (row >= rows_total) return;
+    const uint8_t* s = src + row * stride;
+    uint8_t* d = dst + row * pitch;
+    for (int x = (blockIdx.x * 32 + (threadIdx.x & 31)) * 4; x < pitch; x += gridDim.x * 128) {
+        uint32_t w = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (x + k < cols) w |= (uint32_t)s[x + k] << (8 * k);
+        *reinterpret_cast<uint32_t*>(d + x) = w;
+    }
+}
+
 }  // namespace
+
+int launch_repitch(const uint8_t* src, int stride, uint8_t* dst, int pitch, int cols, long long rows_total, cudaStream_t st) {
+    dim3 grid(min((pitch / 4 + 31) / 32, 4), (unsigned)((rows_total + 7) / 8));
+    SLAM_KERNEL("repitch", st, repitch_kernel<<<grid, 256, 0, st>>>(src, stride, dst, pitch, cols, rows_total));
+    return 1;
+}
 
 int launch_bgr2gray(const uint8_t* bgr, int rows, int cols, int stride, uint8_t* gray, int gstride, cudaStream_t st) {
     dim3 grid((cols + 255) / 256, rows);

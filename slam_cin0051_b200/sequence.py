@@ -96,6 +96,15 @@ class FrameSequence:
             self.ctx.check(st)
             return out[: n.value].copy()
 
+    def process_ptrs(self, detector: FeatureDetector, matcher: FeatureMatcher, host_ptr: int, n: int, chunk: int = 64,
+                     with_keypoints: bool = True, kps_ptr=None, desc_ptr=None, matches_ptr=None, counts_ptr=None):
+        """upload -> extract -> match(f, f+1) -> download for n host frames (dense rows), pipelined by chunks over the
+        copy engines; asynchronous (Context.synchronize() waits for the downloads)."""
+        self.ctx.check(self.ctx.lib.slamcu_sequence_process(
+            self.handle, detector.handle, matcher.handle, C.c_void_p(host_ptr), self.cols, n, chunk,
+            1 if with_keypoints else 0, C.c_void_p(kps_ptr or 0), C.c_void_p(desc_ptr or 0), C.c_void_p(matches_ptr or 0),
+            C.c_void_p(counts_ptr or 0)))
+
     def download_ptrs(self, first, n, kps_ptr=None, desc_ptr=None, matches_ptr=None, counts_ptr=None):
         self.ctx.check(self.ctx.lib.slamcu_sequence_download(self.handle, first, n, C.c_void_p(kps_ptr or 0),
                                                              C.c_void_p(desc_ptr or 0), C.c_void_p(matches_ptr or 0),
