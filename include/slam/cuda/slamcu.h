@@ -226,11 +226,26 @@ int slamcu_undistort(slamcu_context* ctx, const uint8_t* gray, int rows, int col
  * counts[n_models] inlier counts; masks (may be NULL) n_models x n bytes. */
 int slamcu_ransac_score(slamcu_context* ctx, const double* models9, int n_models, const double* x1, const double* x2,
                         int n, double thr2, int32_t* counts, uint8_t* masks);
-/* Full cv::findEssentialMat(p1,p2,K,RANSAC,0.999,1.0,1000) replacement: RNG/sampling sequence,
- * 5-point minimal solver, scoring, sequential accept / adaptive-iteration replay.  p1/p2: n x 2 float
- * pixels; K4 = fx,fy,cx,cy.  E9 row-major; mask n bytes.  n < 5 => SLAMCU_INVALID_ARGUMENT. */
+/* cv::findEssentialMat(p1, p2, K, RANSAC, prob, threshold, maxIters) as called by PoseEstimator::estimate
+ * (pose_estimator.cpp:42; defaults 0.999, 1.0, 1000): cv::RNG sampling sequence, 5-point minimal solver, Sampson
+ * scoring, sequential accept / adaptive-iteration rule, all on the device.  p1/p2: n x 2 float pixels; K4 =
+ * fx,fy,cx,cy.  E9 row-major with |E|_F = 1 (all zeros when no hypothesis was accepted, like cv's empty Mat);
+ * mask n bytes (may be NULL).  n < 6 -> SLAMCU_EMPTY_INPUT (the reference itself returns early below 8 matches,
+ * pose_estimator.cpp:22-26). */
 int slamcu_find_essential(slamcu_context* ctx, const float* p1, const float* p2, int n, const double* K4, double prob,
                           double threshold, int max_iters, double* E9, uint8_t* mask, int* n_inliers);
+/* Stage probe: the 5-point minimal solver on n_samples independent samples.  x1/x2: [n_samples][5][2] normalised
+ * coordinates; models: [n_samples][10][9] (row-major E, unit norm); counts[n_samples] = solutions per sample. */
+int slamcu_fivept_solve(slamcu_context* ctx, const double* x1, const double* x2, int n_samples, double* models,
+                        int32_t* counts);
+/* Batched: findEssentialMat on the matches of pairs (f, f+1), f in [first, first + n_pairs), of a sequence
+ * (keypoints of match.queryIdx / match.trainIdx, as PoseEstimator::estimate gathers them, pose_estimator.cpp:30-35).
+ * One thread block per pair; asynchronous. */
+int slamcu_sequence_essential(slamcu_sequence* seq, int first, int n_pairs, const double* K4, double prob,
+                              double threshold, int max_iters);
+/* Result of one pair: E9, inlier count, RANSAC iterations run, inlier mask over the pair's matches; synchronises. */
+int slamcu_sequence_essential_read(slamcu_sequence* seq, int pair, double* E9, int* n_inliers, int* n_iters, uint8_t* mask,
+                                   int capacity, int* n_points);
 
 #ifdef __cplusplus
 }

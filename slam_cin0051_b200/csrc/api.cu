@@ -144,6 +144,9 @@ struct slamcu_sequence {
     unsigned long long* sort_keys = nullptr;  // [F][cap_kp]
     int* h_counts = nullptr;                  // pinned [F][4]
     uint8_t* stage = nullptr;                 // [F][rows][cols] dense landing zone of linear H2D copies (lazy)
+    EssentialJob ess{};                       // per-pair two-view RANSAC working set (lazy)
+    bool has_ess = false;
+    std::vector<void*> ess_owned;
     std::vector<void*> owned;
     // ORB-mode working set, allocated on first use and keyed by the detector parameters
     bool has_orb = false;
@@ -225,6 +228,7 @@ int slamcu_create(int device_id, slamcu_context** out) {
     cudaDeviceGetAttribute(&ctx->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device_id);
     init_sortnms_attributes(ctx->smem_optin);
     init_orb_attributes(ctx->smem_optin);
+    init_essential_attributes();
     *out = ctx;
     return SLAMCU_OK;
 }
@@ -376,6 +380,7 @@ void slamcu_sequence_destroy(slamcu_sequence* s) {
     for (void* p : s->owned) cudaFree(p);
     for (void* p : s->orb_owned) cudaFree(p);
     if (s->stage) cudaFree(s->stage);
+    for (void* p : s->ess_owned) cudaFree(p);
     if (s->h_counts) cudaFreeHost(s->h_counts);
     delete s;
 }
@@ -1379,9 +1384,144 @@ int slamcu_ransac_score(slamcu_context* ctx, const double* models9, int n_models
     return SLAMCU_OK;
 }
 
-int slamcu_find_essential(slamcu_context* ctx, const float*, const float*, int, const double*, double, double, int,
-                          double*, uint8_t*, int*) {
-    return fail(ctx, SLAMCU_UNSUPPORTED, "slamcu_find_essential: 5-point solver not built yet");
+static void essential_params(EssentialJob& j, const double* K4, double prob, double threshold, int max_iters) {
+    const double t = threshold / ((K4[0] + K4[1]) / 2.0);  // findEssentialMat: threshold /= (fx + fy) / 2
+    j.thr2 = (float)(t * t);
+    j.prob = prob;
+    j.max_iters = max_iters;
+}
+
+int slamcu_find_essential(slamcu_context* ctx, const float* p1, const float* p2, int n, const double* K4, double prob,
+                          double threshold, int max_iters, double* E9, uint8_t* mask, int* n_inliers) {
+    if (!ctx) return SLAMCU_INVALID_ARGUMENT;
+    if (!p1 || !p2 || !K4 || !E9 || n < 0) return fail(ctx, SLAMCU_INVALID_ARGUMENT, "bad arguments");
+    if (n < 6) return fail(ctx, SLAMCU_EMPTY_INPUT, "findEssentialMat needs more than 5 correspondences (got %d)", n);
+    CU(ctx, cudaSetDevice(ctx->device));
+    const size_t b_pts = ((size_t)n * 16 + 255) / 256 * 256, b_in = ((size_t)n * 8 + 255) / 256 * 256;
+    const size_t b_mask = ((size_t)n + 255) / 256 * 256;
+    int rc = ensure_scratch(ctx, 2 * b_pts + 2 * b_in + b_mask + 1024);
+    if (rc != SLAMCU_OK) return rc;
+    uint8_t* base = static_cast<uint8_t*>(ctx->scratch);
+    EssentialJob j{};
+    j.x1 = reinterpret_cast<double2*>(base);
+    j.x2 = reinterpret_cast<double2*>(base + b_pts);
+    float* d_p1 = reinterpret_cast<float*>(base + 2 * b_pts);
+    float* d_p2 = reinterpret_cast<float*>(base + 2 * b_pts + b_in);
+    j.mask = base + 2 * b_pts + 2 * b_in;
+    uint8_t* tail = j.mask + b_mask;
+    j.E = reinterpret_cast<double*>(tail);            // 72 bytes
+    j.n_pts = reinterpret_cast<int*>(tail + 128);
+    j.n_inliers = j.n_pts + 1;
+    j.n_iters = j.n_pts + 2;
+    j.pt_stride = n;
+    essential_params(j, K4, prob, threshold, max_iters);
+    CU(ctx, cudaMemcpyAsync(d_p1, p1, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(d_p2, p2, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    {
+        ProfGuard pg(ctx);
+        ctx->launches += launch_essential_normalise(d_p1, d_p2, n, j, K4, ctx->stream);
+        ctx->launches += launch_essential_ransac(j, 1, ctx->stream);
+    }
+    rc = check_launch(ctx, "essential kernels");
+    if (rc != SLAMCU_OK) return rc;
+    int h[3];
+    CU(ctx, cudaMemcpyAsync(E9, j.E, 72, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(h, j.n_pts, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+    if (mask) CU(ctx, cudaMemcpyAsync(mask, j.mask, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    if (n_inliers) *n_inliers = h[1];
+    return SLAMCU_OK;
+}
+
+int slamcu_fivept_solve(slamcu_context* ctx, const double* x1, const double* x2, int n_samples, double* models, int32_t* counts) {
+    if (!ctx) return SLAMCU_INVALID_ARGUMENT;
+    if (!x1 || !x2 || !models || !counts || n_samples <= 0) return fail(ctx, SLAMCU_INVALID_ARGUMENT, "bad arguments");
+    CU(ctx, cudaSetDevice(ctx->device));
+    const size_t b_pts = (size_t)n_samples * 10 * 8, b_mod = (size_t)n_samples * 90 * 8, b_cnt = (size_t)n_samples * 4;
+    int rc = ensure_scratch(ctx, 2 * b_pts + b_mod + b_cnt + 256);
+    if (rc != SLAMCU_OK) return rc;
+    uint8_t* base = static_cast<uint8_t*>(ctx->scratch);
+    double* d1 = reinterpret_cast<double*>(base);
+    double* d2 = reinterpret_cast<double*>(base + b_pts);
+    double* dm = reinterpret_cast<double*>(base + 2 * b_pts);
+    int* dc = reinterpret_cast<int*>(base + 2 * b_pts + b_mod);
+    CU(ctx, cudaMemcpyAsync(d1, x1, b_pts, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(d2, x2, b_pts, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaMemsetAsync(dm, 0, b_mod, ctx->stream));
+    ctx->launches += launch_fivept_probe(d1, d2, n_samples, dm, dc, ctx->stream);
+    rc = check_launch(ctx, "fivept probe");
+    if (rc != SLAMCU_OK) return rc;
+    CU(ctx, cudaMemcpyAsync(models, dm, b_mod, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(counts, dc, b_cnt, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return SLAMCU_OK;
+}
+
+int slamcu_sequence_essential(slamcu_sequence* s, int first, int n_pairs, const double* K4, double prob, double threshold,
+                              int max_iters) {
+    if (!s || !K4) return SLAMCU_INVALID_ARGUMENT;
+    slamcu_context* ctx = s->ctx;
+    if (first < 0 || n_pairs < 0 || first + n_pairs + 1 > s->max_frames) return fail(ctx, SLAMCU_INVALID_ARGUMENT, "bad pair range");
+    if (n_pairs == 0) return SLAMCU_OK;
+    CU(ctx, cudaSetDevice(ctx->device));
+    const SeqView& v = s->v;
+    if (!s->has_ess) {
+        const size_t F = (size_t)s->max_frames;
+        int rc = SLAMCU_OK;
+        auto A = [&](auto** p, size_t count) {
+            if (rc == SLAMCU_OK) rc = dev_alloc(ctx, p, count, s->ess_owned, true);
+        };
+        EssentialJob& e = s->ess;
+        A(&e.x1, F * v.cap_kp);
+        A(&e.x2, F * v.cap_kp);
+        A(&e.n_pts, F);
+        A(&e.E, F * 9);
+        A(&e.n_inliers, F);
+        A(&e.n_iters, F);
+        A(&e.mask, F * v.cap_kp);
+        if (rc != SLAMCU_OK) return rc;
+        e.pt_stride = v.cap_kp;
+        s->has_ess = true;
+    }
+    EssentialJob j = s->ess;
+    j.x1 += (size_t)first * v.cap_kp;
+    j.x2 += (size_t)first * v.cap_kp;
+    j.n_pts += first;
+    j.E += (size_t)first * 9;
+    j.n_inliers += first;
+    j.n_iters += first;
+    j.mask += (size_t)first * v.cap_kp;
+    essential_params(j, K4, prob, threshold, max_iters);
+    ProfGuard pg(ctx);
+    ctx->launches += launch_essential_gather(v, first, n_pairs, j, K4, ctx->stream);
+    ctx->launches += launch_essential_ransac(j, n_pairs, ctx->stream);
+    return check_launch(ctx, "essential kernels");
+}
+
+int slamcu_sequence_essential_read(slamcu_sequence* s, int pair, double* E9, int* n_inliers, int* n_iters, uint8_t* mask,
+                                   int capacity, int* n_points) {
+    if (!s) return SLAMCU_INVALID_ARGUMENT;
+    slamcu_context* ctx = s->ctx;
+    if (!s->has_ess) return fail(ctx, SLAMCU_UNSUPPORTED, "slamcu_sequence_essential has not run on this sequence");
+    if (pair < 0 || pair + 1 >= s->max_frames) return fail(ctx, SLAMCU_INVALID_ARGUMENT, "bad pair index");
+    const EssentialJob& e = s->ess;
+    int h[3] = {0, 0, 0};
+    CU(ctx, cudaMemcpyAsync(&h[0], e.n_pts + pair, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(&h[1], e.n_inliers + pair, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(&h[2], e.n_iters + pair, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (E9) CU(ctx, cudaMemcpyAsync(E9, e.E + (size_t)pair * 9, 72, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    if (n_points) *n_points = h[0];
+    if (n_inliers) *n_inliers = h[1];
+    if (n_iters) *n_iters = h[2];
+    if (mask) {
+        if (h[0] > capacity) return fail(ctx, SLAMCU_CAPACITY, "need room for %d mask bytes", h[0]);
+        if (h[0] > 0) {
+            CU(ctx, cudaMemcpyAsync(mask, e.mask + (size_t)pair * e.pt_stride, (size_t)h[0], cudaMemcpyDeviceToHost, ctx->stream));
+            CU(ctx, cudaStreamSynchronize(ctx->stream));
+        }
+    }
+    return SLAMCU_OK;
 }
 
 }  // extern "C"

@@ -86,6 +86,23 @@ int launch_remap(const uint8_t* gray, int rows, int cols, int stride, const int*
 int launch_ransac_score(const double* models9, int n_models, const double* x1, const double* x2, int n, double thr2,
                         int* counts, uint8_t* masks, cudaStream_t st);
 
+// two-view geometry (essential.cu): one RANSAC problem per frame pair
+struct EssentialJob {
+    double2* x1; double2* x2;        // [pairs][pt_stride] correspondences normalised by K
+    int* n_pts;                      // [pairs]
+    double* E;                       // [pairs][9] row-major, |E|_F = 1 (zeros when no model was accepted)
+    int* n_inliers; int* n_iters;    // [pairs]
+    uint8_t* mask;                   // [pairs][pt_stride]
+    int pt_stride, max_iters;
+    double prob;
+    float thr2;                      // (float)(t * t), t = threshold / ((fx + fy) / 2)
+};
+void init_essential_attributes();
+int launch_essential_gather(const SeqView& s, int first, int n_pairs, const EssentialJob& job, const double* K4, cudaStream_t st);
+int launch_essential_normalise(const float* p1, const float* p2, int n, const EssentialJob& job, const double* K4, cudaStream_t st);
+int launch_essential_ransac(const EssentialJob& job, int n_pairs, cudaStream_t st);
+int launch_fivept_probe(const double* x1, const double* x2, int n_samples, double* models, int* counts, cudaStream_t st);
+
 // ---- optional per-kernel timing (CUDA events on the launching stream; bench.py's roofline input) ----
 struct Profiler {
     virtual void begin(const char* name, cudaStream_t st) = 0;

@@ -1,0 +1,471 @@
+// essential.cu -- cv::findEssentialMat(p1, p2, K, RANSAC, prob, threshold, maxIters) on the device
+// (row R1 of SURVEY.md section 8a; the reference calls it at src/frontend/pose_estimator.cpp:42).
+//
+// The algorithm lives in OpenCV (calib3d five-point.cpp + ptsetreg.cpp, un-vendored, conanfile.txt:2).  What is
+// reproduced EXACTLY: the cv::RNG multiply-with-carry stream seeded 0xFFFFFFFFFFFFFFFF, the 5-subset draw with
+// redraw on duplicates, the Sampson-error inlier test (double arithmetic in Matx order, narrowed to float, compared
+// with (float)t^2), the strictly-greater accept rule and RANSACUpdateNumIters.  The 5-point minimal solver is the
+// same mathematics (Nister) with its own null-space basis and root finder: candidates agree with OpenCV's to
+// rounding, their order inside one sample may differ (that only matters for exact ties at the maximum).
+//
+// essential_ransac_kernel: one block per frame pair, adaptive like the original loop but in waves of WAVE samples:
+//   thread 0 draws the wave's subsets from the sequential RNG; one thread per sample runs the minimal solver;
+//   one warp per hypothesis scores all correspondences (ballot + popc inlier count); thread 0 replays the
+//   sequential accept / niters rule over the wave; the loop ends as soon as the replay reaches niters.
+// Finally the block writes the winner's inlier mask.
+#include "common.cuh"
+
+namespace slamcu {
+namespace {
+
+constexpr int WAVE = 64;      // samples solved per wave (= threads per block)
+constexpr int MAXM = 10;      // essential matrices per sample
+
+__constant__ int kT11[4][4] = {{0, 3, 4, 6}, {3, 1, 5, 7}, {4, 5, 2, 8}, {6, 7, 8, 9}};
+__constant__ int kT21[10][4] = {{0, 2, 4, 5},    {3, 1, 6, 7},    {10, 13, 16, 17}, {2, 3, 8, 9},     {4, 8, 10, 11},
+                                {8, 6, 13, 14},  {5, 9, 11, 12},  {9, 7, 14, 15},   {11, 14, 17, 18}, {12, 15, 18, 19}};
+
+struct CvRng {
+    unsigned long long s;
+    __device__ unsigned next() {
+        s = (unsigned long long)(unsigned)s * 4164903690ULL + (s >> 32);
+        return (unsigned)s;
+    }
+};
+
+// linear polynomial (x, y, z, 1) products; monomial orders as in oracle/essential_oracle.py
+__device__ void mul11(const double* a, const double* b, double* out /*10, accumulated*/, double sign) {
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) out[kT11[i][j]] += sign * (a[i] * b[j]);
+}
+__device__ void mul21(const double* a, const double* b, double* out /*20, accumulated*/) {
+    for (int i = 0; i < 10; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) out[kT21[i][j]] += a[i] * b[j];
+}
+
+// c = a * b for dense univariate polynomials, highest power first; na, nb = number of coefficients
+__device__ void polymul(const double* a, int na, const double* b, int nb, double* c, double sign, bool clear) {
+    if (clear)
+        for (int i = 0; i < na + nb - 1; i++) c[i] = 0.0;
+    for (int i = 0; i < na; i++)
+        for (int j = 0; j < nb; j++) c[i + j] += sign * (a[i] * b[j]);
+}
+
+__device__ double polyval(const double* a, int n, double x) {
+    double v = a[0];
+    for (int i = 1; i < n; i++) v = v * x + a[i];
+    return v;
+}
+
+// Real roots of a real polynomial (highest power first, n coefficients): Durand-Kerner in complex double
+// ((0.4 + 0.9i)^k start, Gauss-Seidel sweeps), then Newton polishing of the near-real roots.
+__device__ int real_roots(const double* c_in, int n_in, double* out) {
+    int lead = 0;
+    while (lead < n_in && c_in[lead] == 0.0) lead++;
+    const int n = n_in - lead - 1;  // degree
+    if (n < 1) return 0;
+    double a[11];
+    for (int i = 0; i <= n; i++) a[i] = c_in[lead + i] / c_in[lead];
+    double re[10], im[10];
+    {
+        double pr = 1.0, pi = 0.0;
+        for (int k = 0; k < n; k++) {
+            re[k] = pr;
+            im[k] = pi;
+            const double nr = pr * 0.4 - pi * 0.9, ni = pr * 0.9 + pi * 0.4;
+            pr = nr;
+            pi = ni;
+        }
+    }
+    for (int iter = 0; iter < 500; iter++) {
+        double delta = 0.0, big = 1.0;
+        for (int i = 0; i < n; i++) {
+            const double pr = re[i], pi = im[i];
+            double nr = a[0], ni = 0.0;  // Horner in complex
+            for (int k = 1; k <= n; k++) {
+                const double tr = nr * pr - ni * pi + a[k];
+                ni = nr * pi + ni * pr;
+                nr = tr;
+            }
+            double dr = 1.0, di = 0.0;
+            for (int j = 0; j < n; j++) {
+                if (j == i) continue;
+                const double qr = pr - re[j], qi = pi - im[j];
+                const double tr = dr * qr - di * qi;
+                di = dr * qi + di * qr;
+                dr = tr;
+            }
+            const double den = dr * dr + di * di;
+            if (den == 0.0) continue;
+            const double ur = (nr * dr + ni * di) / den, ui = (ni * dr - nr * di) / den;
+            re[i] = pr - ur;
+            im[i] = pi - ui;
+            delta = fmax(delta, sqrt(ur * ur + ui * ui));
+        }
+        for (int i = 0; i < n; i++) big = fmax(big, sqrt(re[i] * re[i] + im[i] * im[i]));
+        if (delta < 1e-15 * big) break;
+    }
+    double da[10], aa[11];
+    for (int i = 0; i < n; i++) da[i] = a[i] * (double)(n - i);
+    for (int i = 0; i <= n; i++) aa[i] = fabs(a[i]);
+    int cnt = 0;
+    for (int i = 0; i < n; i++) {
+        const double scale = fmax(1.0, fabs(re[i]));
+        if (fabs(im[i]) > 1e-6 * scale) continue;
+        double x = re[i];
+        for (int k = 0; k < 3; k++) {
+            const double f = polyval(a, n + 1, x), df = polyval(da, n, x);
+            if (df != 0.0) x -= f / df;
+        }
+        if (fabs(im[i]) <= 1e-10 * scale || fabs(polyval(a, n + 1, x)) < 1e-9 * (1.0 + polyval(aa, n + 1, fabs(x))))
+            out[cnt++] = x;
+    }
+    return cnt;
+}
+
+// Nister's 5-point solver.  x1, x2: 5 normalised correspondences.  models: up to MAXM row-major 3x3, |E|_F = 1.
+__device__ int five_point(const double (*x1)[2], const double (*x2)[2], double* models) {
+    // ---- null space of the 5x9 epipolar system (row-major E), full-pivot Gauss-Jordan + twice MGS
+    double Q[5][9];
+    int cols[9];
+    for (int p = 0; p < 5; p++) {
+        const double a[3] = {x1[p][0], x1[p][1], 1.0}, b[3] = {x2[p][0], x2[p][1], 1.0};
+        for (int i = 0; i < 3; i++)
+            for (int j = 0; j < 3; j++) Q[p][3 * i + j] = b[i] * a[j];
+    }
+    for (int k = 0; k < 9; k++) cols[k] = k;
+    for (int r = 0; r < 5; r++) {
+        int pr = r, pc = r;
+        double best = -1.0;
+        for (int i = r; i < 5; i++)
+            for (int j = r; j < 9; j++)
+                if (fabs(Q[i][j]) > best) { best = fabs(Q[i][j]); pr = i; pc = j; }
+        if (best <= 0.0) return 0;
+        for (int j = 0; j < 9; j++) { const double t = Q[r][j]; Q[r][j] = Q[pr][j]; Q[pr][j] = t; }
+        for (int i = 0; i < 5; i++) { const double t = Q[i][r]; Q[i][r] = Q[i][pc]; Q[i][pc] = t; }
+        { const int t = cols[r]; cols[r] = cols[pc]; cols[pc] = t; }
+        const double piv = Q[r][r];
+        for (int j = 0; j < 9; j++) Q[r][j] = Q[r][j] / piv;
+        for (int k = 0; k < 5; k++) {
+            if (k == r) continue;
+            const double fct = Q[k][r];
+            for (int j = 0; j < 9; j++) Q[k][j] = Q[k][j] - fct * Q[r][j];
+        }
+    }
+    double B4[4][9];
+    for (int k = 0; k < 4; k++) {
+        for (int j = 0; j < 9; j++) B4[k][j] = 0.0;
+        for (int r = 0; r < 5; r++) B4[k][cols[r]] = -Q[r][5 + k];
+        B4[k][cols[5 + k]] = 1.0;
+    }
+    for (int rep = 0; rep < 2; rep++)
+        for (int k = 0; k < 4; k++) {
+            for (int j = 0; j < k; j++) {
+                double d = 0.0;
+                for (int t = 0; t < 9; t++) d += B4[k][t] * B4[j][t];
+                for (int t = 0; t < 9; t++) B4[k][t] = B4[k][t] - d * B4[j][t];
+            }
+            double nn = 0.0;
+            for (int t = 0; t < 9; t++) nn += B4[k][t] * B4[k][t];
+            nn = sqrt(nn);
+            for (int t = 0; t < 9; t++) B4[k][t] = B4[k][t] / nn;
+        }
+    // ---- the ten cubic constraints: det(E) and (E E' - tr(E E')/2 I) E, for E = x B0 + y B1 + z B2 + B3
+    double A[10][20];
+    for (int i = 0; i < 10; i++)
+        for (int j = 0; j < 20; j++) A[i][j] = 0.0;
+    double Ep[9][4];
+    for (int e = 0; e < 9; e++)
+        for (int k = 0; k < 4; k++) Ep[e][k] = B4[k][e];
+    {
+        double t2[10];
+        for (int j = 0; j < 10; j++) t2[j] = 0.0;
+        mul11(Ep[1], Ep[5], t2, 1.0); mul11(Ep[2], Ep[4], t2, -1.0); mul21(t2, Ep[6], A[0]);
+        for (int j = 0; j < 10; j++) t2[j] = 0.0;
+        mul11(Ep[2], Ep[3], t2, 1.0); mul11(Ep[0], Ep[5], t2, -1.0); mul21(t2, Ep[7], A[0]);
+        for (int j = 0; j < 10; j++) t2[j] = 0.0;
+        mul11(Ep[0], Ep[4], t2, 1.0); mul11(Ep[1], Ep[3], t2, -1.0); mul21(t2, Ep[8], A[0]);
+    }
+    {
+        double L[3][3][10];
+        for (int i = 0; i < 3; i++)
+            for (int j = 0; j < 3; j++) {
+                for (int t = 0; t < 10; t++) L[i][j][t] = 0.0;
+                for (int k = 0; k < 3; k++) mul11(Ep[3 * i + k], Ep[3 * j + k], L[i][j], 1.0);
+            }
+        double tr[10];
+        for (int t = 0; t < 10; t++) tr[t] = (L[0][0][t] + L[1][1][t]) + L[2][2][t];
+        for (int i = 0; i < 3; i++)
+            for (int t = 0; t < 10; t++) L[i][i][t] = L[i][i][t] - 0.5 * tr[t];
+        for (int i = 0; i < 3; i++)
+            for (int j = 0; j < 3; j++)
+                for (int k = 0; k < 3; k++) mul21(L[i][k], Ep[3 * k + j], A[1 + 3 * i + j]);
+    }
+    // ---- Gauss-Jordan on the first ten columns, partial pivoting
+    for (int col = 0; col < 10; col++) {
+        int piv = col;
+        double best = fabs(A[col][col]);
+        for (int r = col + 1; r < 10; r++)
+            if (fabs(A[r][col]) > best) { best = fabs(A[r][col]); piv = r; }
+        if (best == 0.0) return 0;
+        if (piv != col)
+            for (int j = 0; j < 20; j++) { const double t = A[col][j]; A[col][j] = A[piv][j]; A[piv][j] = t; }
+        const double d = A[col][col];
+        for (int j = 0; j < 20; j++) A[col][j] = A[col][j] / d;
+        for (int r = 0; r < 10; r++) {
+            if (r == col) continue;
+            const double fct = A[r][col];
+            if (fct == 0.0) continue;
+            for (int j = 0; j < 20; j++) A[r][j] = A[r][j] - fct * A[col][j];
+        }
+    }
+    // ---- rows x^2z - z x^2, y^2z - z y^2, xyz - z xy  ->  B(z) (3 x 3 polynomial matrix), det B(z) of degree 10
+    double bx[3][4], by[3][4], b1[3][5];
+    for (int i = 0; i < 3; i++) {
+        const double* a = &A[4 + 2 * i][10];
+        const double* b = &A[5 + 2 * i][10];
+        bx[i][0] = 0.0 - b[0]; bx[i][1] = a[0] - b[1]; bx[i][2] = a[1] - b[2]; bx[i][3] = a[2] - 0.0;
+        by[i][0] = 0.0 - b[3]; by[i][1] = a[3] - b[4]; by[i][2] = a[4] - b[5]; by[i][3] = a[5] - 0.0;
+        b1[i][0] = 0.0 - b[6]; b1[i][1] = a[6] - b[7]; b1[i][2] = a[7] - b[8]; b1[i][3] = a[8] - b[9]; b1[i][4] = a[9] - 0.0;
+    }
+    double det[11], m[7];
+    polymul(bx[1], 4, by[2], 4, m, 1.0, true); polymul(by[1], 4, bx[2], 4, m, -1.0, false);
+    polymul(b1[0], 5, m, 7, det, 1.0, true);
+    polymul(bx[0], 4, by[2], 4, m, 1.0, true); polymul(by[0], 4, bx[2], 4, m, -1.0, false);
+    polymul(b1[1], 5, m, 7, det, -1.0, false);
+    polymul(bx[0], 4, by[1], 4, m, 1.0, true); polymul(by[0], 4, bx[1], 4, m, -1.0, false);
+    polymul(b1[2], 5, m, 7, det, 1.0, false);
+    double zs[10];
+    const int nz = real_roots(det, 11, zs);
+    int count = 0;
+    for (int k = 0; k < nz && count < MAXM; k++) {
+        const double z = zs[k];
+        const double z2 = z * z, z3 = z2 * z, z4 = z3 * z;
+        double Bz[3][3];
+        for (int i = 0; i < 3; i++) {
+            Bz[i][0] = ((bx[i][0] * z3 + bx[i][1] * z2) + bx[i][2] * z) + bx[i][3];
+            Bz[i][1] = ((by[i][0] * z3 + by[i][1] * z2) + by[i][2] * z) + by[i][3];
+            Bz[i][2] = (((b1[i][0] * z4 + b1[i][1] * z3) + b1[i][2] * z2) + b1[i][3] * z) + b1[i][4];
+        }
+        // null vector of the rank-2 matrix: the largest cross product of two rows
+        double v[3] = {0, 0, 0}, vn = -1.0;
+        const int pa[3] = {0, 0, 1}, pb[3] = {1, 2, 2};
+        for (int c = 0; c < 3; c++) {
+            const double* r0 = Bz[pa[c]];
+            const double* r1 = Bz[pb[c]];
+            const double cx = r0[1] * r1[2] - r0[2] * r1[1], cy = r0[2] * r1[0] - r0[0] * r1[2],
+                         cz = r0[0] * r1[1] - r0[1] * r1[0];
+            const double nn = (cx * cx + cy * cy) + cz * cz;
+            if (nn > vn) { vn = nn; v[0] = cx; v[1] = cy; v[2] = cz; }
+        }
+        if (fabs(v[2]) < 1e-10 * sqrt(vn)) continue;
+        const double x = v[0] / v[2], y = v[1] / v[2];
+        double e[9], nn = 0.0;
+        for (int t = 0; t < 9; t++) {
+            e[t] = ((x * B4[0][t] + y * B4[1][t]) + z * B4[2][t]) + B4[3][t];
+            nn += e[t] * e[t];
+        }
+        nn = sqrt(nn);
+        for (int t = 0; t < 9; t++) models[count * 9 + t] = e[t] / nn;
+        count++;
+    }
+    return count;
+}
+
+// EMEstimatorCallback::computeError for one correspondence; Matx products accumulate left to right (no FMA)
+__device__ __forceinline__ bool sampson_inlier(const double* E, double ax, double ay, double bx, double by, float thr2) {
+    const double e0 = (E[0] * ax + E[1] * ay) + E[2] * 1.0;
+    const double e1 = (E[3] * ax + E[4] * ay) + E[5] * 1.0;
+    const double e2 = (E[6] * ax + E[7] * ay) + E[8] * 1.0;
+    const double t0 = (E[0] * bx + E[3] * by) + E[6] * 1.0;
+    const double t1 = (E[1] * bx + E[4] * by) + E[7] * 1.0;
+    const double dot = (bx * e0 + by * e1) + 1.0 * e2;
+    const float err = (float)(dot * dot / (e0 * e0 + e1 * e1 + t0 * t0 + t1 * t1));
+    return err <= thr2;
+}
+
+__device__ int update_num_iters(double p, double ep, int model_points, int max_iters) {  // RANSACUpdateNumIters
+    p = fmin(fmax(p, 0.0), 1.0);
+    ep = fmin(fmax(ep, 0.0), 1.0);
+    double num = fmax(1.0 - p, 2.2250738585072014e-308);
+    double denom = 1.0 - pow(1.0 - ep, (double)model_points);
+    if (denom < 2.2250738585072014e-308) return 0;
+    num = log(num);
+    denom = log(denom);
+    return (denom >= 0 || -num >= max_iters * (-denom)) ? max_iters : __double2int_rn(num / denom);
+}
+
+__global__ void __launch_bounds__(WAVE) essential_ransac_kernel(EssentialJob job) {
+    extern __shared__ __align__(16) unsigned char esm[];
+    double* models = reinterpret_cast<double*>(esm);                 // [WAVE][MAXM][9]
+    int* nmod = reinterpret_cast<int*>(models + WAVE * MAXM * 9);   // [WAVE]
+    int* counts = nmod + WAVE;                                      // [WAVE][MAXM]
+    int* sidx = counts + WAVE * MAXM;                               // [WAVE][5]
+    __shared__ double bestE[9];
+    __shared__ int sh_best, sh_niters, sh_done, sh_it;
+    __shared__ CvRng rng;
+    const int pair = blockIdx.x;
+    const int n = job.n_pts[pair];
+    const double2* x1 = job.x1 + (size_t)pair * job.pt_stride;
+    const double2* x2 = job.x2 + (size_t)pair * job.pt_stride;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        sh_best = 0;
+        sh_niters = job.max_iters;
+        sh_done = (n < 6 || job.max_iters <= 0) ? 1 : 0;
+        sh_it = 0;
+        rng.s = 0xFFFFFFFFFFFFFFFFULL;
+        for (int t = 0; t < 9; t++) bestE[t] = 0.0;
+    }
+    __syncthreads();
+    while (!sh_done) {
+        const int it0 = sh_it;
+        const int wave = min(WAVE, sh_niters - it0);
+        if (tid == 0) {  // getSubset: 5 distinct indices per sample, redraw on duplicates
+            for (int s = 0; s < wave; s++) {
+                int* id = sidx + s * 5;
+                for (int i = 0; i < 5;) {
+                    const int v = (int)(rng.next() % (unsigned)n);
+                    int j = 0;
+                    for (; j < i; j++)
+                        if (id[j] == v) break;
+                    if (j < i) continue;
+                    id[i++] = v;
+                }
+            }
+        }
+        __syncthreads();
+        if (tid < wave) {
+            double a[5][2], b[5][2];
+            for (int i = 0; i < 5; i++) {
+                const double2 p = x1[sidx[tid * 5 + i]], q = x2[sidx[tid * 5 + i]];
+                a[i][0] = p.x; a[i][1] = p.y; b[i][0] = q.x; b[i][1] = q.y;
+            }
+            nmod[tid] = five_point(a, b, models + (size_t)tid * MAXM * 9);
+        }
+        __syncthreads();
+        // score: one warp per hypothesis
+        for (int h = warp; h < wave * MAXM; h += WAVE / 32) {
+            const int s = h / MAXM, k = h - s * MAXM;
+            if (k >= nmod[s]) continue;
+            const double* E = models + (size_t)h * 9;
+            int good = 0;
+            for (int base = 0; base < n; base += 32) {
+                const int i = base + lane;
+                bool in = false;
+                if (i < n) {
+                    const double2 p = x1[i], q = x2[i];
+                    in = sampson_inlier(E, p.x, p.y, q.x, q.y, job.thr2);
+                }
+                good += __popc(__ballot_sync(0xffffffffu, in));
+            }
+            if (lane == 0) counts[h] = good;
+        }
+        __syncthreads();
+        if (tid == 0) {  // sequential replay of RANSACPointSetRegistrator::run over this wave
+            int it = it0, best = sh_best, niters = sh_niters;
+            for (int s = 0; s < wave && it < niters; s++, it++) {
+                for (int k = 0; k < nmod[s]; k++) {
+                    const int good = counts[s * MAXM + k];
+                    if (good > max(best, 4)) {
+                        best = good;
+                        for (int t = 0; t < 9; t++) bestE[t] = models[((size_t)s * MAXM + k) * 9 + t];
+                        niters = update_num_iters(job.prob, (double)(n - good) / n, 5, niters);
+                    }
+                }
+            }
+            sh_best = best;
+            sh_niters = niters;
+            sh_it = it;
+            sh_done = it >= niters ? 1 : 0;
+        }
+        __syncthreads();
+    }
+    // outputs: E (row-major, zeros if no model was accepted), inlier count, mask
+    uint8_t* mask = job.mask + (size_t)pair * job.pt_stride;
+    if (tid < 9) job.E[(size_t)pair * 9 + tid] = bestE[tid];
+    if (tid == 0) {
+        job.n_inliers[pair] = sh_best;
+        job.n_iters[pair] = sh_it;
+    }
+    const bool have = sh_best > 0;
+    for (int i = tid; i < n; i += WAVE) {
+        bool in = false;
+        if (have) {
+            const double2 p = x1[i], q = x2[i];
+            in = sampson_inlier(bestE, p.x, p.y, q.x, q.y, job.thr2);
+        }
+        mask[i] = in ? 1 : 0;
+    }
+}
+
+// gather matched keypoint coordinates and normalise by K: x = ((double)px - cx) / fx  (findEssentialMat's preamble)
+__global__ void __launch_bounds__(256) essential_gather_kernel(SeqView s, int first, EssentialJob job, double fx, double fy,
+                                                               double cx, double cy) {
+    const int pair = blockIdx.y;
+    const int f = first + pair;
+    const int n = min(s.n_match[f], job.pt_stride);
+    if (blockIdx.x == 0 && threadIdx.x == 0) job.n_pts[pair] = n;
+    const slamcu_dmatch* m = s.matches + (size_t)f * s.cap_kp;
+    const slamcu_keypoint* k1 = s.kps + (size_t)f * s.cap_kp;
+    const slamcu_keypoint* k2 = k1 + s.cap_kp;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const slamcu_keypoint a = k1[m[i].queryIdx], b = k2[m[i].trainIdx];
+        job.x1[(size_t)pair * job.pt_stride + i] = make_double2(((double)a.x - cx) / fx, ((double)a.y - cy) / fy);
+        job.x2[(size_t)pair * job.pt_stride + i] = make_double2(((double)b.x - cx) / fx, ((double)b.y - cy) / fy);
+    }
+}
+
+__global__ void __launch_bounds__(256) essential_normalise_kernel(const float* p1, const float* p2, int n, EssentialJob job,
+                                                                  double fx, double fy, double cx, double cy) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) job.n_pts[0] = n;
+    if (i >= n) return;
+    job.x1[i] = make_double2(((double)p1[2 * i] - cx) / fx, ((double)p1[2 * i + 1] - cy) / fy);
+    job.x2[i] = make_double2(((double)p2[2 * i] - cx) / fx, ((double)p2[2 * i + 1] - cy) / fy);
+}
+
+__global__ void fivept_probe_kernel(const double* x1, const double* x2, int n_samples, double* models, int* counts) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_samples) return;
+    double a[5][2], b[5][2];
+    for (int i = 0; i < 5; i++) {
+        a[i][0] = x1[(s * 5 + i) * 2]; a[i][1] = x1[(s * 5 + i) * 2 + 1];
+        b[i][0] = x2[(s * 5 + i) * 2]; b[i][1] = x2[(s * 5 + i) * 2 + 1];
+    }
+    counts[s] = five_point(a, b, models + (size_t)s * MAXM * 9);
+}
+
+size_t essential_smem_bytes() { return (size_t)WAVE * MAXM * 9 * 8 + (size_t)WAVE * 4 + (size_t)WAVE * MAXM * 4 + (size_t)WAVE * 5 * 4; }
+
+}  // namespace
+
+void init_essential_attributes() {
+    cudaFuncSetAttribute(essential_ransac_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)essential_smem_bytes());
+}
+
+int launch_essential_gather(const SeqView& s, int first, int n_pairs, const EssentialJob& job, const double* K4, cudaStream_t st) {
+    SLAM_KERNEL("essential_gather", st,
+                essential_gather_kernel<<<dim3(4, n_pairs), 256, 0, st>>>(s, first, job, K4[0], K4[1], K4[2], K4[3]));
+    return 1;
+}
+
+int launch_essential_normalise(const float* p1, const float* p2, int n, const EssentialJob& job, const double* K4, cudaStream_t st) {
+    essential_normalise_kernel<<<(n + 255) / 256, 256, 0, st>>>(p1, p2, n, job, K4[0], K4[1], K4[2], K4[3]);
+    return 1;
+}
+
+int launch_essential_ransac(const EssentialJob& job, int n_pairs, cudaStream_t st) {
+    SLAM_KERNEL("essential_ransac", st, essential_ransac_kernel<<<n_pairs, WAVE, essential_smem_bytes(), st>>>(job));
+    return 1;
+}
+
+int launch_fivept_probe(const double* x1, const double* x2, int n_samples, double* models, int* counts, cudaStream_t st) {
+    fivept_probe_kernel<<<(n_samples + 31) / 32, 32, 0, st>>>(x1, x2, n_samples, models, counts);
+    return 1;
+}
+
+}  // namespace slamcu

@@ -1,0 +1,81 @@
+"""Host-side mirror of slam::PoseEstimator (include/slam/frontend/pose_estimator.hpp:13-36) up to the essential
+matrix: PoseEstimator::estimate gathers the matched keypoint coordinates (pose_estimator.cpp:30-35) and calls
+cv::findEssentialMat(points1, points2, K, cv::RANSAC) (:42) -- here slamcu_find_essential on the device."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from ._lib import Context
+from .common import Camera
+
+
+def find_essential(points1, points2, K4, prob: float = 0.999, threshold: float = 1.0, max_iters: int = 1000,
+                   context: Context | None = None):
+    """cv::findEssentialMat(p1, p2, K, RANSAC, prob, threshold, maxIters).  Returns (E 3x3 float64 or None, mask uint8[n],
+    n_inliers).  Raises ValueError below 6 correspondences."""
+    ctx = context or Context.default()
+    p1 = np.ascontiguousarray(points1, np.float32).reshape(-1, 2)
+    p2 = np.ascontiguousarray(points2, np.float32).reshape(-1, 2)
+    if len(p1) != len(p2):
+        raise RuntimeError("point sets must have the same size")
+    k = np.ascontiguousarray(K4, np.float64)
+    E = np.zeros(9, np.float64)
+    mask = np.zeros(max(len(p1), 1), np.uint8)
+    n_in = C.c_int(0)
+    ctx.check(ctx.lib.slamcu_find_essential(ctx.handle, p1.ctypes.data, p2.ctypes.data, len(p1), k.ctypes.data, prob, threshold,
+                                            max_iters, E.ctypes.data, mask.ctypes.data, C.byref(n_in)))
+    mask = mask[: len(p1)]
+    if n_in.value <= 0:
+        return None, mask, 0
+    return E.reshape(3, 3), mask, n_in.value
+
+
+def fivept_solve(x1, x2, context: Context | None = None):
+    """5-point minimal solver probe: x1, x2 (S, 5, 2) normalised points -> list of (k_s, 3, 3) arrays."""
+    ctx = context or Context.default()
+    a = np.ascontiguousarray(x1, np.float64).reshape(-1, 5, 2)
+    b = np.ascontiguousarray(x2, np.float64).reshape(-1, 5, 2)
+    S = len(a)
+    models = np.zeros((S, 10, 9), np.float64)
+    counts = np.zeros(S, np.int32)
+    ctx.check(ctx.lib.slamcu_fivept_solve(ctx.handle, a.ctypes.data, b.ctypes.data, S, models.ctypes.data, counts.ctypes.data))
+    return [models[s, : counts[s]].reshape(-1, 3, 3).copy() for s in range(S)]
+
+
+def ransac_score(models, x1, x2, thr2: float, with_masks: bool = False, context: Context | None = None):
+    """Sampson-error inlier counts of M essential-matrix hypotheses against n normalised correspondences."""
+    ctx = context or Context.default()
+    m = np.ascontiguousarray(models, np.float64).reshape(-1, 9)
+    a = np.ascontiguousarray(x1, np.float64).reshape(-1, 2)
+    b = np.ascontiguousarray(x2, np.float64).reshape(-1, 2)
+    counts = np.zeros(len(m), np.int32)
+    masks = np.zeros((len(m), len(a)), np.uint8) if with_masks else None
+    ctx.check(ctx.lib.slamcu_ransac_score(ctx.handle, m.ctypes.data, len(m), a.ctypes.data, b.ctypes.data, len(a), thr2,
+                                          counts.ctypes.data, masks.ctypes.data if with_masks else None))
+    return (counts, masks) if with_masks else counts
+
+
+class PoseEstimator:
+    """slam::PoseEstimator up to E and the inlier mask.  `estimate` mirrors the reference's guard: fewer than 8 matches
+    -> returns None without touching anything (pose_estimator.cpp:22-26)."""
+
+    def __init__(self, camera: Camera, context: Context | None = None):
+        self.camera = camera
+        self.ctx = context or camera.ctx
+
+    def estimate_essential(self, keypoints1, keypoints2, matches):
+        """keypoints: KEYPOINT_DTYPE arrays; matches: MATCH_DTYPE array or (n, 2) index pairs."""
+        m = np.asarray(matches)
+        if m.dtype.names:
+            q, t = m["queryIdx"], m["trainIdx"]
+        else:
+            m = m.reshape(-1, 2)
+            q, t = m[:, 0], m[:, 1]
+        if len(q) < 8:
+            return None
+        p1 = np.stack([keypoints1["x"][q], keypoints1["y"][q]], 1)
+        p2 = np.stack([keypoints2["x"][t], keypoints2["y"][t]], 1)
+        c = self.camera
+        return find_essential(p1, p2, (c.fx, c.fy, c.cx, c.cy), context=self.ctx)

@@ -105,6 +105,23 @@ class FrameSequence:
             1 if with_keypoints else 0, C.c_void_p(kps_ptr or 0), C.c_void_p(desc_ptr or 0), C.c_void_p(matches_ptr or 0),
             C.c_void_p(counts_ptr or 0)))
 
+    def essential(self, K4, first: int = 0, n_pairs: int | None = None, prob: float = 0.999, threshold: float = 1.0,
+                  max_iters: int = 1000):
+        """cv::findEssentialMat(RANSAC) on the matches of every pair (f, f+1) of the range; asynchronous."""
+        n_pairs = self.max_frames - 1 - first if n_pairs is None else n_pairs
+        k = np.ascontiguousarray(K4, np.float64)
+        self.ctx.check(self.ctx.lib.slamcu_sequence_essential(self.handle, first, n_pairs, k.ctypes.data, prob, threshold, max_iters))
+
+    def essential_result(self, pair: int):
+        """(E 3x3 or None, mask uint8[n_matches], n_inliers, n_iters) of one pair; synchronises."""
+        E = np.zeros(9, np.float64)
+        n_in, n_it, n_pt = C.c_int(0), C.c_int(0), C.c_int(0)
+        cap = 1 << 16
+        mask = np.zeros(cap, np.uint8)
+        self.ctx.check(self.ctx.lib.slamcu_sequence_essential_read(self.handle, pair, E.ctypes.data, C.byref(n_in), C.byref(n_it),
+                                                                  mask.ctypes.data, cap, C.byref(n_pt)))
+        return (E.reshape(3, 3) if n_in.value > 0 else None), mask[: n_pt.value].copy(), n_in.value, n_it.value
+
     def download_ptrs(self, first, n, kps_ptr=None, desc_ptr=None, matches_ptr=None, counts_ptr=None):
         self.ctx.check(self.ctx.lib.slamcu_sequence_download(self.handle, first, n, C.c_void_p(kps_ptr or 0),
                                                              C.c_void_p(desc_ptr or 0), C.c_void_p(matches_ptr or 0),

@@ -1,0 +1,69 @@
+"""CPU pins of oracle/essential_oracle.py (restatement of cv::findEssentialMat's RANSAC) against OpenCV's own outputs:
+the committed fixtures tests/golden/essential_*.npz (tools/make_golden_essential.py) and live cv2 calls.
+Tolerance: inlier masks identical; E equal up to sign within 1e-9 (unit Frobenius norm) -- the minimal solver is the
+same mathematics with a different null-space basis and root finder, everything else is reproduced exactly."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+GOLD = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "essential_*.npz")))
+E_TOL = 1e-9
+
+
+def e_diff(a, b):
+    return min(np.abs(a - b).max(), np.abs(a + b).max())
+
+
+def test_cv_rng_stream():
+    from oracle import essential_oracle as eo
+    r = eo.CvRNG()
+    # state = (uint32)state * 4164903690 + (state >> 32), seeded 0xFFFFFFFFFFFFFFFF
+    s = 0xFFFFFFFFFFFFFFFF
+    for _ in range(5):
+        s = ((s & 0xFFFFFFFF) * 4164903690 + (s >> 32)) & 0xFFFFFFFFFFFFFFFF
+        assert r.next() == (s & 0xFFFFFFFF)
+    idx = eo.sample_indices(eo.CvRNG(), 300)
+    assert len(set(idx)) == 5 and all(0 <= i < 300 for i in idx)
+
+
+@pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p)[10:-4] for p in GOLD])
+def test_find_essential_equals_cv2_golden(path):
+    from oracle import essential_oracle as eo
+    g = np.load(path)
+    K = g["K"]
+    E, mask, good = eo.find_essential(g["p1"], g["p2"], (K[0, 0], K[1, 1], K[0, 2], K[1, 2]))
+    assert good == int(g["mask"].sum())
+    assert np.array_equal(mask, g["mask"])
+    assert e_diff(E, g["E"]) < E_TOL
+
+
+def test_five_point_solution_sets_match_cv2():
+    cv2 = pytest.importorskip("cv2")
+    from oracle import essential_oracle as eo
+    g = np.load(GOLD[0])
+    K = g["K"]
+    K4 = (K[0, 0], K[1, 1], K[0, 2], K[1, 2])
+    x1, x2 = eo.normalise(g["p1"], K4), eo.normalise(g["p2"], K4)
+    rng = np.random.default_rng(0)
+    close = total = missed = 0
+    for _ in range(60):
+        idx = rng.choice(len(x1), 5, replace=False)
+        Es = cv2.findEssentialMat(g["p1"][idx].astype(np.float64), g["p2"][idx].astype(np.float64), K, method=cv2.RANSAC)[0]
+        cvE = [] if Es is None else [Es[3 * i:3 * i + 3] for i in range(len(Es) // 3)]
+        mine = eo.five_point(x1[idx], x2[idx])
+        # (cv2 occasionally keeps one more root: a near-infinite z whose E is numerically the z basis matrix)
+        assert len(cvE) - 1 <= len(mine) <= len(cvE)
+        missed += len(cvE) - len(mine)
+        for M in mine:
+            total += 1
+            close += min(e_diff(E, M) for E in cvE) < 1e-6
+        for M in mine:  # every solution satisfies the epipolar constraint on its 5 points and the cubic constraints
+            assert np.abs(np.einsum("ni,ij,nj->n", np.c_[x2[idx], np.ones(5)], M, np.c_[x1[idx], np.ones(5)])).max() < 1e-9
+            assert abs(np.linalg.det(M)) < 1e-6
+            assert np.abs(2 * M @ M.T @ M - np.trace(M @ M.T) * M).max() < 1e-6
+    assert missed <= 2
+    assert close >= 0.97 * total  # ill-conditioned samples may differ beyond 1e-6 between two correct solvers

@@ -1,0 +1,115 @@
+"""GPU parity of the two-view geometry row (R1): slamcu_ransac_score, slamcu_fivept_solve, slamcu_find_essential and
+the batched slamcu_sequence_essential, against oracle/essential_oracle.py and the committed cv2 outputs.
+Stated tolerance: inlier masks and counts identical; E equal up to sign within 1e-9 (unit Frobenius norm)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from conftest import DATA, ROOT
+
+pytestmark = pytest.mark.gpu
+GOLD = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "essential_*.npz")))
+E_TOL = 1e-9
+
+
+def e_diff(a, b):
+    return min(np.abs(a - b).max(), np.abs(a + b).max())
+
+
+def k4(K):
+    return (K[0, 0], K[1, 1], K[0, 2], K[1, 2])
+
+
+def test_ransac_score_counts_and_masks(gpu_ctx):
+    import slam_cin0051_b200 as s
+    from oracle import essential_oracle as eo
+    g = np.load(GOLD[0])
+    x1, x2 = eo.normalise(g["p1"], k4(g["K"])), eo.normalise(g["p2"], k4(g["K"]))
+    rng = np.random.default_rng(1)
+    models = [g["E"]]
+    for _ in range(40):
+        idx = rng.choice(len(x1), 5, replace=False)
+        models += eo.five_point(x1[idx], x2[idx])
+    thr = 1.0 / ((g["K"][0, 0] + g["K"][1, 1]) / 2.0)
+    t2 = float(np.float32(thr * thr))
+    counts, masks = s.ransac_score(np.array(models), x1, x2, thr * thr, with_masks=True, context=gpu_ctx)
+    for E, c, m in zip(models, counts, masks):
+        want = eo.sampson_errors(E, x1, x2) <= np.float32(t2)
+        assert c == int(want.sum()) and np.array_equal(m.astype(bool), want)
+    assert counts[0] == int(g["mask"].sum())
+
+
+def test_fivept_solver_equals_oracle(gpu_ctx):
+    import slam_cin0051_b200 as s
+    from oracle import essential_oracle as eo
+    g = np.load(GOLD[1])
+    x1, x2 = eo.normalise(g["p1"], k4(g["K"])), eo.normalise(g["p2"], k4(g["K"]))
+    rng = np.random.default_rng(2)
+    idx = np.stack([rng.choice(len(x1), 5, replace=False) for _ in range(200)])
+    got = s.fivept_solve(x1[idx], x2[idx], context=gpu_ctx)
+    total = close = 0
+    for i in range(len(idx)):
+        want = eo.five_point(x1[idx[i]], x2[idx[i]])
+        assert abs(len(got[i]) - len(want)) <= 1
+        for M in got[i]:
+            total += 1
+            close += min((e_diff(M, W) for W in want), default=9.0) < 1e-8
+            assert abs(np.sqrt((M * M).sum()) - 1.0) < 1e-12
+    assert total > 400 and close >= 0.99 * total
+
+
+@pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p)[10:-4] for p in GOLD])
+def test_find_essential_equals_cv2_golden(gpu_ctx, path):
+    import slam_cin0051_b200 as s
+    g = np.load(path)
+    E, mask, good = s.find_essential(g["p1"], g["p2"], k4(g["K"]), context=gpu_ctx)
+    assert good == int(g["mask"].sum())
+    assert np.array_equal(mask, g["mask"])
+    assert e_diff(E, g["E"]) < E_TOL
+
+
+def test_find_essential_edge_cases(gpu_ctx):
+    import slam_cin0051_b200 as s
+    g = np.load(GOLD[0])
+    with pytest.raises(ValueError):
+        s.find_essential(g["p1"][:5], g["p2"][:5], k4(g["K"]), context=gpu_ctx)
+    # pure noise: whatever is returned must be self-consistent (count == mask sum) and reproducible
+    rng = np.random.default_rng(3)
+    p1 = rng.uniform(0, 640, (50, 2)).astype(np.float32)
+    p2 = rng.uniform(0, 640, (50, 2)).astype(np.float32)
+    a = s.find_essential(p1, p2, k4(g["K"]), context=gpu_ctx)
+    b = s.find_essential(p1, p2, k4(g["K"]), context=gpu_ctx)
+    assert a[2] == int(a[1].sum()) == b[2] and np.array_equal(a[1], b[1])
+    # the reference's own guard: fewer than 8 matches -> estimate returns without a result (pose_estimator.cpp:22-26)
+    cam = s.Camera(os.path.join(DATA, "camera.yml"), 0, gpu_ctx)
+    est = s.PoseEstimator(cam, gpu_ctx)
+    kp = np.zeros(10, s.KEYPOINT_DTYPE)
+    assert est.estimate_essential(kp, kp, np.zeros((7, 2), np.int64)) is None
+
+
+def test_sequence_essential_equals_single_calls(gpu_ctx):
+    import slam_cin0051_b200 as s
+    from slam_cin0051_b200.synth import make_sequence
+    det = s.FeatureDetector(os.path.join(DATA, "feature_detector_orb.yml"), gpu_ctx)
+    mat = s.FeatureMatcher(os.path.join(DATA, "feature_matcher_orb.yml"), gpu_ctx)
+    n = 5
+    frames = make_sequence(480, 640, n, pitch_px=17, seed=5)
+    seq = s.FrameSequence(480, 640, n, desc_bytes=32, max_keypoints=2560, context=gpu_ctx)
+    seq.upload(frames)
+    seq.extract(det)
+    seq.match_consecutive(mat, with_keypoints=False)
+    K4 = (525.0, 525.0, 319.5, 239.5)
+    seq.essential(K4)
+    for f in range(n - 1):
+        k1, _ = seq.frame(f)
+        k2, _ = seq.frame(f + 1)
+        m = seq.matches(f)
+        assert len(m) >= 8
+        p1 = np.stack([k1["x"][m["queryIdx"]], k1["y"][m["queryIdx"]]], 1)
+        p2 = np.stack([k2["x"][m["trainIdx"]], k2["y"][m["trainIdx"]]], 1)
+        E1, mask1, good1 = s.find_essential(p1, p2, K4, context=gpu_ctx)
+        E, mask, good, iters = seq.essential_result(f)
+        assert good == good1 and np.array_equal(mask, mask1) and iters >= 1
+        assert (E is None and E1 is None) or np.array_equal(E, E1)
