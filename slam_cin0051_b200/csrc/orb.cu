@@ -124,13 +124,16 @@ __device__ __forceinline__ void fast9_load_ring(const uint8_t* t, int stride, in
     for (int k = 0; k < 16; k++) p[k] = t[dys[k] * stride + dxs[k]];
 }
 
-__device__ __forceinline__ bool fast9_is_corner(int v, const int (&p)[16], int thr) {
+// Segment test.  Returns 0 (no corner), 1 (a 9-arc of brighter pixels) or 2 (a 9-arc of darker pixels); both cannot
+// hold at once (two disjoint 9-arcs do not fit in 16).  The ring masks are built by shifting in sign bits:
+// p > up  <=>  up - p < 0.
+__device__ __forceinline__ int fast9_corner_kind(int v, const int (&p)[16], int thr) {
     const int up = v + thr, dn = v - thr;
     unsigned mh = 0, ml = 0;
 #pragma unroll
     for (int k = 0; k < 16; k++) {
-        mh |= (unsigned)(p[k] > up) << k;
-        ml |= (unsigned)(p[k] < dn) << k;
+        mh = __funnelshift_l((unsigned)(up - p[k]), mh, 1);
+        ml = __funnelshift_l((unsigned)(p[k] - dn), ml, 1);
     }
     mh |= mh << 16;
     ml |= ml << 16;
@@ -141,7 +144,34 @@ __device__ __forceinline__ bool fast9_is_corner(int v, const int (&p)[16], int t
     rl &= rl >> 4;            // runs of 8
     rh &= mh >> 8;
     rl &= ml >> 8;            // runs of 9
-    return (rh | rl) != 0;
+    return rh ? 1 : (rl ? 2 : 0);
+}
+
+// cornerScore restricted to the polarity the segment test found: for a bright corner every 9-arc contains a pixel
+// that is not darker than v - thr, so the dark term is <= thr and cannot change max(thr, bright, dark); and v.v.
+__device__ __forceinline__ int fast9_ring_score_kind(int v, const int (&p)[16], int thr, int kind) {
+    int a2[16], a4[16];
+    int best;
+    if (kind == 1) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) a2[i] = min(p[i], p[(i + 1) & 15]);
+#pragma unroll
+        for (int i = 0; i < 16; i++) a4[i] = min(a2[i], a2[(i + 2) & 15]);
+        int m = 0;
+#pragma unroll
+        for (int i = 0; i < 16; i++) m = max(m, min(min(a4[i], a4[(i + 4) & 15]), p[(i + 8) & 15]));
+        best = m - v;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 16; i++) a2[i] = max(p[i], p[(i + 1) & 15]);
+#pragma unroll
+        for (int i = 0; i < 16; i++) a4[i] = max(a2[i], a2[(i + 2) & 15]);
+        int m = 255;
+#pragma unroll
+        for (int i = 0; i < 16; i++) m = min(m, max(max(a4[i], a4[(i + 4) & 15]), p[(i + 8) & 15]));
+        best = v - m;
+    }
+    return max(thr, best) - 1;
 }
 
 // bytes of |a - b| that exceed thr -> bit 7 of the byte (SWAR; thr in [0, 255])
@@ -165,7 +195,7 @@ __global__ void __launch_bounds__(256) fast9_mask_kernel(SeqView s, OrbView o, i
     const uint8_t* img = level_ptr(s, o, f, l);
     // ---- phase 0
     constexpr int VPR = FSW / 16;
-    for (int v = threadIdx.x; v < FSH * VPR; v += blockDim.x) {
+    for (int v = threadIdx.x; v < FSH * VPR; v += 256) {
         const int r = v / VPR, cv = v - r * VPR;
         const int gy = y0 - 4 + r, gx = x0 - FHX + cv * 16;
         uint4 val = make_uint4(0, 0, 0, 0);
@@ -173,68 +203,78 @@ __global__ void __launch_bounds__(256) fast9_mask_kernel(SeqView s, OrbView o, i
             val = __ldg(reinterpret_cast<const uint4*>(img + (size_t)gy * L.pitch + gx));
         *reinterpret_cast<uint4*>(tile + r * FSW + cv * 16) = val;
     }
-    for (int v = threadIdx.x; v < SCH * SCW / 16; v += blockDim.x) reinterpret_cast<uint4*>(sc)[v] = make_uint4(0, 0, 0, 0);
+    for (int v = threadIdx.x; v < SCH * SCW / 16; v += 256) reinterpret_cast<uint4*>(sc)[v] = make_uint4(0, 0, 0, 0);
     if (threadIdx.x < FTH * (FTW / 32)) mw[threadIdx.x] = 0;
     if (threadIdx.x == 0) { n1 = 0; n2 = 0; }
     __syncthreads();
-    // ---- phase 1: 4 pixels per thread
+    // ---- phase 1: a warp per score-grid row, a lane per 4-pixel group of the tile's 128 columns; the two ring
+    // columns (x0-1, x0+128) skip the pre-test and go straight to list 1
     {
         const bool big = thr >= 128;
         const unsigned k7 = (unsigned)(big ? 255 - thr : 127 - thr) * 0x01010101u;
         // valid score-grid columns: the FAST domain [3, cols-3) intersected with [x0-1, x0+129)
         const int lo = max(3, x0 - 1), hi = min(L.cols - 3, x0 + FTW + 1);
-        for (int g = threadIdx.x; g < SCH * SCG; g += blockDim.x) {
-            const int ry = g / SCG, gc = g - ry * SCG;
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        for (int ry = warp; ry < SCH; ry += 8) {
             const int gy = y0 - 1 + ry;
             if ((unsigned)(gy - 3) >= (unsigned)(L.rows - 6)) continue;
-            const uint32_t* row = reinterpret_cast<const uint32_t*>(tile + (ry + 3) * FSW) + 3 + gc;
+            const uint32_t* row = reinterpret_cast<const uint32_t*>(tile + (ry + 3) * FSW) + 4 + lane;
             const unsigned w0 = row[0], wm = row[-1], wp = row[1];
             const unsigned wn = row[-3 * (FSW / 4)], ws = row[3 * (FSW / 4)];
             const unsigned we = __funnelshift_r(w0, wp, 24);  // pixels x+3 .. x+6
             const unsigned ww = __funnelshift_r(wm, w0, 8);   // pixels x-3 .. x
             unsigned m = (swar_absdiff_gt(wn, w0, k7, big) | swar_absdiff_gt(ws, w0, k7, big)) &
                          (swar_absdiff_gt(we, w0, k7, big) | swar_absdiff_gt(ww, w0, k7, big)) & 0x80808080u;
-            if (m == 0) continue;
-            const int gxb = x0 - 4 + 4 * gc;
-            if (gxb < lo || gxb + 4 > hi) {
+            const int gxb = x0 + 4 * lane;
+            if (m != 0 && (gxb < lo || gxb + 4 > hi)) {
 #pragma unroll
                 for (int k = 0; k < 4; k++)
                     if ((unsigned)(gxb + k - lo) >= (unsigned)(hi - lo)) m &= ~(0x80u << (8 * k));
-                if (m == 0) continue;
             }
-            int pos = atomicAdd(&n1, __popc(m));
-            const int base = ry * SCW + 4 * gc;
+            if (m != 0) {
+                int pos = atomicAdd(&n1, __popc(m));
+                const int base = ry * SCW + 4 + 4 * lane;
 #pragma unroll
-            for (int k = 0; k < 4; k++)
-                if (m & (0x80u << (8 * k))) list1[pos++] = (uint16_t)(base + k);
+                for (int k = 0; k < 4; k++)
+                    if (m & (0x80u << (8 * k))) list1[pos++] = (uint16_t)(base + k);
+            }
+        }
+        if (threadIdx.x < 2 * SCH) {  // the two ring columns of every score-grid row
+            const int ry = threadIdx.x >> 1, gy = y0 - 1 + ry;
+            const int cx = (threadIdx.x & 1) ? FTW + 4 : 3;  // score-grid columns of x0+128 and x0-1
+            const int gx = x0 - 4 + cx;
+            if ((unsigned)(gy - 3) < (unsigned)(L.rows - 6) && gx >= lo && gx < hi)
+                list1[atomicAdd(&n1, 1)] = (uint16_t)(ry * SCW + cx);
         }
     }
     __syncthreads();
-    // ---- phase 2: segment test
+    // ---- phase 2: segment test (list-2 entries carry the polarity in bits 13-14)
     const int c1 = n1;
-    for (int e = threadIdx.x; e < c1; e += blockDim.x) {
+    for (int e = threadIdx.x; e < c1; e += 256) {
         const int idx = list1[e];
         const int ry = idx / SCW, cx = idx - ry * SCW;
         const uint8_t* t = tile + (ry + 3) * FSW + (FHX - 4) + cx;
         int p[16];
         fast9_load_ring(t, FSW, p);
-        if (fast9_is_corner(t[0], p, thr)) list2[atomicAdd(&n2, 1)] = (uint16_t)idx;
+        const int kind = fast9_corner_kind(t[0], p, thr);
+        if (kind) list2[atomicAdd(&n2, 1)] = (uint16_t)(idx | (kind << 13));
     }
     __syncthreads();
     // ---- phase 3: scores
     const int c2 = n2;
-    for (int e = threadIdx.x; e < c2; e += blockDim.x) {
-        const int idx = list2[e];
+    for (int e = threadIdx.x; e < c2; e += 256) {
+        const int ent = list2[e];
+        const int idx = ent & 0x1fff, kind = ent >> 13;
         const int ry = idx / SCW, cx = idx - ry * SCW;
         const uint8_t* t = tile + (ry + 3) * FSW + (FHX - 4) + cx;
         int p[16];
         fast9_load_ring(t, FSW, p);
-        sc[idx] = (uint8_t)fast9_ring_score(t[0], p, thr);
+        sc[idx] = (uint8_t)fast9_ring_score_kind(t[0], p, thr, kind);
     }
     __syncthreads();
     // ---- phase 4: NMS + border filter
-    for (int e = threadIdx.x; e < c2; e += blockDim.x) {
-        const int idx = list2[e];
+    for (int e = threadIdx.x; e < c2; e += 256) {
+        const int idx = list2[e] & 0x1fff;
         const int ry = idx / SCW, cx = idx - ry * SCW;
         const int r = ry - 1, lx = cx - 4;
         if ((unsigned)r >= (unsigned)FTH || (unsigned)lx >= (unsigned)FTW) continue;
@@ -548,21 +588,21 @@ __global__ void __launch_bounds__(256) blur7_kernel(SeqView s, OrbView o, int fi
                 k3 = __uint_as_float(0x3e5d4ae0u);
     const bool interior = x0 >= 4 && x0 + GW + 3 <= L.cols;  // no horizontal reflection inside the staged span
     if (interior) {
-        for (int i = threadIdx.x; i < GIH * (GIW / 4); i += blockDim.x) {
+        for (int i = threadIdx.x; i < GIH * (GIW / 4); i += 256) {
             const int r = i / (GIW / 4), c = i - r * (GIW / 4);
             const int gy = reflect101(y0 - 3 + r, L.rows);
             reinterpret_cast<uint32_t*>(tin)[i] =
                 __ldg(reinterpret_cast<const uint32_t*>(img + (size_t)gy * L.pitch + x0 - 4) + c);
         }
     } else {
-        for (int i = threadIdx.x; i < GIH * GIW; i += blockDim.x) {
+        for (int i = threadIdx.x; i < GIH * GIW; i += 256) {
             const int r = i / GIW, c = i - r * GIW;
             const int gy = reflect101(y0 - 3 + r, L.rows), gx = reflect101(x0 - 4 + c, L.cols);
             tin[i] = img[(size_t)gy * L.pitch + gx];
         }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < GIH * (GW / 4); i += blockDim.x) {
+    for (int i = threadIdx.x; i < GIH * (GW / 4); i += 256) {
         const int r = i / (GW / 4), c = i - r * (GW / 4);
         const uint32_t* w = reinterpret_cast<const uint32_t*>(tin + r * GIW) + c;  // pixels x-4 .. x+7 of 4 outputs at x
         const unsigned w0 = w[0], w1 = w[1], w2 = w[2];
