@@ -1,0 +1,291 @@
+// frontend.hpp -- host C++ adapters that re-seat the reference's src/frontend classes on the CUDA C ABI (slamcu.h).
+//
+//   slam::cuda::FeatureDetector  <->  slam::FeatureDetector  (include/slam/frontend/feature_detector.hpp:47-192)
+//   slam::cuda::FeatureMatcher   <->  slam::FeatureMatcher   (include/slam/frontend/feature_matcher.hpp:38-87)
+//   slam::cuda::EssentialSolver  <->  the cv::findEssentialMat call of PoseEstimator::estimate (pose_estimator.cpp:42)
+//
+// Same constructors (a YAML path), same method names and argument order, same exception types and messages.  The
+// methods are templates over the container types so that the header works both inside the reference tree, with
+//   EigenGrayMatrix / DescriptorMatrix (row-major Eigen matrices: .data() .rows() .cols() .resize(r, c)),
+//   slam::Keypoint {x, y, size, angle, response; Keypoint(x, y, size)} and slam::Match(q, t, dist),
+// and without Eigen / OpenCV (tools/cli, test/frontend in this repository) with the look-alike types below.
+// There is no CPU fallback: construction throws if no CUDA device is available.
+#pragma once
+#include <algorithm>
+#include <cstdint>
+#include <filesystem>
+#include <fstream>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "slamcu.h"
+#include "yaml_lite.hpp"
+
+namespace slam::cuda {
+
+// ---- Eigen-free look-alikes (layout-identical to the reference's types) --------------------------------------------
+struct Keypoint {  // slam::Keypoint, feature_detector.hpp:28-38
+    float x{}, y{}, size{}, angle{}, response{};
+    Keypoint() = default;
+    Keypoint(float X, float Y, float s = 6.0F) : x(X), y(Y), size(s) {}
+};
+struct Match {  // slam::Match, feature_matcher.hpp:18-25
+    int queryIdx;
+    int trainIdx;
+    float distance;
+    Match(int q, int t, float d) : queryIdx(q), trainIdx(t), distance(d) {}
+};
+template <class T>
+class RowMajorMatrix {  // the subset of Eigen::Matrix<T, Dynamic, Dynamic, RowMajor> the adapters touch
+public:
+    RowMajorMatrix() = default;
+    RowMajorMatrix(long r, long c) : m_rows(r), m_cols(c), m_data(static_cast<size_t>(r * c)) {}
+    void resize(long r, long c) { m_rows = r; m_cols = c; m_data.assign(static_cast<size_t>(r * c), T{}); }
+    long rows() const { return m_rows; }
+    long cols() const { return m_cols; }
+    T* data() { return m_data.data(); }
+    const T* data() const { return m_data.data(); }
+    T& operator()(long r, long c) { return m_data[static_cast<size_t>(r * m_cols + c)]; }
+    const T& operator()(long r, long c) const { return m_data[static_cast<size_t>(r * m_cols + c)]; }
+private:
+    long m_rows = 0, m_cols = 0;
+    std::vector<T> m_data;
+};
+using GrayMatrix = RowMajorMatrix<uint8_t>;
+using DescriptorMatrix = RowMajorMatrix<uint8_t>;
+
+// ---- context: one per device, shared by the adapters ----------------------------------------------------------------
+class Context {
+public:
+    explicit Context(int device = 0) {
+        const int st = slamcu_create(device, &m_ctx);
+        if (st != SLAMCU_OK) throw std::runtime_error("slamcu_create failed: no usable CUDA device (there is no CPU fallback)");
+    }
+    ~Context() { slamcu_destroy(m_ctx); }
+    Context(const Context&) = delete;
+    Context& operator=(const Context&) = delete;
+    slamcu_context* get() const { return m_ctx; }
+    static Context& instance() {
+        static Context ctx(0);
+        return ctx;
+    }
+    // status -> the exception the reference throws for the same condition
+    void check(int status) const {
+        if (status == SLAMCU_OK) return;
+        const std::string msg = slamcu_last_error(m_ctx);
+        if (status == SLAMCU_EMPTY_INPUT) throw std::invalid_argument(msg.empty() ? "Empty descriptors provided." : msg);
+        throw std::runtime_error(msg.empty() ? slamcu_status_string(status) : msg);
+    }
+private:
+    slamcu_context* m_ctx = nullptr;
+};
+
+// ---- FeatureDetector -----------------------------------------------------------------------------------------------
+class FeatureDetector {
+public:
+    explicit FeatureDetector(const std::filesystem::path& configPath, Context& ctx = Context::instance()) : m_ctx(ctx) {
+        YamlLite fs(configPath.string());
+        if (!fs.isOpened()) throw std::runtime_error("Could not open feature detector file: " + configPath.string());
+        slamcu_detector_config c{};
+        c.intensity_threshold = fs.getInt("IntensityThreshold");
+        if (c.intensity_threshold < 0 || c.intensity_threshold > 255)
+            throw std::runtime_error("Intensity threshold must be in the range [0, 255].");
+        c.contiguous_pixels_threshold = fs.getInt("ContiguousPixelsThreshold");
+        if (c.contiguous_pixels_threshold < 0 || c.contiguous_pixels_threshold > 16)
+            throw std::runtime_error("Contiguous pixels threshold must be in the range [0, 16].");
+        c.non_max_suppression = fs.getInt("NonMaxSuppression");
+        if (c.non_max_suppression != 0 && c.non_max_suppression != 1)
+            throw std::runtime_error("Non-max suppression must be either 0 (false) or 1 (true).");
+        c.suppression_window_size = fs.getInt("SuppressionWindowSize");
+        if (c.suppression_window_size <= 0) throw std::runtime_error("Suppression window size must be a positive integer.");
+        c.patch_size = fs.getInt("PatchSize");
+        if (c.patch_size <= 0 || c.patch_size % 2 == 0) throw std::runtime_error("Patch size must be a positive odd integer.");
+        c.num_brief_pairs = fs.getInt("NumBRIEFPairs");
+        if (c.num_brief_pairs <= 0 || c.num_brief_pairs % 8 != 0)
+            throw std::runtime_error("Number of BRIEF pairs must be a positive multiple of 8.");
+        // generateBRIEFPattern() and the blur kernel come from the host C++ library, like in the reference
+        m_pattern.resize(static_cast<size_t>(c.num_brief_pairs) * 4);
+        int n = 0;
+        m_ctx.check(slamcu_default_brief_pattern(c.patch_size, c.num_brief_pairs, m_pattern.data(), c.num_brief_pairs, &n));
+        m_ctx.check(slamcu_default_blur_weights(m_blur));
+        c.n_pattern = n;
+        c.pattern = m_pattern.data();
+        c.blur_weights = m_blur;
+        // opt-in OpenCV-ORB-compatible mode: keys the reference's YAML does not have
+        if (fs.has("NumLevels") || fs.has("MaxFeatures") || fs.has("ScaleFactor")) {
+            if (!fs.has("OrbPatternFile"))
+                throw std::runtime_error("ORB mode needs OrbPatternFile (256x4 int32 rBRIEF pattern, raw little-endian).");
+            std::ifstream pf(fs.getString("OrbPatternFile"), std::ios::binary);
+            m_orbPattern.resize(1024);
+            pf.read(reinterpret_cast<char*>(m_orbPattern.data()), 4096);
+            if (pf.gcount() != 4096) throw std::runtime_error("Could not read OrbPatternFile.");
+            c.mode = SLAMCU_MODE_ORB;
+            c.n_levels = fs.has("NumLevels") ? fs.getInt("NumLevels") : 8;
+            c.scale_factor = fs.has("ScaleFactor") ? fs.getFloat("ScaleFactor") : 1.2F;
+            c.max_features = fs.has("MaxFeatures") ? fs.getInt("MaxFeatures") : 2000;
+            c.fast_threshold = fs.has("FastThreshold") ? fs.getInt("FastThreshold") : c.intensity_threshold;
+            c.orb_pattern = m_orbPattern.data();
+        }
+        m_descBytes = c.num_brief_pairs / 8;
+        m_ctx.check(slamcu_detector_create(m_ctx.get(), &c, &m_det));
+    }
+    ~FeatureDetector() { slamcu_detector_destroy(m_det); }
+    FeatureDetector(const FeatureDetector&) = delete;
+    FeatureDetector& operator=(const FeatureDetector&) = delete;
+
+    template <class Gray, class KP>
+    void detect(const Gray& image, std::vector<KP>& keypoints) {
+        keypoints.clear();
+        run(image, keypoints, static_cast<std::vector<uint8_t>*>(nullptr), false);
+    }
+
+    template <class Gray, class KP, class Desc>
+    void compute(const Gray& image, std::vector<KP>& keypoints, Desc& descriptors) {
+        if (keypoints.empty()) {  // feature_detector.cpp:22-25
+            descriptors = Desc(0, 0);
+            return;
+        }
+        std::vector<slamcu_keypoint> k(keypoints.size());
+        for (size_t i = 0; i < k.size(); i++) k[i] = {keypoints[i].x, keypoints[i].y, keypoints[i].size, keypoints[i].angle, keypoints[i].response};
+        descriptors.resize(static_cast<long>(k.size()), m_descBytes);
+        m_ctx.check(slamcu_compute(m_det, image.data(), static_cast<int>(image.rows()), static_cast<int>(image.cols()),
+                                   static_cast<int>(image.cols()), k.data(), static_cast<int>(k.size()), descriptors.data(), m_descBytes));
+        for (size_t i = 0; i < k.size(); i++) keypoints[i].angle = k[i].angle;
+    }
+
+    template <class Gray, class KP, class Desc>
+    void detectAndCompute(const Gray& image, std::vector<KP>& keypoints, Desc& descriptors) {
+        keypoints.clear();
+        std::vector<uint8_t> d;
+        run(image, keypoints, &d, true);
+        if (keypoints.empty()) {
+            descriptors = Desc(0, 0);
+            return;
+        }
+        descriptors.resize(static_cast<long>(keypoints.size()), m_descBytes);
+        std::copy(d.begin(), d.begin() + static_cast<long>(keypoints.size()) * m_descBytes, descriptors.data());
+    }
+
+    slamcu_detector* handle() const { return m_det; }
+    int descriptorBytes() const { return m_descBytes; }
+
+private:
+    template <class Gray, class KP>
+    void run(const Gray& image, std::vector<KP>& keypoints, std::vector<uint8_t>* desc, bool withDesc) {
+        const int rows = static_cast<int>(image.rows()), cols = static_cast<int>(image.cols());
+        int cap = std::max(4096, rows * cols / 16), n = 0;
+        std::vector<slamcu_keypoint> k;
+        for (;;) {
+            k.resize(static_cast<size_t>(cap));
+            int st;
+            if (withDesc) {
+                desc->resize(static_cast<size_t>(cap) * m_descBytes);
+                st = slamcu_detect_and_compute(m_det, image.data(), rows, cols, cols, k.data(), desc->data(), m_descBytes, cap, &n);
+            } else {
+                st = slamcu_detect(m_det, image.data(), rows, cols, cols, k.data(), cap, &n);
+            }
+            if (st == SLAMCU_CAPACITY && n > cap) { cap = n; continue; }
+            m_ctx.check(st);
+            break;
+        }
+        keypoints.reserve(static_cast<size_t>(n));
+        for (int i = 0; i < n; i++) {
+            KP kp(k[i].x, k[i].y, k[i].size);
+            kp.angle = k[i].angle;
+            kp.response = k[i].response;
+            keypoints.push_back(kp);
+        }
+    }
+    Context& m_ctx;
+    slamcu_detector* m_det = nullptr;
+    std::vector<int32_t> m_pattern, m_orbPattern;
+    double m_blur[25]{};
+    int m_descBytes = 32;
+};
+
+// ---- FeatureMatcher --------------------------------------------------------------------------------------------------
+class FeatureMatcher {
+public:
+    explicit FeatureMatcher(const std::filesystem::path& configPath, Context& ctx = Context::instance()) : m_ctx(ctx) {
+        YamlLite fs(configPath.string());
+        if (!fs.isOpened()) throw std::runtime_error("Could not open feature matcher config file: " + configPath.string());
+        slamcu_matcher_config c{};
+        const std::string dt = fs.getString("DistanceType");
+        if (dt == "HAMMING") c.distance_type = SLAMCU_DISTANCE_HAMMING;
+        else if (dt == "L2") c.distance_type = SLAMCU_DISTANCE_L2;
+        else throw std::runtime_error("Invalid distance type. Must be 'HAMMING' or 'L2'.");
+        c.filter_matches = fs.getInt("FilterMatches");
+        if (c.filter_matches != 0 && c.filter_matches != 1) throw std::runtime_error("FilterMatches must be either 0 (false) or 1 (true).");
+        c.good_matches_count = fs.getInt("GoodMatchesCount");
+        if (c.filter_matches && c.good_matches_count <= 0)
+            throw std::runtime_error("GoodMatchesCount must be positive when filtering is enabled.");
+        c.use_ratio_test = fs.getInt("UseRatioTest");
+        if (c.use_ratio_test != 0 && c.use_ratio_test != 1) throw std::runtime_error("UseRatioTest must be either 0 (false) or 1 (true).");
+        c.ratio_test_threshold = fs.getFloat("RatioTestThreshold");
+        if (c.ratio_test_threshold < 0.0F || c.ratio_test_threshold > 1.0F)
+            throw std::runtime_error("RatioTestThreshold must be in the range [0, 1].");
+        m_ctx.check(slamcu_matcher_create(m_ctx.get(), &c, &m_matcher));
+    }
+    ~FeatureMatcher() { slamcu_matcher_destroy(m_matcher); }
+    FeatureMatcher(const FeatureMatcher&) = delete;
+    FeatureMatcher& operator=(const FeatureMatcher&) = delete;
+
+    template <class Desc, class M, class KP = Keypoint>
+    void match(const Desc& descriptors1, const Desc& descriptors2, std::vector<M>& matches,
+               const std::vector<KP>& keypoints1 = {}, const std::vector<KP>& keypoints2 = {}) const {
+        matches.clear();  // feature_matcher.cpp:76
+        auto pack = [](const std::vector<KP>& in) {
+            std::vector<slamcu_keypoint> out(in.size());
+            for (size_t i = 0; i < in.size(); i++) out[i] = {in[i].x, in[i].y, in[i].size, in[i].angle, in[i].response};
+            return out;
+        };
+        const std::vector<slamcu_keypoint> k1 = pack(keypoints1), k2 = pack(keypoints2);
+        const int n1 = static_cast<int>(descriptors1.rows()), n2 = static_cast<int>(descriptors2.rows());
+        std::vector<slamcu_dmatch> out(static_cast<size_t>(std::max(n1, 1)));
+        int n = 0;
+        m_ctx.check(slamcu_match(m_matcher, n1 ? descriptors1.data() : nullptr, n1, static_cast<int>(descriptors1.cols()),
+                                 n2 ? descriptors2.data() : nullptr, n2, static_cast<int>(descriptors2.cols()),
+                                 k1.empty() ? nullptr : k1.data(), static_cast<int>(k1.size()), k2.empty() ? nullptr : k2.data(),
+                                 static_cast<int>(k2.size()), out.data(), static_cast<int>(out.size()), &n));
+        matches.reserve(static_cast<size_t>(n));
+        for (int i = 0; i < n; i++) matches.emplace_back(out[i].queryIdx, out[i].trainIdx, out[i].distance);
+    }
+    slamcu_matcher* handle() const { return m_matcher; }
+
+private:
+    Context& m_ctx;
+    slamcu_matcher* m_matcher = nullptr;
+};
+
+// ---- the cv::findEssentialMat call of PoseEstimator::estimate -------------------------------------------------------
+struct EssentialResult {
+    bool valid = false;       // false: fewer than 8 matches (pose_estimator.cpp:22-26) or no hypothesis accepted (:44-47)
+    double E[9]{};            // row-major, |E|_F = 1
+    std::vector<uint8_t> mask;
+    int inliers = 0;
+};
+class EssentialSolver {
+public:
+    // K4 = fx, fy, cx, cy of slam::Camera::getIntrinsicMatrix()
+    explicit EssentialSolver(const double K4[4], Context& ctx = Context::instance()) : m_ctx(ctx) {
+        for (int i = 0; i < 4; i++) m_K[i] = K4[i];
+    }
+    // pts1 / pts2: matched pixel coordinates (x, y) as PoseEstimator::estimate gathers them (pose_estimator.cpp:30-35)
+    EssentialResult solve(const std::vector<float>& pts1, const std::vector<float>& pts2, double prob = 0.999,
+                          double threshold = 1.0, int maxIters = 1000) const {
+        EssentialResult r;
+        const int n = static_cast<int>(pts1.size() / 2);
+        if (n < 8) return r;
+        r.mask.resize(static_cast<size_t>(n));
+        m_ctx.check(slamcu_find_essential(m_ctx.get(), pts1.data(), pts2.data(), n, m_K, prob, threshold, maxIters, r.E,
+                                          r.mask.data(), &r.inliers));
+        r.valid = r.inliers > 0;
+        return r;
+    }
+private:
+    Context& m_ctx;
+    double m_K[4]{};
+};
+
+}  // namespace slam::cuda

@@ -18,6 +18,7 @@
 #ifndef SLAM_CUDA_SLAMCU_H_
 #define SLAM_CUDA_SLAMCU_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -107,6 +108,9 @@ const char* slamcu_last_error(const slamcu_context* ctx);
 int slamcu_set_stream(slamcu_context* ctx, void* cuda_stream /* cudaStream_t, NULL = own stream */);
 void* slamcu_get_stream(slamcu_context* ctx);
 int slamcu_synchronize(slamcu_context* ctx);
+/* Page-locked host memory for the asynchronous sequence calls (so host programs need not link the CUDA runtime). */
+int slamcu_alloc_pinned(size_t bytes, void** out);
+void slamcu_free_pinned(void* p);
 /* number of kernels this library launched on the context since creation (bench.py gpu_launches) */
 int64_t slamcu_launch_count(const slamcu_context* ctx);
 /* Per-kernel device timing: when enabled, every kernel launch on the context is bracketed by CUDA

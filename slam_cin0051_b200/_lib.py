@@ -47,6 +47,8 @@ SYMBOLS = {
     "slamcu_get_stream": (_vp, [_vp]),
     "slamcu_synchronize": (_i, [_vp]),
     "slamcu_launch_count": (C.c_int64, [_vp]),
+    "slamcu_alloc_pinned": (_i, [C.c_size_t, C.POINTER(_vp)]),
+    "slamcu_free_pinned": (None, [_vp]),
     "slamcu_popc_peak": (_i, [_vp, C.POINTER(C.c_double)]),
     "slamcu_profile_enable": (_i, [_vp, _i]),
     "slamcu_profile_read": (_i, [_vp, _i, C.c_char_p, _i, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),

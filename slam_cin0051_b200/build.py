@@ -56,5 +56,28 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return OUT
 
 
+def build_host_tools(verbose: bool = False) -> list:
+    """Host C++ programs above the C ABI: tools/cli/slam_bench and test/frontend/test_frontend_cuda (g++, no CUDA
+    headers needed; they link libslamcu.so with an rpath to the package directory)."""
+    root = os.path.normpath(os.path.join(HERE, ".."))
+    outdir = os.path.join(HERE, "build")
+    os.makedirs(outdir, exist_ok=True)
+    outs = []
+    for src, name in ((os.path.join(root, "tools", "cli", "slam_bench.cpp"), "slam_bench"),
+                      (os.path.join(root, "test", "frontend", "test_frontend_cuda.cpp"), "test_frontend_cuda")):
+        out = os.path.join(outdir, name)
+        deps = [src, os.path.join(root, "include", "slam", "cuda", "frontend.hpp"), os.path.join(root, "include", "slam", "cuda", "slamcu.h"),
+                os.path.join(root, "include", "slam", "cuda", "yaml_lite.hpp")]
+        if not os.path.exists(out) or _newest(deps) > os.path.getmtime(out):
+            cmd = ["g++", "-O2", "-std=c++17", "-Wall", "-I", os.path.join(root, "include"), src, "-o", out, "-L", HERE, "-lslamcu",
+                   "-Wl,-rpath," + HERE, "-Wl,-rpath,/usr/local/cuda/lib64"]
+            if verbose:
+                print(" ".join(cmd))
+            subprocess.check_call(cmd)
+        outs.append(out)
+    return outs
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_host_tools(verbose="-v" in sys.argv))

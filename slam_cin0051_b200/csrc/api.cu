@@ -261,6 +261,15 @@ int slamcu_synchronize(slamcu_context* ctx) {
 }
 int64_t slamcu_launch_count(const slamcu_context* ctx) { return ctx ? ctx->launches : 0; }
 
+int slamcu_alloc_pinned(size_t bytes, void** out) {
+    if (!out) return SLAMCU_INVALID_ARGUMENT;
+    *out = nullptr;
+    return cudaMallocHost(out, bytes ? bytes : 1) == cudaSuccess ? SLAMCU_OK : SLAMCU_CUDA_ERROR;
+}
+void slamcu_free_pinned(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
 int slamcu_popc_peak(slamcu_context* ctx, double* gpopc_per_s) {
     if (!ctx || !gpopc_per_s) return SLAMCU_INVALID_ARGUMENT;
     CU(ctx, cudaSetDevice(ctx->device));
@@ -1043,6 +1052,8 @@ int slamcu_compute(slamcu_detector* d, const uint8_t* image, int rows, int cols,
     slamcu_context* ctx = d->ctx;
     if (n < 0) return fail(ctx, SLAMCU_INVALID_ARGUMENT, "negative keypoint count");
     if (n == 0) return SLAMCU_OK;  // reference: descriptors = DescriptorMatrix(0, 0) (feature_detector.cpp:22-25)
+    if (d->mode == SLAMCU_MODE_ORB)
+        return fail(ctx, SLAMCU_UNSUPPORTED, "compute() on caller-supplied keypoints is a reference-mode call; ORB mode extracts with detectAndCompute()");
     if (!kps || !desc) return fail(ctx, SLAMCU_INVALID_ARGUMENT, "null keypoints / descriptors");
     int rc = check_image(ctx, image, rows, cols, stride);
     if (rc != SLAMCU_OK) return rc;

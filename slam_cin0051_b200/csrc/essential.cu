@@ -33,7 +33,7 @@ struct CvRng {
     }
 };
 
-// linear polynomial (x, y, z, 1) products; monomial orders as in oracle/essential_oracle.py
+// linear polynomial (x, y, z, 1) products; monomial orders documented in DESIGN.md (x, y, z, 1 | xx, yy, zz, xy, xz, yz, x, y, z, 1 | Nister order)
 __device__ void mul11(const double* a, const double* b, double* out /*10, accumulated*/, double sign) {
 #pragma unroll
     for (int i = 0; i < 4; i++)

@@ -1,0 +1,101 @@
+// test_frontend_cuda -- the reference's three frontend smoke tests (test/frontend/test_feature_detector.cpp,
+// test_feature_matcher.cpp, test_pose_estimator.cpp) re-seated on the CUDA adapters, with VALUE output: it prints
+// counts and FNV-1a-64 digests of every result so that tests/test_gpu_cpp_host.py can compare the C++ host path with
+// the oracle.  Images are binary PGM (the reference reads PNG through OpenCV, which this image does not have in C++).
+//
+//   test_frontend_cuda image0.pgm image1.pgm detector.yml matcher.yml [fx fy cx cy]
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <string>
+#include <vector>
+
+#include <slam/cuda/frontend.hpp>
+
+using namespace slam::cuda;
+
+static GrayMatrix read_pgm(const std::string& path) {
+    std::ifstream in(path, std::ios::binary);
+    std::string magic;
+    int w = 0, h = 0, maxv = 0;
+    in >> magic >> w >> h >> maxv;
+    in.get();
+    if (!in || magic != "P5" || maxv != 255) throw std::runtime_error("Could not read image: " + path);
+    GrayMatrix m(h, w);
+    in.read(reinterpret_cast<char*>(m.data()), static_cast<std::streamsize>(h) * w);
+    if (in.gcount() != static_cast<std::streamsize>(h) * w) throw std::runtime_error("Truncated image: " + path);
+    return m;
+}
+
+static unsigned long long fnv(const void* p, size_t n, unsigned long long h = 1469598103934665603ULL) {
+    const unsigned char* b = static_cast<const unsigned char*>(p);
+    for (size_t i = 0; i < n; i++) { h ^= b[i]; h *= 1099511628211ULL; }
+    return h;
+}
+
+int main(int argc, char** argv) {
+    if (argc < 5) {
+        std::fprintf(stderr, "usage: %s image0.pgm image1.pgm detector.yml matcher.yml [fx fy cx cy]\n", argv[0]);
+        return -1;
+    }
+    try {
+        const GrayMatrix img0 = read_pgm(argv[1]), img1 = read_pgm(argv[2]);
+        FeatureDetector detector(argv[3]);
+        FeatureMatcher matcher(argv[4]);
+        // test_feature_detector.cpp: detect, compute, detectAndCompute
+        std::vector<Keypoint> kps;
+        detector.detect(img0, kps);
+        std::vector<Keypoint> kps0, kps1;
+        DescriptorMatrix desc0, desc1;
+        detector.detectAndCompute(img0, kps0, desc0);
+        detector.detectAndCompute(img1, kps1, desc1);
+        bool same = kps.size() == kps0.size();
+        try {
+            DescriptorMatrix desc;
+            detector.compute(img0, kps, desc);
+            same = same && fnv(desc.data(), desc.rows() * desc.cols()) == fnv(desc0.data(), desc0.rows() * desc0.cols());
+        } catch (const std::runtime_error& e) {  // ORB mode: compute() on supplied keypoints is not offered
+            std::fprintf(stderr, "compute: %s\n", e.what());
+        }
+        if (!same) {
+            std::fprintf(stderr, "detect+compute differs from detectAndCompute\n");
+            return -1;
+        }
+        std::printf("kp0 %zu %016llx desc0 %016llx\n", kps0.size(), fnv(kps0.data(), kps0.size() * sizeof(Keypoint)),
+                    fnv(desc0.data(), static_cast<size_t>(desc0.rows() * desc0.cols())));
+        std::printf("kp1 %zu %016llx desc1 %016llx\n", kps1.size(), fnv(kps1.data(), kps1.size() * sizeof(Keypoint)),
+                    fnv(desc1.data(), static_cast<size_t>(desc1.rows() * desc1.cols())));
+        // test_feature_matcher.cpp: match WITH keypoints; test_pose_estimator.cpp: match WITHOUT keypoints
+        std::vector<Match> mk, mn;
+        matcher.match(desc0, desc1, mk, kps0, kps1);
+        matcher.match(desc0, desc1, mn);
+        std::printf("match_kp %zu %016llx match_nokp %zu %016llx\n", mk.size(), fnv(mk.data(), mk.size() * sizeof(Match)), mn.size(),
+                    fnv(mn.data(), mn.size() * sizeof(Match)));
+        // empty descriptors -> std::invalid_argument("Empty descriptors provided.") like feature_matcher.cpp:99-102
+        try {
+            std::vector<Match> none;
+            matcher.match(DescriptorMatrix(0, 32), desc1, none);
+            std::fprintf(stderr, "expected std::invalid_argument\n");
+            return -1;
+        } catch (const std::invalid_argument& e) {
+            std::printf("empty: %s\n", e.what());
+        }
+        if (argc >= 9) {  // PoseEstimator::estimate up to E (pose_estimator.cpp:18-47)
+            const double K4[4] = {std::atof(argv[5]), std::atof(argv[6]), std::atof(argv[7]), std::atof(argv[8])};
+            std::vector<float> p1, p2;
+            for (const Match& m : mn) {
+                p1.push_back(kps0[m.queryIdx].x); p1.push_back(kps0[m.queryIdx].y);
+                p2.push_back(kps1[m.trainIdx].x); p2.push_back(kps1[m.trainIdx].y);
+            }
+            const EssentialResult r = EssentialSolver(K4).solve(p1, p2);
+            std::printf("essential valid %d inliers %d of %zu mask %016llx E", r.valid ? 1 : 0, r.inliers, mn.size(),
+                        fnv(r.mask.data(), r.mask.size()));
+            for (double v : r.E) std::printf(" %.17g", v);
+            std::printf("\n");
+        }
+    } catch (const std::exception& e) {
+        std::fprintf(stderr, "Exception: %s\n", e.what());
+        return -1;
+    }
+    return 0;
+}
