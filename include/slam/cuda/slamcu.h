@@ -209,10 +209,14 @@ int slamcu_sequence_download(slamcu_sequence* seq, int first, int n, slamcu_keyp
  * include/slam/model/model.hpp:20-27): upload -> detectAndCompute -> match(f, f+1) -> download, software-pipelined
  * in chunks of `chunk` frames (<= 0: 64) over separate H2D / compute / D2H streams.  host_frames: n frames of
  * rows x stride bytes (pinned for overlap); outputs as in slamcu_sequence_download (any may be NULL; pinned).
- * Asynchronous: slamcu_synchronize() waits for the downloads too. */
+ * Asynchronous: slamcu_sequence_wait(seq) waits for this sequence's latest call (kernels and downloads),
+ * slamcu_synchronize() for everything.  Dependencies are tracked per sequence, so calls that alternate between two
+ * sequences double-buffer: the copies of one overlap the kernels of the other. */
 int slamcu_sequence_process(slamcu_sequence* seq, slamcu_detector* det, slamcu_matcher* m, const uint8_t* host_frames,
                             int stride, int n, int chunk, int with_keypoints, slamcu_keypoint* keypoints,
                             uint8_t* descriptors, slamcu_dmatch* matches, int32_t* counts4);
+
+int slamcu_sequence_wait(slamcu_sequence* seq);
 
 /* ---- image preparation (src/preprocessing) ---------------------------------------------------- */
 /* cv::cvtColor(BGR2GRAY) (preprocessor.cpp:136): gray = (3735 B + 19235 G + 9798 R + 16384) >> 15. */

@@ -144,6 +144,8 @@ struct slamcu_sequence {
     unsigned long long* sort_keys = nullptr;  // [F][cap_kp]
     int* h_counts = nullptr;                  // pinned [F][4]
     uint8_t* stage = nullptr;                 // [F][rows][cols] dense landing zone of linear H2D copies (lazy)
+    cudaEvent_t ev_compute_done = nullptr;    // last kernel of the latest slamcu_sequence_process call
+    cudaEvent_t ev_out_done = nullptr;        // last download of the latest slamcu_sequence_process call
     EssentialJob ess{};                       // per-pair two-view RANSAC working set (lazy)
     bool has_ess = false;
     std::vector<void*> ess_owned;
@@ -257,6 +259,8 @@ void* slamcu_get_stream(slamcu_context* ctx) { return ctx ? ctx->stream : nullpt
 int slamcu_synchronize(slamcu_context* ctx) {
     if (!ctx) return SLAMCU_INVALID_ARGUMENT;
     CU(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->s_in) CU(ctx, cudaStreamSynchronize(ctx->s_in));
+    if (ctx->s_out) CU(ctx, cudaStreamSynchronize(ctx->s_out));
     return SLAMCU_OK;
 }
 int64_t slamcu_launch_count(const slamcu_context* ctx) { return ctx ? ctx->launches : 0; }
@@ -374,6 +378,9 @@ int slamcu_sequence_create(slamcu_context* ctx, int rows, int cols, int max_fram
     A(&s->sort_keys, F * max_kp, false);
     if (rc == SLAMCU_OK && cudaMallocHost(reinterpret_cast<void**>(&s->h_counts), F * 4 * sizeof(int)) != cudaSuccess)
         rc = fail(ctx, SLAMCU_CUDA_ERROR, "cudaMallocHost failed");
+    if (rc == SLAMCU_OK && (cudaEventCreateWithFlags(&s->ev_compute_done, cudaEventDisableTiming) != cudaSuccess ||
+                            cudaEventCreateWithFlags(&s->ev_out_done, cudaEventDisableTiming) != cudaSuccess))
+        rc = fail(ctx, SLAMCU_CUDA_ERROR, "cudaEventCreate failed");
     if (rc != SLAMCU_OK) {
         slamcu_sequence_destroy(s);
         return rc;
@@ -386,6 +393,10 @@ void slamcu_sequence_destroy(slamcu_sequence* s) {
     if (!s) return;
     cudaSetDevice(s->ctx->device);
     cudaStreamSynchronize(s->ctx->stream);
+    if (s->ctx->s_in) cudaStreamSynchronize(s->ctx->s_in);
+    if (s->ctx->s_out) cudaStreamSynchronize(s->ctx->s_out);
+    if (s->ev_compute_done) cudaEventDestroy(s->ev_compute_done);
+    if (s->ev_out_done) cudaEventDestroy(s->ev_out_done);
     for (void* p : s->owned) cudaFree(p);
     for (void* p : s->orb_owned) cudaFree(p);
     if (s->stage) cudaFree(s->stage);
@@ -765,6 +776,14 @@ int slamcu_sequence_download(slamcu_sequence* s, int first, int n, slamcu_keypoi
     return SLAMCU_OK;
 }
 
+int slamcu_sequence_wait(slamcu_sequence* s) {
+    if (!s) return SLAMCU_INVALID_ARGUMENT;
+    slamcu_context* ctx = s->ctx;
+    CU(ctx, cudaEventSynchronize(s->ev_compute_done));
+    CU(ctx, cudaEventSynchronize(s->ev_out_done));
+    return SLAMCU_OK;
+}
+
 static int ctx_pipeline_resources(slamcu_context* ctx, size_t n_events) {
     if (!ctx->s_in) CU(ctx, cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
     if (!ctx->s_out) CU(ctx, cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
@@ -791,18 +810,21 @@ int slamcu_sequence_process(slamcu_sequence* s, slamcu_detector* det, slamcu_mat
     if (n == 0) return SLAMCU_OK;
     if (chunk <= 0) chunk = 64;
     CU(ctx, cudaSetDevice(ctx->device));
-    const int n_chunks = (n + chunk - 1) / chunk;
+    std::vector<int> sizes;
+    for (int left = n; left > 0; left -= chunk) sizes.push_back(std::min(chunk, left));
+    const int n_chunks = (int)sizes.size();
     int rc = ctx_pipeline_resources(ctx, (size_t)2 * n_chunks + 2);
     if (rc != SLAMCU_OK) return rc;
     const SeqView& v = s->v;
     cudaStream_t cs = ctx->stream;
-    // everything already queued on the compute stream (e.g. the previous call) precedes the first copy
-    cudaEvent_t ev_start = ctx->events[2 * n_chunks];
-    CU(ctx, cudaEventRecord(ev_start, cs));
-    CU(ctx, cudaStreamWaitEvent(ctx->s_in, ev_start, 0));
-    CU(ctx, cudaStreamWaitEvent(ctx->s_out, ev_start, 0));
+    // hazards are per sequence: the new frames may overwrite this sequence's stores only after ITS previous kernels,
+    // and its kernels may overwrite the result arrays only after ITS previous downloads.  A call on another sequence
+    // (double buffering) therefore overlaps its copies with this one's kernels.
+    CU(ctx, cudaStreamWaitEvent(ctx->s_in, s->ev_compute_done, 0));
+    CU(ctx, cudaStreamWaitEvent(cs, s->ev_out_done, 0));
+    int f0 = 0;
     for (int c = 0; c < n_chunks; c++) {
-        const int f0 = c * chunk, cnt = std::min(chunk, n - f0);
+        const int cnt = sizes[c];
         bool rp = false;
         rc = seq_upload_async(s, f0, cnt, host_frames + (size_t)f0 * v.rows * stride, stride, ctx->s_in, &rp);
         if (rc != SLAMCU_OK) return rc;
@@ -831,6 +853,7 @@ int slamcu_sequence_process(slamcu_sequence* s, slamcu_detector* det, slamcu_mat
         if (matches && np > 0)
             CU(ctx, cudaMemcpyAsync(matches + (size_t)p0 * v.cap_kp, v.matches + (size_t)p0 * v.cap_kp,
                                     (size_t)np * v.cap_kp * sizeof(slamcu_dmatch), cudaMemcpyDeviceToHost, ctx->s_out));
+        f0 += cnt;
     }
     if (counts4) {
         CU(ctx, cudaMemcpy2DAsync(counts4 + 0, 16, v.n_kp, 4, 4, n, cudaMemcpyDeviceToHost, ctx->s_out));
@@ -838,10 +861,8 @@ int slamcu_sequence_process(slamcu_sequence* s, slamcu_detector* det, slamcu_mat
         CU(ctx, cudaMemcpy2DAsync(counts4 + 2, 16, v.n_raw, 4, 4, n, cudaMemcpyDeviceToHost, ctx->s_out));
         CU(ctx, cudaMemcpy2DAsync(counts4 + 3, 16, v.status, 4, 4, n, cudaMemcpyDeviceToHost, ctx->s_out));
     }
-    // join: slamcu_synchronize() on the context now also covers the downloads
-    cudaEvent_t ev_end = ctx->events[2 * n_chunks + 1];
-    CU(ctx, cudaEventRecord(ev_end, ctx->s_out));
-    CU(ctx, cudaStreamWaitEvent(cs, ev_end, 0));
+    CU(ctx, cudaEventRecord(s->ev_compute_done, cs));
+    CU(ctx, cudaEventRecord(s->ev_out_done, ctx->s_out));  // slamcu_sequence_wait() / slamcu_synchronize() cover it
     return SLAMCU_OK;
 }
 

@@ -122,6 +122,10 @@ class FrameSequence:
                                                                   mask.ctypes.data, cap, C.byref(n_pt)))
         return (E.reshape(3, 3) if n_in.value > 0 else None), mask[: n_pt.value].copy(), n_in.value, n_it.value
 
+    def wait(self):
+        """Blocks until the latest process_ptrs() call on this sequence (kernels and downloads) has finished."""
+        self.ctx.check(self.ctx.lib.slamcu_sequence_wait(self.handle))
+
     def download_ptrs(self, first, n, kps_ptr=None, desc_ptr=None, matches_ptr=None, counts_ptr=None):
         self.ctx.check(self.ctx.lib.slamcu_sequence_download(self.handle, first, n, C.c_void_p(kps_ptr or 0),
                                                              C.c_void_p(desc_ptr or 0), C.c_void_p(matches_ptr or 0),
