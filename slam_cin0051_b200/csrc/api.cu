@@ -81,6 +81,8 @@ struct slamcu_context {
 
 namespace {
 
+constexpr int kMaxMatchSlices = 32;
+
 int fail(slamcu_context* ctx, int status, const char* fmt, ...) {
     if (ctx) {
         char buf[512];
@@ -1233,7 +1235,7 @@ static int matcher_workspace(slamcu_matcher* m, int n1, int n2, int words) {
     CU(ctx, cudaMalloc(reinterpret_cast<void**>(&m->d2), (size_t)c2 * w * 4));
     CU(ctx, cudaMalloc(reinterpret_cast<void**>(&m->k1), (size_t)c1 * sizeof(slamcu_keypoint)));
     CU(ctx, cudaMalloc(reinterpret_cast<void**>(&m->k2), (size_t)c2 * sizeof(slamcu_keypoint)));
-    CU(ctx, cudaMalloc(reinterpret_cast<void**>(&m->cand), (size_t)c1 * sizeof(int4)));
+    CU(ctx, cudaMalloc(reinterpret_cast<void**>(&m->cand), (size_t)c1 * kMaxMatchSlices * sizeof(int4)));
     CU(ctx, cudaMalloc(reinterpret_cast<void**>(&m->matches), (size_t)c1 * sizeof(slamcu_dmatch)));
     CU(ctx, cudaMalloc(reinterpret_cast<void**>(&m->keys), (size_t)c1 * sizeof(unsigned long long)));
     CU(ctx, cudaMalloc(reinterpret_cast<void**>(&m->ors), (size_t)2 * w * 4));
@@ -1291,7 +1293,16 @@ static int match_common(slamcu_matcher* m, const uint8_t* d1, int n1, int width1
     j.desc_words = words;
     j.max_q = n1;
     j.cap_out = n1;
-    ctx->launches += launch_match(j, 1, m->p, emit, with_kp ? 1 : 0, m->keys, ctx->stream);
+    // a single problem: slice the train set so that the grid fills the device (>= ~4 blocks per SM), 128-descriptor
+    // tiles at least; the batched sequence path has thousands of blocks and does not need it
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+    const int q_blocks = (n1 + 127) / 128;
+    int n_seg = std::min(std::min((4 * sms + q_blocks - 1) / q_blocks, (n2 + 127) / 128), kMaxMatchSlices);
+    n_seg = std::max(n_seg, 1);
+    const int seg_len = ((n2 + n_seg - 1) / n_seg + 127) / 128 * 128;
+    n_seg = (n2 + seg_len - 1) / seg_len;
+    ctx->launches += launch_match(j, 1, m->p, emit, with_kp ? 1 : 0, m->keys, ctx->stream, n_seg, seg_len, (size_t)m->cap1);
     return check_launch(ctx, "match kernels");
 }
 

@@ -74,8 +74,10 @@ struct MatchJob {
     int desc_words, max_q, cap_out;
 };
 // sort_keys: [n_pairs][cand_pair_stride] 64-bit scratch for the top-K / sort stage
+// n_seg > 1 splits the train set into n_seg slices of seg_len descriptors (extra grid dimension, for single small
+// problems); job.cand must then hold n_seg blocks of seg_stride entries, slice 0 doubling as the merged result
 int launch_match(const MatchJob& job, int n_pairs, const MatchParams& p, bool emit_matches, int with_kp,
-                 unsigned long long* sort_keys, cudaStream_t st);
+                 unsigned long long* sort_keys, cudaStream_t st, int n_seg = 1, int seg_len = 0, size_t seg_stride = 0);
 
 int launch_repitch(const uint8_t* src, int stride, uint8_t* dst, int pitch, int cols, long long rows_total, cudaStream_t st);
 int launch_bgr2gray(const uint8_t* bgr, int rows, int cols, int stride, uint8_t* gray, int gstride, cudaStream_t st);

@@ -70,8 +70,10 @@ __device__ __forceinline__ int penalise(int dist, float qx, float qy, float tx, 
 }
 
 // W = descriptor words handled by the unrolled path (8 = 256 bits); W = 0 -> generic loop.
+// n_seg > 1: blockIdx.z selects a slice of the train set; each slice writes its own top-2 (cand + seg * seg_stride)
+// and merge_segments_kernel combines them -- the global top-2 by (distance, index) is the top-2 of the slices' top-2s.
 template <int W>
-__global__ void __launch_bounds__(QT) match_kernel(MatchJob job, int with_kp) {
+__global__ void __launch_bounds__(QT) match_kernel(MatchJob job, int with_kp, int n_seg, int seg_len, size_t seg_stride) {
     extern __shared__ __align__(16) uint32_t smem[];
     const int pair = blockIdx.y;
     const int nq = job.nq[(size_t)pair * job.count_stride];
@@ -111,8 +113,10 @@ __global__ void __launch_bounds__(QT) match_kernel(MatchJob job, int with_kp) {
     const bool packed = W == 8 && !with_kp && wmax > 2 && nt <= (1 << kKeyShift);
     uint32_t kbest = 0xffffffffu, ksecond = 0xffffffffu;
 
-    for (int t0 = 0; t0 < nt; t0 += TT) {
-        const int cnt = min(TT, nt - t0);
+    const int t_begin = n_seg > 1 ? (int)blockIdx.z * seg_len : 0;
+    const int t_end = n_seg > 1 ? min(nt, t_begin + seg_len) : nt;
+    for (int t0 = t_begin; t0 < t_end; t0 += TT) {
+        const int cnt = min(TT, t_end - t0);
         __syncthreads();
         if ((dw & 3) == 0) {
             const uint4* src = reinterpret_cast<const uint4*>(dt + (size_t)t0 * dw);
@@ -168,7 +172,21 @@ __global__ void __launch_bounds__(QT) match_kernel(MatchJob job, int with_kp) {
         if (kbest != 0xffffffffu) { t.best = (int)(kbest >> kKeyShift); t.bidx = (int)(kbest & ((1u << kKeyShift) - 1)); }
         if (ksecond != 0xffffffffu) { t.second = (int)(ksecond >> kKeyShift); t.sidx = (int)(ksecond & ((1u << kKeyShift) - 1)); }
     }
-    if (qok) job.cand[(size_t)pair * job.cand_pair_stride + q] = make_int4(t.bidx, t.best, t.second, t.sidx);
+    if (qok) job.cand[(size_t)blockIdx.z * seg_stride + (size_t)pair * job.cand_pair_stride + q] = make_int4(t.bidx, t.best, t.second, t.sidx);
+}
+
+__global__ void __launch_bounds__(256) merge_segments_kernel(MatchJob job, int n_seg, size_t seg_stride) {
+    const int pair = blockIdx.y;
+    const int nq = job.nq[(size_t)pair * job.count_stride];
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    Top2 t{INT_MAX, INT_MAX, -1, -1};
+    for (int s = 0; s < n_seg; s++) {  // slices are in ascending index order, so strict < keeps the lowest index
+        const int4 c = job.cand[(size_t)s * seg_stride + (size_t)pair * job.cand_pair_stride + q];
+        if (c.x >= 0) top2_update(t, c.y, c.x);
+        if (c.w >= 0) top2_update(t, c.z, c.w);
+    }
+    job.cand[(size_t)pair * job.cand_pair_stride + q] = make_int4(t.bidx, t.best, t.second, t.sidx);
 }
 
 struct MatchLess {  // sortPredicate: a.distance < b.distance (feature_matcher.cpp:192-194); key = dist<<32 | slot
@@ -273,13 +291,21 @@ __global__ void __launch_bounds__(256) finalize_kernel(MatchJob job, MatchParams
 }  // namespace
 
 int launch_match(const MatchJob& job, int n_pairs, const MatchParams& p, bool emit_matches, int with_kp,
-                 unsigned long long* sort_keys, cudaStream_t st) {
+                 unsigned long long* sort_keys, cudaStream_t st, int n_seg, int seg_len, size_t seg_stride) {
     if (n_pairs <= 0) return 0;
-    dim3 grid((job.max_q + QT - 1) / QT, n_pairs);
+    if (n_seg < 1) n_seg = 1;
+    dim3 grid((job.max_q + QT - 1) / QT, n_pairs, n_seg);
     const size_t smem = (size_t)TT * job.desc_words * 4 + TT * sizeof(float2);
-    if (job.desc_words == 8) SLAM_KERNEL("match", st, match_kernel<8><<<grid, QT, smem, st>>>(job, with_kp));
-    else SLAM_KERNEL("match", st, match_kernel<0><<<grid, QT, smem, st>>>(job, with_kp));
+    if (job.desc_words == 8)
+        SLAM_KERNEL("match", st, match_kernel<8><<<grid, QT, smem, st>>>(job, with_kp, n_seg, seg_len, seg_stride));
+    else
+        SLAM_KERNEL("match", st, match_kernel<0><<<grid, QT, smem, st>>>(job, with_kp, n_seg, seg_len, seg_stride));
     int launches = 1;
+    if (n_seg > 1) {
+        SLAM_KERNEL("match_merge", st,
+                    merge_segments_kernel<<<dim3((job.max_q + 255) / 256, n_pairs), 256, 0, st>>>(job, n_seg, seg_stride));
+        launches++;
+    }
     if (emit_matches) {
         const int smem_cap = 4096;
         SLAM_KERNEL("match_finalize", st, finalize_kernel<<<n_pairs, 256, smem_cap * sizeof(unsigned long long), st>>>(job, p, sort_keys, smem_cap));
