@@ -209,9 +209,10 @@ __device__ int disc_half_width(int dyi, int window, float fw) {
 }
 
 // Greedy radius suppression over the sorted list; one warp per frame.
-__global__ void __launch_bounds__(32) nms_kernel(SeqView s, int first_frame, int window, int use_smem) {
+__global__ void __launch_bounds__(32) nms_kernel(SeqView s, int first_frame, int window, int use_smem, int only_flagged) {
     extern __shared__ uint32_t sbits[];
     const int f = first_frame + blockIdx.x;
+    if (only_flagged && s.n_kp[f] != -1) return;  // already done by nms_parallel_kernel
     const int n = s.n_raw[f];
     const unsigned lane = lane_id();
     const uint32_t* keys = s.keys + (size_t)f * s.cap_raw;
@@ -300,12 +301,207 @@ __global__ void __launch_bounds__(32) nms_kernel(SeqView s, int first_frame, int
     }
 }
 
+// ---- exact greedy NMS, parallel form ------------------------------------------------------------------------------
+// The greedy walk of feature_detector.cpp:165-185 is the lexicographically-first maximal independent set of the
+// "closer than window" graph in sorted order.  It is computed here as a fixed point: a corner is KEPT once every
+// earlier-ranked neighbour is known to be suppressed, and SUPPRESSED once some earlier-ranked neighbour is known to be
+// kept; decided states are final, so by induction on the rank the result equals the sequential walk.
+//   * kept corners stamp their suppression disc into a 1-bit/pixel bitmap (the reference's float predicate decides the
+//     half width of every disc row), so "some earlier neighbour is kept" is one bit test.  (A kept corner that covers a
+//     still-undecided corner r is necessarily earlier: a later one could only be kept after r was suppressed.)
+//   * "every earlier neighbour is decided" scans a uniform grid (cell >= window, 3x3 cells cover the disc) whose
+//     per-cell lists are sorted by rank, and stops at the first earlier neighbour that is still undecided.
+// Everything lives in shared memory, one block per frame.  Frames that do not fit (n_kp = -1) are left to the
+// one-warp walker above.
+constexpr int kNmsThreads = 1024;
+enum : uint8_t { kUnknown = 0, kKept = 1, kSuppressed = 2 };
+
+__global__ void __launch_bounds__(kNmsThreads) nms_parallel_kernel(SeqView s, int first_frame, int window, int smem_bytes) {
+    extern __shared__ __align__(16) uint8_t nsm[];
+    __shared__ int sh_scan[kNmsThreads / 32];
+    __shared__ int sh_carry;
+    __shared__ short hwtab[kHwTab];
+    const int f = first_frame + blockIdx.x;
+    const int n = s.n_raw[f];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (n <= 0) {
+        if (tid == 0) s.n_kp[f] = 0;
+        return;
+    }
+    const int bm_words = s.rows * s.mwords;
+    const int nrows = 2 * window - 1;
+    // grid geometry: the smallest cell >= window whose table fits next to the bitmap and the per-corner arrays
+    int cell = window;
+    int gw = (s.cols + cell - 1) / cell, gh = (s.rows + cell - 1) / cell;
+    const long long per_corner = 4 + 2 + 1;  // position, cell-list entry (u16), state
+    const long long avail_cells = ((long long)smem_bytes - 4LL * bm_words - per_corner * n - 64) / 8 - 2;
+    while ((long long)gw * gh > avail_cells && cell < 4096) {
+        cell += max(cell / 4, 1);
+        gw = (s.cols + cell - 1) / cell;
+        gh = (s.rows + cell - 1) / cell;
+    }
+    const int ncell = gw * gh;
+    if (n >= 65536 || (long long)ncell > avail_cells || nrows > kHwTab) {  // does not fit: the sequential walker takes it
+        if (tid == 0) s.n_kp[f] = -1;
+        return;
+    }
+    uint32_t* bm = reinterpret_cast<uint32_t*>(nsm);                        // [rows][mwords] suppressed pixels
+    uint32_t* pxy = bm + bm_words;                                          // [n]  (y << 16) | x by rank
+    int* cstart = reinterpret_cast<int*>(pxy + n);                          // [ncell + 1]
+    int* cfill = cstart + ncell + 1;                                         // [ncell]
+    uint16_t* clist = reinterpret_cast<uint16_t*>(cfill + ncell);           // [n] ranks grouped by cell, ascending
+    uint8_t* state = reinterpret_cast<uint8_t*>(clist + n + (n & 1));       // [n]
+    const uint32_t* keys = s.keys + (size_t)f * s.cap_raw;
+    const uint32_t* xy = s.raw_xy + (size_t)f * s.cap_raw;
+    const float fw = (float)window;
+    for (int i = tid; i < bm_words; i += kNmsThreads) bm[i] = 0u;
+    for (int i = tid; i <= ncell; i += kNmsThreads) cstart[i] = 0;
+    for (int r = tid; r < nrows; r += kNmsThreads) hwtab[r] = (short)disc_half_width(r - (window - 1), window, fw);
+    __syncthreads();
+    for (int r = tid; r < n; r += kNmsThreads) {
+        const uint32_t p = xy[keys[r] & kKeyIdxMask];
+        pxy[r] = p;
+        state[r] = kUnknown;
+        atomicAdd(&cstart[((p >> 16) / cell) * gw + (p & 0xffff) / cell], 1);
+    }
+    __syncthreads();
+    // exclusive scan of the cell counts
+    if (tid == 0) sh_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < ncell; base += kNmsThreads) {
+        const int i = base + tid;
+        const int v = i < ncell ? cstart[i] : 0;
+        int inc = v;
+#pragma unroll
+        for (int q = 1; q < 32; q <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, inc, q);
+            if (lane >= q) inc += t;
+        }
+        if (lane == 31) sh_scan[warp] = inc;
+        __syncthreads();
+        int off = sh_carry;
+        for (int w = 0; w < warp; w++) off += sh_scan[w];
+        if (i < ncell) {
+            cstart[i] = off + inc - v;
+            cfill[i] = off + inc - v;
+        }
+        __syncthreads();
+        if (tid == kNmsThreads - 1) sh_carry = off + inc;
+        __syncthreads();
+    }
+    if (tid == 0) cstart[ncell] = n;
+    __syncthreads();
+    for (int r = tid; r < n; r += kNmsThreads) {
+        const uint32_t p = pxy[r];
+        clist[atomicAdd(&cfill[((p >> 16) / cell) * gw + (p & 0xffff) / cell], 1)] = (uint16_t)r;
+    }
+    __syncthreads();
+    for (int c = tid; c < ncell; c += kNmsThreads) {  // ascending rank inside every cell (insertion sort, short lists)
+        const int a = cstart[c], b = cstart[c + 1];
+        for (int i = a + 1; i < b; i++) {
+            const uint16_t v = clist[i];
+            int j = i - 1;
+            while (j >= a && clist[j] > v) { clist[j + 1] = clist[j]; j--; }
+            clist[j + 1] = v;
+        }
+    }
+    __syncthreads();
+    // fixed-point rounds
+    for (;;) {
+        int pending = 0;
+        for (int r = tid; r < n; r += kNmsThreads) {
+            if (state[r] != kUnknown) continue;
+            const uint32_t p = pxy[r];
+            const int x = p & 0xffff, y = p >> 16;
+            if ((bm[y * s.mwords + (x >> 5)] >> (x & 31)) & 1u) {
+                state[r] = kSuppressed;
+                continue;
+            }
+            const int cx = x / cell, cy = y / cell;
+            bool wait = false, dead = false;
+            for (int ny = max(cy - 1, 0); ny <= min(cy + 1, gh - 1) && !(dead | wait); ny++)
+                for (int nx = max(cx - 1, 0); nx <= min(cx + 1, gw - 1) && !(dead | wait); nx++) {
+                    const int c = ny * gw + nx;
+                    for (int k = cstart[c]; k < cstart[c + 1]; k++) {
+                        const int j = clist[k];
+                        if (j >= r) break;  // ascending: only earlier ranks matter
+                        const uint8_t sj = state[j];
+                        if (sj == kSuppressed) continue;
+                        const uint32_t q = pxy[j];
+                        // feature_detector.cpp:177-183 (coordinates are integral floats)
+                        const float dx = (float)((int)(q & 0xffff) - x), dy = (float)((int)(q >> 16) - y);
+                        if (!(sqrtf((dx * dx) + (dy * dy)) < fw)) continue;
+                        if (sj == kKept) dead = true;  // kept this round, its disc is not stamped yet
+                        else wait = true;
+                        break;
+                    }
+                }
+            if (dead) {
+                state[r] = kSuppressed;
+            } else if (wait) {
+                pending = 1;
+            } else {
+                state[r] = kKept;
+                for (int ri = 0; ri < nrows; ri++) {  // stamp the suppression disc
+                    const int yy = y + ri - (window - 1);
+                    const int hw = hwtab[ri];
+                    if (yy < 0 || yy >= s.rows || hw < 0) continue;
+                    const int xa = max(x - hw, 0), xb = min(x + hw, s.cols - 1);
+                    for (int w = xa >> 5; w <= (xb >> 5); w++) {
+                        const int lo = max(xa, w * 32) - w * 32, hi = min(xb, w * 32 + 31) - w * 32;
+                        const uint32_t m = (hi == 31 ? 0xffffffffu : ((1u << (hi + 1)) - 1u)) & ~((1u << lo) - 1u);
+                        atomicOr(&bm[yy * s.mwords + w], m);
+                    }
+                }
+            }
+        }
+        if (!__syncthreads_or(pending)) break;
+    }
+    // ordered emission of the kept corners
+    slamcu_keypoint* out = s.kps + (size_t)f * s.cap_kp;
+    if (tid == 0) sh_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += kNmsThreads) {
+        const int r = base + tid;
+        const bool keep = r < n && state[r] == kKept;
+        const unsigned b = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) sh_scan[warp] = __popc(b);
+        __syncthreads();
+        int off = sh_carry;
+        for (int w = 0; w < warp; w++) off += sh_scan[w];
+        const int pos = off + __popc(b & lanemask_lt());
+        if (keep && pos < s.cap_kp) {
+            const uint32_t p = pxy[r];
+            slamcu_keypoint kp;
+            kp.x = (float)(p & 0xffff);
+            kp.y = (float)(p >> 16);
+            kp.size = 6.0f;
+            kp.angle = 0.0f;
+            kp.response = (float)(keys[r] >> kKeyIdxBits);
+            out[pos] = kp;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int tot = 0;
+            for (int w = 0; w < kNmsThreads / 32; w++) tot += sh_scan[w];
+            sh_carry += tot;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        const int kept = sh_carry;
+        s.n_kp[f] = min(kept, s.cap_kp);
+        if (kept > s.cap_kp) atomicOr(&s.status[f], kStKpOverflow);
+    }
+}
+
 }  // namespace
 
 // per-device opt-in to large dynamic shared memory (called from slamcu_create)
 void init_sortnms_attributes(int smem_optin) {
     cudaFuncSetAttribute(sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin - 1024);
     cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin - 1024);
+    cudaFuncSetAttribute(nms_parallel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin - 4096);
 }
 
 int launch_sort_nms(const SeqView& s, int first, int n, const DetParams& p, int smem_optin, cudaStream_t st) {
@@ -315,8 +511,10 @@ int launch_sort_nms(const SeqView& s, int first, int n, const DetParams& p, int 
     SLAM_KERNEL("sort", st, sort_kernel<<<n, 256, sort_smem, st>>>(s, first, smem_keys));
     const size_t bm_bytes = (size_t)s.rows * s.mwords * 4;
     const int use_smem = bm_bytes <= (size_t)(smem_optin - 1024);
-    SLAM_KERNEL("nms", st, nms_kernel<<<n, 32, use_smem ? bm_bytes : 0, st>>>(s, first, p.window, use_smem));
-    return 2;
+    const int par_smem = smem_optin - 4096;  // leaves room for the kernel's static shared memory
+    SLAM_KERNEL("nms", st, nms_parallel_kernel<<<n, kNmsThreads, par_smem, st>>>(s, first, p.window, par_smem));
+    SLAM_KERNEL("nms_fallback", st, nms_kernel<<<n, 32, use_smem ? bm_bytes : 0, st>>>(s, first, p.window, use_smem, 1));
+    return 3;
 }
 
 }  // namespace slamcu
