@@ -283,6 +283,26 @@ public:
         r.valid = r.inliers > 0;
         return r;
     }
+    // PoseEstimator::estimate end to end: findEssentialMat + simpleRecoverPose (simple_pose_recover.cpp:35-97).
+    // valid == false where the reference logs a warning and leaves R, t untouched.
+    struct Pose {
+        bool valid = false;
+        double R[9]{}, t[3]{}, E[9]{};
+        int inliers = 0, front[4]{};
+        std::vector<uint8_t> mask;
+    };
+    Pose estimate(const std::vector<float>& pts1, const std::vector<float>& pts2) const {
+        Pose p;
+        const int n = static_cast<int>(pts1.size() / 2);
+        if (n < 8) return p;
+        p.mask.resize(static_cast<size_t>(n));
+        const int st = slamcu_estimate_pose(m_ctx.get(), pts1.data(), pts2.data(), n, m_K, p.E, p.mask.data(), &p.inliers, p.R, p.t, p.front);
+        if (st == SLAMCU_EMPTY_INPUT) return p;
+        m_ctx.check(st);
+        p.valid = true;
+        return p;
+    }
+
 private:
     Context& m_ctx;
     double m_K[4]{};

@@ -242,6 +242,13 @@ int slamcu_ransac_score(slamcu_context* ctx, const double* models9, int n_models
  * pose_estimator.cpp:22-26). */
 int slamcu_find_essential(slamcu_context* ctx, const float* p1, const float* p2, int n, const double* K4, double prob,
                           double threshold, int max_iters, double* E9, uint8_t* mask, int* n_inliers);
+/* PoseEstimator::estimate (pose_estimator.cpp:18-67) end to end: findEssentialMat as above (defaults 0.999, 1.0, 1000),
+ * then simpleRecoverPose (simple_pose_recover.cpp:35-97): E -> R1, R2, +-t by SVD and the cheirality vote over all
+ * correspondences (4x4 DLT per point and candidate).  R9 row-major, t3 unit norm, front4 = points in front of both
+ * cameras for the candidates (R1,t), (R2,t), (R1,-t), (R2,-t).  n < 8 or no accepted hypothesis -> SLAMCU_EMPTY_INPUT
+ * (the reference logs a warning and returns without touching R, t). */
+int slamcu_estimate_pose(slamcu_context* ctx, const float* p1, const float* p2, int n, const double* K4, double* E9, uint8_t* mask,
+                         int* n_inliers, double* R9, double* t3, int32_t* front4);
 /* Stage probe: the 5-point minimal solver on n_samples independent samples.  x1/x2: [n_samples][5][2] normalised
  * coordinates; models: [n_samples][10][9] (row-major E, unit norm); counts[n_samples] = solutions per sample. */
 int slamcu_fivept_solve(slamcu_context* ctx, const double* x1, const double* x2, int n_samples, double* models,

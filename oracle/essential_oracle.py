@@ -282,3 +282,46 @@ def find_essential(p1, p2, K4, prob=0.999, threshold=1.0, max_iters=1000, solver
     if return_trace:
         return bestE, bestmask, best, trace, it
     return bestE, bestmask, best
+
+
+# ---- simpleRecoverPose (src/frontend/simple_pose_recover.cpp:6-97) as PoseEstimator::estimate calls it ---------------------
+def _svd(a, backend):
+    """(w, u, vt) with cv::SVD's conventions when backend is cv2 (cv2.SVDecomp), else LAPACK's."""
+    if backend is not None:
+        w, u, vt = backend.SVDecomp(np.ascontiguousarray(a, np.float64))
+        return w.ravel(), u, vt
+    u, w, vt = np.linalg.svd(np.asarray(a, np.float64))
+    return w, u, vt
+
+
+def simple_recover_pose(E, p1, p2, K4, backend=None):
+    """E: 3x3; p1, p2: (n, 2) float32 PIXEL coordinates; returns (R, t (3,1), front[4]).
+
+    Follows pose_estimator.cpp:53-66 + simple_pose_recover.cpp literally: the points are normalised by K and stored as
+    float (cv::Point2f), yet the candidate projections are K [R|t]; first maximum of the cheirality vote wins."""
+    fx, fy, cx, cy = K4
+    K = np.array([[fx, 0, cx], [0, fy, cy], [0, 0, 1.0]])
+    n1 = np.stack([((p1[:, 0].astype(np.float64) - cx) / fx), ((p1[:, 1].astype(np.float64) - cy) / fy)], 1).astype(F32)
+    n2 = np.stack([((p2[:, 0].astype(np.float64) - cx) / fx), ((p2[:, 1].astype(np.float64) - cy) / fy)], 1).astype(F32)
+    w, u, vt = _svd(E, backend)
+    W = np.array([[0, -1, 0], [1, 0, 0], [0, 0, 1.0]])
+    R1, R2, t = u @ W @ vt, u @ W.T @ vt, u[:, 2:3].copy()
+    if np.linalg.det(R1) < 0:
+        R1 = -R1
+    if np.linalg.det(R2) < 0:
+        R2 = -R2
+    cands = [(R1, t), (R2, t), (R1, -t), (R2, -t)]
+    KP0 = K @ np.eye(3, 4)
+    front = []
+    for R, tt in cands:
+        KP = K @ np.hstack([R, tt])
+        cnt = 0
+        for a, b in zip(n1.astype(np.float64), n2.astype(np.float64)):
+            A = np.stack([a[0] * KP0[2] - KP0[0], a[1] * KP0[2] - KP0[1], b[0] * KP[2] - KP[0], b[1] * KP[2] - KP[1]])
+            _, _, v = _svd(A, backend)
+            X = v[3] / v[3][3]
+            cnt += (X[2] > 0) and ((KP @ X)[2] > 0)
+        front.append(int(cnt))
+    best = int(np.argmax(front))  # first maximum
+    R, tt = cands[best]
+    return R, tt, front

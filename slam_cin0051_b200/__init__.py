@@ -8,7 +8,7 @@ sequence.py (device-resident batched path).  No CPU fallback anywhere.
 from ._lib import KEYPOINT_DTYPE, KNN2_DTYPE, MATCH_DTYPE, Context, SlamcuError, load  # noqa: F401
 from .common import Camera, bgr_to_gray  # noqa: F401
 from .frontend import FeatureDetector, FeatureMatcher  # noqa: F401
-from .pose import PoseEstimator, find_essential, fivept_solve, ransac_score  # noqa: F401
+from .pose import PoseEstimator, estimate_pose, find_essential, fivept_solve, ransac_score  # noqa: F401
 from .sequence import FrameSequence  # noqa: F401
 
 __all__ = ["Context", "SlamcuError", "FeatureDetector", "FeatureMatcher", "FrameSequence", "Camera", "bgr_to_gray", "PoseEstimator", "find_essential",

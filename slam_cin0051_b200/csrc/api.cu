@@ -1476,6 +1476,48 @@ int slamcu_find_essential(slamcu_context* ctx, const float* p1, const float* p2,
     return SLAMCU_OK;
 }
 
+int slamcu_estimate_pose(slamcu_context* ctx, const float* p1, const float* p2, int n, const double* K4, double* E9, uint8_t* mask,
+                         int* n_inliers, double* R9, double* t3, int32_t* front4) {
+    if (!ctx) return SLAMCU_INVALID_ARGUMENT;
+    if (!p1 || !p2 || !K4 || !R9 || !t3 || n < 0) return fail(ctx, SLAMCU_INVALID_ARGUMENT, "bad arguments");
+    if (n < 8) return fail(ctx, SLAMCU_EMPTY_INPUT, "Cannot estimate pose, not enough matches (%d). Required at least 8.", n);
+    double E[9];
+    int inl = 0;
+    int rc = slamcu_find_essential(ctx, p1, p2, n, K4, 0.999, 1.0, 1000, E, mask, &inl);  // leaves x1/x2/E in the scratch block
+    if (rc != SLAMCU_OK) return rc;
+    if (E9) memcpy(E9, E, sizeof E);
+    if (n_inliers) *n_inliers = inl;
+    if (inl <= 0) return fail(ctx, SLAMCU_EMPTY_INPUT, "Essential Matrix could not be computed.");
+    // rebuild the job view over the scratch block exactly as slamcu_find_essential laid it out
+    const size_t b_pts = ((size_t)n * 16 + 255) / 256 * 256, b_in = ((size_t)n * 8 + 255) / 256 * 256;
+    const size_t b_mask = ((size_t)n + 255) / 256 * 256;
+    uint8_t* base = static_cast<uint8_t*>(ctx->scratch);
+    EssentialJob j{};
+    j.x1 = reinterpret_cast<double2*>(base);
+    j.x2 = reinterpret_cast<double2*>(base + b_pts);
+    j.mask = base + 2 * b_pts + 2 * b_in;
+    uint8_t* tail = j.mask + b_mask;
+    j.E = reinterpret_cast<double*>(tail);
+    j.n_pts = reinterpret_cast<int*>(tail + 128);
+    j.pt_stride = n;
+    double* dR = reinterpret_cast<double*>(tail + 256);
+    double* dt = dR + 9;
+    int* dfront = reinterpret_cast<int*>(tail + 256 + 12 * 8);
+    {
+        ProfGuard pg(ctx);
+        ctx->launches += launch_recover_pose(j, 1, K4, dR, dt, dfront, ctx->stream);
+    }
+    rc = check_launch(ctx, "recover_pose");
+    if (rc != SLAMCU_OK) return rc;
+    int hf[4];
+    CU(ctx, cudaMemcpyAsync(R9, dR, 72, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(t3, dt, 24, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(hf, dfront, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    if (front4) memcpy(front4, hf, sizeof hf);
+    return SLAMCU_OK;
+}
+
 int slamcu_fivept_solve(slamcu_context* ctx, const double* x1, const double* x2, int n_samples, double* models, int32_t* counts) {
     if (!ctx) return SLAMCU_INVALID_ARGUMENT;
     if (!x1 || !x2 || !models || !counts || n_samples <= 0) return fail(ctx, SLAMCU_INVALID_ARGUMENT, "bad arguments");

@@ -103,6 +103,7 @@ void init_essential_attributes();
 int launch_essential_gather(const SeqView& s, int first, int n_pairs, const EssentialJob& job, const double* K4, cudaStream_t st);
 int launch_essential_normalise(const float* p1, const float* p2, int n, const EssentialJob& job, const double* K4, cudaStream_t st);
 int launch_essential_ransac(const EssentialJob& job, int n_pairs, cudaStream_t st);
+int launch_recover_pose(const EssentialJob& job, int n_pairs, const double* K4, double* R, double* t, int* front, cudaStream_t st);
 int launch_fivept_probe(const double* x1, const double* x2, int n_samples, double* models, int* counts, cudaStream_t st);
 
 // ---- optional per-kernel timing (CUDA events on the launching stream; bench.py's roofline input) ----

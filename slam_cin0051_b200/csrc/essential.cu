@@ -469,3 +469,171 @@ int launch_fivept_probe(const double* x1, const double* x2, int n_samples, doubl
 }
 
 }  // namespace slamcu
+
+// ---- simpleRecoverPose (src/frontend/simple_pose_recover.cpp:35-97) as called by PoseEstimator::estimate ---------------
+// E -> (R1, R2, +-t) through an SVD, then a cheirality vote: every correspondence is triangulated (4x4 DLT, smallest
+// right singular vector) against each of the four candidates and the candidate with the most points in front of both
+// cameras wins (first maximum).  Faithful to the reference including its quirk: the points are already normalised by K
+// (rounded to float, pose_estimator.cpp:58-64) and are still projected with K * [R | t] (simple_pose_recover.cpp:61-65).
+// cv::SVD is a one-sided Jacobi SVD; so is this one (sign / ordering conventions of the singular vectors do not change
+// the set of four candidates nor the triangulated points).  Tolerance is stated in tests/test_gpu_essential.py.
+namespace slamcu {
+namespace {
+
+// One-sided (Hestenes) Jacobi on the columns of an n x n matrix A (row-major, n <= 4); V accumulates the rotations.
+// On return the columns of A are U * diag(w); w[k] = column norms.
+template <int N>
+__device__ void jacobi_svd(double (&A)[N][N], double (&V)[N][N], double (&w)[N]) {
+    for (int i = 0; i < N; i++)
+        for (int j = 0; j < N; j++) V[i][j] = i == j ? 1.0 : 0.0;
+    for (int sweep = 0; sweep < 30; sweep++) {
+        bool changed = false;
+        for (int p = 0; p < N - 1; p++)
+            for (int q = p + 1; q < N; q++) {
+                double a = 0, b = 0, g = 0;
+                for (int k = 0; k < N; k++) { a += A[k][p] * A[k][p]; b += A[k][q] * A[k][q]; g += A[k][p] * A[k][q]; }
+                if (fabs(g) <= 2.220446049250313e-16 * sqrt(a * b)) continue;
+                changed = true;
+                const double beta = a - b, gamma = hypot(2.0 * g, beta);
+                double c, s;
+                if (beta < 0) {
+                    const double delta = (gamma - beta) * 0.5;
+                    s = sqrt(delta / gamma);
+                    c = g / (gamma * s);
+                } else {
+                    c = sqrt((gamma + beta) / (gamma * 2.0));
+                    s = g / (gamma * c);
+                }
+                for (int k = 0; k < N; k++) {
+                    const double t0 = c * A[k][p] + s * A[k][q], t1 = -s * A[k][p] + c * A[k][q];
+                    A[k][p] = t0; A[k][q] = t1;
+                    const double v0 = c * V[k][p] + s * V[k][q], v1 = -s * V[k][p] + c * V[k][q];
+                    V[k][p] = v0; V[k][q] = v1;
+                }
+            }
+        if (!changed) break;
+    }
+    for (int j = 0; j < N; j++) {
+        double nn = 0;
+        for (int k = 0; k < N; k++) nn += A[k][j] * A[k][j];
+        w[j] = sqrt(nn);
+    }
+}
+
+__device__ double det3(const double* m) {
+    return m[0] * (m[4] * m[8] - m[5] * m[7]) - m[1] * (m[3] * m[8] - m[5] * m[6]) + m[2] * (m[3] * m[7] - m[4] * m[6]);
+}
+
+__global__ void __launch_bounds__(128) recover_pose_kernel(EssentialJob job, double fx, double fy, double cx, double cy,
+                                                           double* Rout, double* tout, int* front_out) {
+    __shared__ double P[4][12];   // K * [R | t] for the four candidates
+    __shared__ double Rc[2][9], tc[3];
+    __shared__ int front[4];
+    const int pair = blockIdx.x;
+    const int n = job.n_pts[pair];
+    const double* E = job.E + (size_t)pair * 9;
+    const int tid = threadIdx.x;
+    if (tid < 4) front[tid] = 0;
+    if (tid == 0) {
+        double A[3][3], V[3][3], w[3];
+        for (int i = 0; i < 3; i++)
+            for (int j = 0; j < 3; j++) A[i][j] = E[3 * i + j];
+        jacobi_svd<3>(A, V, w);
+        // order the singular values descending (cv::SVD does); U columns = A columns / w
+        int ord[3] = {0, 1, 2};
+        for (int i = 0; i < 2; i++)
+            for (int j = i + 1; j < 3; j++)
+                if (w[ord[j]] > w[ord[i]]) { const int t = ord[i]; ord[i] = ord[j]; ord[j] = t; }
+        double U[3][3], Vt[3][3];
+        for (int c = 0; c < 3; c++) {
+            const int s = ord[c];
+            for (int k = 0; k < 3; k++) {
+                U[k][c] = w[s] > 0 ? A[k][s] / w[s] : 0.0;
+                Vt[c][k] = V[k][s];
+            }
+        }
+        // the null direction has no defined U column from A / w: complete the basis with a cross product
+        if (!(w[ord[2]] > 1e-12 * w[ord[0]])) {
+            U[0][2] = U[1][0] * U[2][1] - U[2][0] * U[1][1];
+            U[1][2] = U[2][0] * U[0][1] - U[0][0] * U[2][1];
+            U[2][2] = U[0][0] * U[1][1] - U[1][0] * U[0][1];
+        }
+        const double W[3][3] = {{0, -1, 0}, {1, 0, 0}, {0, 0, 1}};
+        for (int v = 0; v < 2; v++) {  // R1 = U W Vt, R2 = U W' Vt
+            double UW[3][3];
+            for (int i = 0; i < 3; i++)
+                for (int j = 0; j < 3; j++) {
+                    double acc = 0;
+                    for (int k = 0; k < 3; k++) acc += U[i][k] * (v == 0 ? W[k][j] : W[j][k]);
+                    UW[i][j] = acc;
+                }
+            for (int i = 0; i < 3; i++)
+                for (int j = 0; j < 3; j++) {
+                    double acc = 0;
+                    for (int k = 0; k < 3; k++) acc += UW[i][k] * Vt[k][j];
+                    Rc[v][3 * i + j] = acc;
+                }
+            if (det3(Rc[v]) < 0)
+                for (int k = 0; k < 9; k++) Rc[v][k] = -Rc[v][k];
+        }
+        for (int k = 0; k < 3; k++) tc[k] = U[k][2];
+        const double K[3][3] = {{fx, 0, cx}, {0, fy, cy}, {0, 0, 1}};
+        for (int c = 0; c < 4; c++) {
+            const double* R = Rc[c & 1];
+            const double sgn = c < 2 ? 1.0 : -1.0;
+            for (int i = 0; i < 3; i++)
+                for (int j = 0; j < 4; j++) {
+                    double acc = 0;
+                    for (int k = 0; k < 3; k++) acc += K[i][k] * (j < 3 ? R[3 * k + j] : sgn * tc[k]);
+                    P[c][4 * i + j] = acc;
+                }
+        }
+    }
+    __syncthreads();
+    const double P0[12] = {fx, 0, cx, 0, 0, fy, cy, 0, 0, 0, 1, 0};  // K * [I | 0]
+    const double2* x1 = job.x1 + (size_t)pair * job.pt_stride;
+    const double2* x2 = job.x2 + (size_t)pair * job.pt_stride;
+    int mine[4] = {0, 0, 0, 0};
+    for (int j = tid; j < n; j += blockDim.x) {
+        // Point2f((pt.x - cx) / fx, (pt.y - cy) / fy): the double quotient narrowed to float
+        const double ax = (double)(float)x1[j].x, ay = (double)(float)x1[j].y;
+        const double bx = (double)(float)x2[j].x, by = (double)(float)x2[j].y;
+        for (int c = 0; c < 4; c++) {
+            double A[4][4], V[4][4], w[4];
+            for (int k = 0; k < 4; k++) {
+                A[0][k] = ax * P0[8 + k] - P0[k];
+                A[1][k] = ay * P0[8 + k] - P0[4 + k];
+                A[2][k] = bx * P[c][8 + k] - P[c][k];
+                A[3][k] = by * P[c][8 + k] - P[c][4 + k];
+            }
+            jacobi_svd<4>(A, V, w);
+            int m = 0;
+            for (int k = 1; k < 4; k++)
+                if (w[k] < w[m]) m = k;
+            const double X0 = V[0][m] / V[3][m], X1 = V[1][m] / V[3][m], X2 = V[2][m] / V[3][m];
+            const double z1 = X2;
+            const double z2 = ((P[c][8] * X0 + P[c][9] * X1) + P[c][10] * X2) + P[c][11] * 1.0;
+            if (z1 > 0 && z2 > 0) mine[c]++;
+        }
+    }
+    for (int c = 0; c < 4; c++)
+        if (mine[c]) atomicAdd(&front[c], mine[c]);
+    __syncthreads();
+    if (tid == 0) {
+        int best = 0, maxFront = -1;
+        for (int c = 0; c < 4; c++)
+            if (front[c] > maxFront) { maxFront = front[c]; best = c; }
+        for (int k = 0; k < 9; k++) Rout[(size_t)pair * 9 + k] = Rc[best & 1][k];
+        for (int k = 0; k < 3; k++) tout[(size_t)pair * 3 + k] = best < 2 ? tc[k] : -tc[k];
+        for (int c = 0; c < 4; c++) front_out[(size_t)pair * 4 + c] = front[c];
+    }
+}
+
+}  // namespace
+
+int launch_recover_pose(const EssentialJob& job, int n_pairs, const double* K4, double* R, double* t, int* front, cudaStream_t st) {
+    SLAM_KERNEL("recover_pose", st, recover_pose_kernel<<<n_pairs, 128, 0, st>>>(job, K4[0], K4[1], K4[2], K4[3], R, t, front));
+    return 1;
+}
+
+}  // namespace slamcu

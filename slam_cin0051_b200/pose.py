@@ -32,6 +32,27 @@ def find_essential(points1, points2, K4, prob: float = 0.999, threshold: float =
     return E.reshape(3, 3), mask, n_in.value
 
 
+def estimate_pose(points1, points2, K4, context: Context | None = None):
+    """PoseEstimator::estimate on gathered pixel correspondences: findEssentialMat(RANSAC) + simpleRecoverPose.
+    Returns dict(E, mask, inliers, R, t, front) or None where the reference returns early (< 8 matches / no E)."""
+    ctx = context or Context.default()
+    p1 = np.ascontiguousarray(points1, np.float32).reshape(-1, 2)
+    p2 = np.ascontiguousarray(points2, np.float32).reshape(-1, 2)
+    if len(p1) < 8:
+        return None
+    k = np.ascontiguousarray(K4, np.float64)
+    E, R, t = np.zeros(9), np.zeros(9), np.zeros(3)
+    mask = np.zeros(len(p1), np.uint8)
+    front = np.zeros(4, np.int32)
+    n_in = C.c_int(0)
+    st = ctx.lib.slamcu_estimate_pose(ctx.handle, p1.ctypes.data, p2.ctypes.data, len(p1), k.ctypes.data, E.ctypes.data,
+                                      mask.ctypes.data, C.byref(n_in), R.ctypes.data, t.ctypes.data, front.ctypes.data)
+    if st == 2:  # SLAMCU_EMPTY_INPUT: the reference's early returns
+        return None
+    ctx.check(st)
+    return {"E": E.reshape(3, 3), "mask": mask, "inliers": n_in.value, "R": R.reshape(3, 3), "t": t.reshape(3, 1), "front": front}
+
+
 def fivept_solve(x1, x2, context: Context | None = None):
     """5-point minimal solver probe: x1, x2 (S, 5, 2) normalised points -> list of (k_s, 3, 3) arrays."""
     ctx = context or Context.default()
@@ -79,3 +100,19 @@ class PoseEstimator:
         p2 = np.stack([keypoints2["x"][t], keypoints2["y"][t]], 1)
         c = self.camera
         return find_essential(p1, p2, (c.fx, c.fy, c.cx, c.cy), context=self.ctx)
+
+    def estimate(self, keypoints1, keypoints2, matches):
+        """PoseEstimator::estimate: returns (R 3x3, t 3x1) or None where the reference leaves R, t untouched."""
+        m = np.asarray(matches)
+        if m.dtype.names:
+            q, t = m["queryIdx"], m["trainIdx"]
+        else:
+            m = m.reshape(-1, 2)
+            q, t = m[:, 0], m[:, 1]
+        if len(q) < 8:
+            return None
+        p1 = np.stack([keypoints1["x"][q], keypoints1["y"][q]], 1)
+        p2 = np.stack([keypoints2["x"][t], keypoints2["y"][t]], 1)
+        c = self.camera
+        r = estimate_pose(p1, p2, (c.fx, c.fy, c.cx, c.cy), context=self.ctx)
+        return None if r is None else (r["R"], r["t"])

@@ -92,6 +92,10 @@ int main(int argc, char** argv) {
                         fnv(r.mask.data(), r.mask.size()));
             for (double v : r.E) std::printf(" %.17g", v);
             std::printf("\n");
+            const EssentialSolver::Pose pose = EssentialSolver(K4).estimate(p1, p2);
+            std::printf("pose valid %d R", pose.valid ? 1 : 0);
+            for (double v : pose.R) std::printf(" %.17g", v);
+            std::printf(" t %.17g %.17g %.17g\n", pose.t[0], pose.t[1], pose.t[2]);
         }
     } catch (const std::exception& e) {
         std::fprintf(stderr, "Exception: %s\n", e.what());

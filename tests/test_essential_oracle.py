@@ -67,3 +67,16 @@ def test_five_point_solution_sets_match_cv2():
             assert np.abs(2 * M @ M.T @ M - np.trace(M @ M.T) * M).max() < 1e-6
     assert missed <= 2
     assert close >= 0.97 * total  # ill-conditioned samples may differ beyond 1e-6 between two correct solvers
+
+
+@pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p)[10:-4] for p in GOLD])
+def test_simple_recover_pose_equals_cv_svd_golden(path):
+    """simpleRecoverPose restated over LAPACK's SVD picks the same (R, t) as the restatement over cv::SVD (the committed
+    vectors): the labelling of the four candidates depends on the SVD's sign conventions, the winner does not."""
+    from oracle import essential_oracle as eo
+    g = np.load(path)
+    K = g["K"]
+    R, t, front = eo.simple_recover_pose(g["E"], g["p1"], g["p2"], (K[0, 0], K[1, 1], K[0, 2], K[1, 2]))
+    assert np.abs(R - g["R"]).max() < 1e-12 and np.abs(t - g["t"]).max() < 1e-12
+    assert sorted(front) == sorted(g["front"].tolist())
+    assert abs(np.linalg.det(R) - 1.0) < 1e-12 and np.abs(R.T @ R - np.eye(3)).max() < 1e-12  # test_pose_estimator.cpp:34-43

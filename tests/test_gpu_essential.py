@@ -113,3 +113,24 @@ def test_sequence_essential_equals_single_calls(gpu_ctx):
         E, mask, good, iters = seq.essential_result(f)
         assert good == good1 and np.array_equal(mask, mask1) and iters >= 1
         assert (E is None and E1 is None) or np.array_equal(E, E1)
+
+
+@pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p)[10:-4] for p in GOLD])
+def test_estimate_pose_equals_reference_restatement(gpu_ctx, path):
+    """PoseEstimator::estimate end to end (findEssentialMat + simpleRecoverPose).  Tolerance: R and t within 1e-9 of the
+    restatement over cv::SVD; the cheirality counts agree as a multiset (candidate labelling follows the SVD's signs)."""
+    import slam_cin0051_b200 as s
+    g = np.load(path)
+    r = s.estimate_pose(g["p1"], g["p2"], k4(g["K"]), context=gpu_ctx)
+    assert r is not None and r["inliers"] == int(g["mask"].sum()) and np.array_equal(r["mask"], g["mask"])
+    assert e_diff(r["E"], g["E"]) < E_TOL
+    assert np.abs(r["R"] - g["R"]).max() < 1e-9 and np.abs(r["t"] - g["t"]).max() < 1e-9
+    assert sorted(r["front"].tolist()) == sorted(g["front"].tolist())
+    # the reference's only hard check (test_pose_estimator.cpp:34-43): R is a rotation matrix
+    assert np.abs(r["R"].T @ r["R"] - np.eye(3)).max() < 1e-6 and abs(np.linalg.det(r["R"]) - 1.0) < 1e-9
+
+
+def test_estimate_pose_early_returns(gpu_ctx):
+    import slam_cin0051_b200 as s
+    g = np.load(GOLD[0])
+    assert s.estimate_pose(g["p1"][:7], g["p2"][:7], k4(g["K"]), context=gpu_ctx) is None  # pose_estimator.cpp:22-26

@@ -59,8 +59,11 @@ def main():
     }
     for name, (p1, p2, K) in cases.items():
         E, mask = cv2.findEssentialMat(p1, p2, K, method=cv2.RANSAC, prob=0.999, threshold=1.0)
+        # R, t: the reference's simpleRecoverPose restated over cv2.SVDecomp (= cv::SVD), on ALL correspondences
+        from oracle import essential_oracle as eo
+        R, t, front = eo.simple_recover_pose(E, p1, p2, (K[0, 0], K[1, 1], K[0, 2], K[1, 2]), backend=cv2)
         np.savez_compressed(os.path.join(OUT, f"essential_{name}.npz"), p1=p1, p2=p2, K=K, E=E, mask=mask.ravel().astype(np.uint8),
-                            cv2_version=cv2.__version__)
+                            R=R, t=t, front=np.array(front, np.int32), cv2_version=cv2.__version__)
         print(name, len(p1), "inliers", int(mask.sum()), E.shape)
 
 
