@@ -195,15 +195,24 @@ __global__ void __launch_bounds__(256) fast9_mask_kernel(SeqView s, OrbView o, i
     const uint8_t* img = level_ptr(s, o, f, l);
     // ---- phase 0
     constexpr int VPR = FSW / 16;
-    for (int v = threadIdx.x; v < FSH * VPR; v += 256) {
-        const int r = v / VPR, cv = v - r * VPR;
-        const int gy = y0 - 4 + r, gx = x0 - FHX + cv * 16;
-        uint4 val = make_uint4(0, 0, 0, 0);
-        if (gy >= 0 && gy < L.rows && gx >= 0 && gx < L.pitch)
-            val = __ldg(reinterpret_cast<const uint4*>(img + (size_t)gy * L.pitch + gx));
-        *reinterpret_cast<uint4*>(tile + r * FSW + cv * 16) = val;
+    {
+        uint4 val[2];  // both 128-bit loads of a thread are in flight before the first store
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const int v = threadIdx.x + 256 * k;
+            const int r = v / VPR, cv = v - r * VPR;
+            const int gy = y0 - 4 + r, gx = x0 - FHX + cv * 16;
+            val[k] = make_uint4(0, 0, 0, 0);
+            if (v < FSH * VPR && gy >= 0 && gy < L.rows && gx >= 0 && gx < L.pitch)
+                val[k] = __ldg(reinterpret_cast<const uint4*>(img + (size_t)gy * L.pitch + gx));
+        }
+        for (int v = threadIdx.x; v < SCH * SCW / 16; v += 256) reinterpret_cast<uint4*>(sc)[v] = make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const int v = threadIdx.x + 256 * k;
+            if (v < FSH * VPR) reinterpret_cast<uint4*>(tile)[v] = val[k];
+        }
     }
-    for (int v = threadIdx.x; v < SCH * SCW / 16; v += 256) reinterpret_cast<uint4*>(sc)[v] = make_uint4(0, 0, 0, 0);
     if (threadIdx.x < FTH * (FTW / 32)) mw[threadIdx.x] = 0;
     if (threadIdx.x == 0) { n1 = 0; n2 = 0; }
     __syncthreads();
@@ -575,50 +584,64 @@ __device__ __forceinline__ float byte_to_float(unsigned w, unsigned sel) {
     return __uint_as_float(__byte_perm(w, 0x4B000000u, sel)) - 8388608.0f;
 }
 
+__device__ __forceinline__ unsigned sat_u8_rn(float v) {  // cvRound (round half to even) + saturate_cast<uchar>
+    unsigned r;
+    asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return r;
+}
+
 __global__ void __launch_bounds__(256) blur7_kernel(SeqView s, OrbView o, int first, int l) {
-    __shared__ __align__(16) uint8_t tin[GIH * GIW];      // pixels x0-4 .. x0+GW+3, rows y0-3 .. y0+GH+2
+    __shared__ __align__(16) float tin[GIH * GIW];        // pixels x0-4 .. x0+GW+3, rows y0-3 .. y0+GH+2, as floats
     __shared__ __align__(16) float trow[GIH * GW];
     const int f = first + blockIdx.z;
     const OrbLevel& L = o.lv[l];
     const uint8_t* img = level_ptr(s, o, f, l);
     uint8_t* out = blur_ptr(s, o, f, l);
     const int x0 = blockIdx.x * GW, y0 = blockIdx.y * GH;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // getGaussianKernel(7, 2, CV_32F) (bit patterns of the cv2 result; OpenCV computes exp(-x^2/8) normalised)
     const float k0 = __uint_as_float(0x3d8fafb1u), k1 = __uint_as_float(0x3e06387eu), k2 = __uint_as_float(0x3e434a39u),
                 k3 = __uint_as_float(0x3e5d4ae0u);
     const bool interior = x0 >= 4 && x0 + GW + 3 <= L.cols;  // no horizontal reflection inside the staged span
+    // stage: bytes -> floats once; the three word loads of a thread are issued together (latency overlap)
     if (interior) {
-        for (int i = threadIdx.x; i < GIH * (GIW / 4); i += 256) {
+        constexpr int NW = GIH * (GIW / 4);  // 684 words
+        unsigned w[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const int i = threadIdx.x + 256 * k;
             const int r = i / (GIW / 4), c = i - r * (GIW / 4);
-            const int gy = reflect101(y0 - 3 + r, L.rows);
-            reinterpret_cast<uint32_t*>(tin)[i] =
-                __ldg(reinterpret_cast<const uint32_t*>(img + (size_t)gy * L.pitch + x0 - 4) + c);
+            w[k] = 0;
+            if (i < NW)
+                w[k] = __ldg(reinterpret_cast<const uint32_t*>(img + (size_t)reflect101(y0 - 3 + r, L.rows) * L.pitch + x0 - 4) + c);
+        }
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const int i = threadIdx.x + 256 * k;
+            if (i < NW) {
+                float4 v;
+                v.x = byte_to_float(w[k], 0x7440u);
+                v.y = byte_to_float(w[k], 0x7441u);
+                v.z = byte_to_float(w[k], 0x7442u);
+                v.w = byte_to_float(w[k], 0x7443u);
+                reinterpret_cast<float4*>(tin)[i] = v;
+            }
         }
     } else {
-        for (int i = threadIdx.x; i < GIH * GIW; i += 256) {
-            const int r = i / GIW, c = i - r * GIW;
-            const int gy = reflect101(y0 - 3 + r, L.rows), gx = reflect101(x0 - 4 + c, L.cols);
-            tin[i] = img[(size_t)gy * L.pitch + gx];
+        for (int r = warp; r < GIH; r += 8) {
+            const uint8_t* row = img + (size_t)reflect101(y0 - 3 + r, L.rows) * L.pitch;
+            for (int c = lane; c < GIW; c += 32) tin[r * GIW + c] = (float)row[reflect101(x0 - 4 + c, L.cols)];
         }
     }
     __syncthreads();
+    // row pass: 4 outputs per thread from 12 staged floats (pixels x-4 .. x+7 of the outputs at x .. x+3)
     for (int i = threadIdx.x; i < GIH * (GW / 4); i += 256) {
-        const int r = i / (GW / 4), c = i - r * (GW / 4);
-        const uint32_t* w = reinterpret_cast<const uint32_t*>(tin + r * GIW) + c;  // pixels x-4 .. x+7 of 4 outputs at x
-        const unsigned w0 = w[0], w1 = w[1], w2 = w[2];
-        float p[10];  // pixels x-3 .. x+6
-        p[0] = byte_to_float(w0, 0x7441u);
-        p[1] = byte_to_float(w0, 0x7442u);
-        p[2] = byte_to_float(w0, 0x7443u);
-        p[3] = byte_to_float(w1, 0x7440u);
-        p[4] = byte_to_float(w1, 0x7441u);
-        p[5] = byte_to_float(w1, 0x7442u);
-        p[6] = byte_to_float(w1, 0x7443u);
-        p[7] = byte_to_float(w2, 0x7440u);
-        p[8] = byte_to_float(w2, 0x7441u);
-        p[9] = byte_to_float(w2, 0x7442u);
+        const int r = i >> 4, c = i & 15;
+        const float4* w = reinterpret_cast<const float4*>(tin + r * GIW) + c;
+        const float4 a = w[0], b = w[1], d = w[2];
+        const float p[10] = {a.y, a.z, a.w, b.x, b.y, b.z, b.w, d.x, d.y, d.z};  // pixels x-3 .. x+6
         float4 acc;
-        float* a = &acc.x;
+        float* q = &acc.x;
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             float v = k0 * p[k];
@@ -628,7 +651,7 @@ __global__ void __launch_bounds__(256) blur7_kernel(SeqView s, OrbView o, int fi
             v = fmaf(k2, p[k + 4], v);
             v = fmaf(k1, p[k + 5], v);
             v = fmaf(k0, p[k + 6], v);
-            a[k] = v;
+            q[k] = v;
         }
         reinterpret_cast<float4*>(trow)[i] = acc;
     }
@@ -644,16 +667,16 @@ __global__ void __launch_bounds__(256) blur7_kernel(SeqView s, OrbView o, int fi
                      a3 = q[3 * (GW / 4)], b3 = q[-3 * (GW / 4)];
         const float* pc = &c0.x;
         const float *pa1 = &a1.x, *pb1 = &b1.x, *pa2 = &a2.x, *pb2 = &b2.x, *pa3 = &a3.x, *pb3 = &b3.x;
-        uint32_t packed = 0;
+        unsigned v[4];
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             float acc = k3 * pc[k];
             acc = fmaf(k2, pa1[k] + pb1[k], acc);
             acc = fmaf(k1, pa2[k] + pb2[k], acc);
             acc = fmaf(k0, pa3[k] + pb3[k], acc);
-            const int v = min(max(__float2int_rn(acc), 0), 255);
-            packed |= (uint32_t)v << (8 * k);
+            v[k] = sat_u8_rn(acc);
         }
+        const uint32_t packed = __byte_perm(__byte_perm(v[0], v[1], 0x0040), __byte_perm(v[2], v[3], 0x0040), 0x5410);
         if (x0 + tx * 4 < L.pitch) *reinterpret_cast<uint32_t*>(out + (size_t)gy * L.pitch + x0 + tx * 4) = packed;
     }
 }
