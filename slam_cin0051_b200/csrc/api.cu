@@ -77,6 +77,9 @@ struct slamcu_context {
     // copy engines of the pipelined sequence path: H2D and D2H run on their own streams
     cudaStream_t s_in = nullptr, s_out = nullptr;
     std::vector<cudaEvent_t> events;
+    // auxiliary compute stream: kernels that are independent inside one extract call overlap with the main chain
+    cudaStream_t s_aux = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 
 namespace {
@@ -245,6 +248,9 @@ void slamcu_destroy(slamcu_context* ctx) {
     if (ctx->s_in) { cudaStreamSynchronize(ctx->s_in); cudaStreamDestroy(ctx->s_in); }
     if (ctx->s_out) { cudaStreamSynchronize(ctx->s_out); cudaStreamDestroy(ctx->s_out); }
     for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
+    if (ctx->s_aux) { cudaStreamSynchronize(ctx->s_aux); cudaStreamDestroy(ctx->s_aux); }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -593,7 +599,12 @@ static int seq_extract_orb(slamcu_sequence* s, slamcu_detector* det, int first, 
     if (rc != SLAMCU_OK) return rc;
     ProfGuard pg(ctx);
     CU(ctx, cudaMemsetAsync(s->v.status + first, 0, (size_t)n * sizeof(int), ctx->stream));
-    ctx->launches += launch_orb_extract(s->v, s->orb, first, n, ctx->stream);
+    if (!ctx->s_aux) {
+        CU(ctx, cudaStreamCreateWithFlags(&ctx->s_aux, cudaStreamNonBlocking));
+        CU(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+        CU(ctx, cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+    }
+    ctx->launches += launch_orb_extract(s->v, s->orb, first, n, ctx->stream, ctx->s_aux, ctx->ev_fork, ctx->ev_join);
     {
         const SeqView& v = s->v;
         ctx->launches += launch_desc_or(v.desc + (size_t)first * v.cap_kp * v.desc_words, v.n_kp + first, v.desc_words,

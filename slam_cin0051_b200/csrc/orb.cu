@@ -794,7 +794,8 @@ void init_orb_attributes(int smem_optin) {
     (void)smem_optin;
 }
 
-int launch_orb_extract(const SeqView& s, const OrbView& o, int first, int n, cudaStream_t st) {
+int launch_orb_extract(const SeqView& s, const OrbView& o, int first, int n, cudaStream_t st, cudaStream_t aux, cudaEvent_t ev_fork,
+                       cudaEvent_t ev_join) {
     int launches = 0;
     int max_rows = 0, max_capc = 0;
     for (int l = 0; l < o.nlevels; l++) {
@@ -806,6 +807,21 @@ int launch_orb_extract(const SeqView& s, const OrbView& o, int first, int n, cud
         SLAM_KERNEL("pyr_down", st, pyr_down_kernel<<<grid, 256, 0, st>>>(s, o, first, l));
         launches++;
     }
+    // The blurred levels depend only on the pyramid: they run on the auxiliary stream next to the corner chain
+    // (FAST -> select -> Harris -> retain -> assemble) and join before the descriptor kernel.
+    // (not while per-kernel timing is on: overlapped kernels would each be charged the other's time)
+    const bool forked = aux != nullptr && aux != st && slamcu::g_prof == nullptr;
+    cudaStream_t bs = forked ? aux : st;
+    if (forked) {
+        cudaEventRecord(ev_fork, st);
+        cudaStreamWaitEvent(aux, ev_fork, 0);
+    }
+    for (int l = 0; l < o.nlevels; l++) {
+        dim3 grid((o.lv[l].cols + GW - 1) / GW, (o.lv[l].rows + GH - 1) / GH, n);
+        SLAM_KERNEL("blur7", bs, blur7_kernel<<<grid, 256, 0, bs>>>(s, o, first, l));
+        launches++;
+    }
+    if (forked) cudaEventRecord(ev_join, aux);
     for (int l = 0; l < o.nlevels; l++) {
         dim3 grid((o.lv[l].cols + FTW - 1) / FTW, (o.lv[l].rows + FTH - 1) / FTH, n);
         SLAM_KERNEL("fast9_mask", st, fast9_mask_kernel<<<grid, 256, 0, st>>>(s, o, first, l));
@@ -821,11 +837,7 @@ int launch_orb_extract(const SeqView& s, const OrbView& o, int first, int n, cud
                 orb_retain_kernel<<<dim3(o.nlevels, n), 256, retain_cap * sizeof(float), st>>>(s, o, first, retain_cap));
     SLAM_KERNEL("orb_assemble", st, orb_assemble_kernel<<<n, 256, 0, st>>>(s, o, first));
     launches += 4;
-    for (int l = 0; l < o.nlevels; l++) {
-        dim3 grid((o.lv[l].cols + GW - 1) / GW, (o.lv[l].rows + GH - 1) / GH, n);
-        SLAM_KERNEL("blur7", st, blur7_kernel<<<grid, 256, 0, st>>>(s, o, first, l));
-        launches++;
-    }
+    if (forked) cudaStreamWaitEvent(st, ev_join, 0);
     SLAM_KERNEL("orb_describe", st,
                 orb_describe_kernel<<<dim3((s.cap_kp + 127) / 128, n), 128, 0, st>>>(s, o, first, o.patf));
     launches++;

@@ -48,6 +48,8 @@ struct OrbView {
     const float2* patf;     // the same points as float2 (x, y)
 };
 
-int launch_orb_extract(const SeqView& s, const OrbView& o, int first, int n, cudaStream_t st);
+// aux / ev_fork / ev_join: optional second stream (and two events) on which the blur kernels run concurrently
+int launch_orb_extract(const SeqView& s, const OrbView& o, int first, int n, cudaStream_t st, cudaStream_t aux = nullptr,
+                       cudaEvent_t ev_fork = nullptr, cudaEvent_t ev_join = nullptr);
 
 }  // namespace slamcu
