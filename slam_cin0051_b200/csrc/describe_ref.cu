@@ -21,8 +21,27 @@ constexpr int BW = 64, BH = 16;           // output tile
 constexpr int BSW = BW + 8;               // smem stride (x0-4 .. x0+68), word aligned
 constexpr int BSH = BH + 4;
 
-struct BlurW { double w[25]; };
+struct BlurW {
+    double w[25];
+    uint32_t q[25];  // weights in 8.24 fixed point (round to nearest); all zero = filter disabled
+};
 
+// exact value of one blurred pixel: the reference's double accumulation, ky outer / kx inner, no FMA, std::round
+__device__ __forceinline__ uint32_t blur5_exact(const uint8_t* c, const BlurW& bw) {
+    double acc = 0.0;
+#pragma unroll
+    for (int ky = -2; ky <= 2; ky++)
+#pragma unroll
+        for (int kx = -2; kx <= 2; kx++)
+            acc = __dadd_rn(acc, __dmul_rn((double)c[ky * BSW + kx], bw.w[(ky + 2) * 5 + (kx + 2)]));
+    return (uint32_t)(int)round(acc) & 0xffu;  // std::round: half away from zero (:351)
+}
+
+// Exactness filter.  The result is round(S) with S the reference's double sum; all that matters is on which side of
+// k + 0.5 it lies.  An integer sum with the weights rounded to 2^-24 differs from the real-arithmetic sum by at most
+// 255 * 25 * 2^-25 (3187.5 units of 2^-24), and the reference's own rounding errors are below 1e-11, so whenever the
+// fixed-point fraction is farther than 4096 units from one half the rounded byte is already decided; the (0.05 % of)
+// pixels inside that band take the exact FP64 path.  25 IMADs instead of 25 I2F + 25 DMUL + 25 DADD for the rest.
 __global__ void __launch_bounds__(256) blur5_kernel(SeqView s, int first, BlurW bw) {
     __shared__ __align__(16) uint8_t tile[BSH * BSW];
     const int f = first + blockIdx.z;
@@ -30,35 +49,55 @@ __global__ void __launch_bounds__(256) blur5_kernel(SeqView s, int first, BlurW 
     const uint8_t* img = s.img + (size_t)f * s.frame_bytes;
     uint8_t* out = s.blur + (size_t)f * s.frame_bytes;
     constexpr int WPR = BSW / 4;
-    for (int v = threadIdx.x; v < BSH * WPR; v += blockDim.x) {
-        const int r = v / WPR, cw = v - r * WPR;
-        const int gy = y0 - 2 + r, gx = x0 - 4 + cw * 4;
-        uint32_t val = 0;
-        if (gy >= 0 && gy < s.rows && gx >= 0 && gx < s.pitch)
-            val = __ldg(reinterpret_cast<const uint32_t*>(img + (size_t)gy * s.pitch + gx));
-        *reinterpret_cast<uint32_t*>(tile + r * BSW + cw * 4) = val;
+    {
+        uint32_t val[2];
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const int v = threadIdx.x + 256 * k;
+            const int r = v / WPR, cw = v - r * WPR;
+            const int gy = y0 - 2 + r, gx = x0 - 4 + cw * 4;
+            val[k] = 0;
+            if (v < BSH * WPR && gy >= 0 && gy < s.rows && gx >= 0 && gx < s.pitch)
+                val[k] = __ldg(reinterpret_cast<const uint32_t*>(img + (size_t)gy * s.pitch + gx));
+        }
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const int v = threadIdx.x + 256 * k;
+            if (v < BSH * WPR) reinterpret_cast<uint32_t*>(tile)[v] = val[k];
+        }
     }
     __syncthreads();
     // each thread produces 4 horizontally adjacent pixels -> one 32-bit store
     const int tx = (threadIdx.x & 15) * 4, ty = threadIdx.x >> 4;
     const int gy = y0 + ty;
     if (gy >= s.rows) return;
+    const uint8_t* c0 = tile + (ty + 2) * BSW + 4 + tx;
+    uint32_t sum[4] = {0, 0, 0, 0};
+    const bool filter = bw.q[12] != 0;
+    if (filter) {
+#pragma unroll
+        for (int ky = -2; ky <= 2; ky++) {
+            uint32_t px[8];  // columns tx-2 .. tx+5 of this row
+#pragma unroll
+            for (int j = 0; j < 8; j++) px[j] = c0[ky * BSW + j - 2];
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+#pragma unroll
+                for (int kx = 0; kx < 5; kx++) sum[k] += px[k + kx] * bw.q[(ky + 2) * 5 + kx];
+        }
+    }
     uint32_t packed = 0;
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         const int gx = x0 + tx + k;
-        const uint8_t* c = tile + (ty + 2) * BSW + 4 + tx + k;
         uint32_t v;
         if (gx >= 2 && gx < s.cols - 2 && gy >= 2 && gy < s.rows - 2) {
-            double acc = 0.0;
-#pragma unroll
-            for (int ky = -2; ky <= 2; ky++)
-#pragma unroll
-                for (int kx = -2; kx <= 2; kx++)
-                    acc = __dadd_rn(acc, __dmul_rn((double)c[ky * BSW + kx], bw.w[(ky + 2) * 5 + (kx + 2)]));
-            v = (uint32_t)(int)round(acc) & 0xffu;  // std::round: half away from zero (:351)
+            const uint32_t frac = sum[k] & 0xffffffu;
+            const uint32_t off = frac > 0x800000u ? frac - 0x800000u : 0x800000u - frac;  // distance from one half
+            if (filter && off > 4096u) v = (sum[k] + 0x800000u) >> 24;
+            else v = blur5_exact(c0 + k, bw);
         } else {
-            v = c[0];  // border frame copied from the input (:356-361)
+            v = c0[k];  // border frame copied from the input (:356-361)
         }
         packed |= v << (8 * k);
     }
@@ -178,7 +217,17 @@ __global__ void __launch_bounds__(256) desc_or_kernel(const uint32_t* __restrict
 
 int launch_blur(const SeqView& s, int first, int n, const DetParams& p, cudaStream_t st) {
     BlurW bw;
-    for (int i = 0; i < 25; i++) bw.w[i] = p.blur_w[i];
+    // fixed-point copy for the exactness filter: only for non-negative weights whose integer sum cannot overflow
+    bool ok = true;
+    unsigned long long total = 0;
+    for (int i = 0; i < 25; i++) {
+        bw.w[i] = p.blur_w[i];
+        if (!(p.blur_w[i] >= 0.0 && p.blur_w[i] < 1.0)) ok = false;
+        bw.q[i] = ok ? (uint32_t)llround(p.blur_w[i] * 16777216.0) : 0u;
+        total += bw.q[i];
+    }
+    if (!ok || total * 255ull >= (1ull << 32) || bw.q[12] == 0)
+        for (int i = 0; i < 25; i++) bw.q[i] = 0u;
     dim3 grid((s.cols + BW - 1) / BW, (s.rows + BH - 1) / BH, n);
     SLAM_KERNEL("blur5", st, blur5_kernel<<<grid, 256, 0, st>>>(s, first, bw));
     return 1;

@@ -58,40 +58,92 @@ __device__ __forceinline__ bool segment_test(const uint8_t* t /* -> centre pixel
     return (rh | rl) != 0;
 }
 
+// bytes of |a - b| that exceed thr -> bit 7 of the byte (SWAR; thr in [0, 255]); k7 = (thr < 128 ? 127 - thr : 255 - thr) * 0x01010101
+__device__ __forceinline__ unsigned swar_absdiff_gt(unsigned a, unsigned b, unsigned k7, bool big) {
+    const unsigned d = __vabsdiffu4(a, b);
+    const unsigned s = (d & 0x7f7f7f7fu) + k7;  // no carry between bytes: both addends are <= 127
+    return big ? (s & d) : (s | d);
+}
+
+// Compacting phases, so that the (divergent) literal test runs on full warps:
+//   1  SWAR filter on packed bytes, 4 pixels per thread: the reference's cardinal pre-test (feature_detector.cpp:81-113)
+//      needs three of the four compass pixels beyond the threshold on one side, hence three of four with |diff| > thr;
+//      this is implied by the literal pre-test for every ContiguousPixelsThreshold, so nothing is lost
+//   2  the literal isFASTCorner on the survivors -> bits OR-ed into the tile's mask words in shared memory
 __global__ void __launch_bounds__(256) fast_mask_kernel(SeqView s, int first, int thr, int arc) {
     __shared__ __align__(16) uint8_t tile[SH * SW];
+    __shared__ uint16_t list[TH * TW];
+    __shared__ unsigned mw[TH * (TW / 32)];
+    __shared__ int n_list;
     const int f = first + blockIdx.z;
     const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
     const uint8_t* img = s.img + (size_t)f * s.frame_bytes;
 
-    // stage the tile (+3 rows, +16 cols of halo) with aligned 128-bit loads
+    // stage the tile (+3 rows, +16 cols of halo) with aligned 128-bit loads, all of a thread's loads in flight at once
     constexpr int VPR = SW / 16;  // vectors per smem row
-    for (int v = threadIdx.x; v < SH * VPR; v += blockDim.x) {
-        const int r = v / VPR, cv = v - r * VPR;
-        const int gy = y0 - 3 + r, gx = x0 - HALO_X + cv * 16;
-        uint4 val = make_uint4(0, 0, 0, 0);
-        if (gy >= 0 && gy < s.rows && gx >= 0 && gx < s.pitch)
-            val = __ldg(reinterpret_cast<const uint4*>(img + (size_t)gy * s.pitch + gx));
-        *reinterpret_cast<uint4*>(tile + r * SW + cv * 16) = val;
+    {
+        uint4 val[2];
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const int v = threadIdx.x + 256 * k;
+            const int r = v / VPR, cv = v - r * VPR;
+            const int gy = y0 - 3 + r, gx = x0 - HALO_X + cv * 16;
+            val[k] = make_uint4(0, 0, 0, 0);
+            if (v < SH * VPR && gy >= 0 && gy < s.rows && gx >= 0 && gx < s.pitch)
+                val[k] = __ldg(reinterpret_cast<const uint4*>(img + (size_t)gy * s.pitch + gx));
+        }
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const int v = threadIdx.x + 256 * k;
+            if (v < SH * VPR) reinterpret_cast<uint4*>(tile)[v] = val[k];
+        }
     }
+    if (threadIdx.x < TH * (TW / 32)) mw[threadIdx.x] = 0;
+    if (threadIdx.x == 0) n_list = 0;
     __syncthreads();
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint32_t* mask = s.mask + (size_t)f * s.rows * s.mwords;
-    for (int r = warp; r < TH; r += 8) {
-        const int gy = y0 + r;
-        if (gy >= s.rows) break;
-        const bool row_ok = gy >= 3 && gy < s.rows - 3;
+    {
+        const bool big = thr >= 128;
+        const unsigned k7 = (unsigned)(big ? 255 - thr : 127 - thr) * 0x01010101u;
+        const int lo = 3, hi = s.cols - 3;  // isFASTCorner is evaluated for x in [3, cols - 3) (feature_detector.cpp:59-66)
+        for (int r = warp; r < TH; r += 8) {
+            const int gy = y0 + r;
+            if (gy < 3 || gy >= s.rows - 3) continue;
+            const uint32_t* row = reinterpret_cast<const uint32_t*>(tile + (r + 3) * SW) + HALO_X / 4 + lane;
+            const unsigned w0 = row[0], wm = row[-1], wp = row[1];
+            const unsigned wn = row[-3 * (SW / 4)], ws = row[3 * (SW / 4)];
+            const unsigned we = __funnelshift_r(w0, wp, 24);  // pixels x+3 .. x+6
+            const unsigned ww = __funnelshift_r(wm, w0, 8);   // pixels x-3 .. x
+            const unsigned an = swar_absdiff_gt(wn, w0, k7, big), as = swar_absdiff_gt(ws, w0, k7, big);
+            const unsigned ae = swar_absdiff_gt(we, w0, k7, big), aw = swar_absdiff_gt(ww, w0, k7, big);
+            unsigned m = ((an & as & (ae | aw)) | (ae & aw & (an | as))) & 0x80808080u;
+            const int gxb = x0 + 4 * lane;
+            if (m != 0 && (gxb < lo || gxb + 4 > hi)) {
 #pragma unroll
-        for (int wx = 0; wx < TW / 32; wx++) {
-            const int gx = x0 + wx * 32 + lane;
-            bool corner = false;
-            if (row_ok && gx >= 3 && gx < s.cols - 3)
-                corner = segment_test(tile + (r + 3) * SW + HALO_X + wx * 32 + lane, thr, arc);
-            const unsigned word = __ballot_sync(0xffffffffu, corner);
-            const int wi = (x0 >> 5) + wx;
-            if (lane == 0 && wi < s.mwords) mask[(size_t)gy * s.mwords + wi] = word;
+                for (int k = 0; k < 4; k++)
+                    if ((unsigned)(gxb + k - lo) >= (unsigned)(hi - lo)) m &= ~(0x80u << (8 * k));
+            }
+            if (m != 0) {
+                int pos = atomicAdd(&n_list, __popc(m));
+                const int base = r * TW + 4 * lane;
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if (m & (0x80u << (8 * k))) list[pos++] = (uint16_t)(base + k);
+            }
         }
+    }
+    __syncthreads();
+    const int cnt = n_list;
+    for (int e = threadIdx.x; e < cnt; e += 256) {
+        const int idx = list[e];
+        const int r = idx / TW, lx = idx - r * TW;
+        if (segment_test(tile + (r + 3) * SW + HALO_X + lx, thr, arc)) atomicOr(&mw[r * (TW / 32) + (lx >> 5)], 1u << (lx & 31));
+    }
+    __syncthreads();
+    if (threadIdx.x < TH * (TW / 32)) {
+        const int gy = y0 + (threadIdx.x >> 2), wi = (x0 >> 5) + (threadIdx.x & 3);
+        if (gy < s.rows && wi < s.mwords) (s.mask + (size_t)f * s.rows * s.mwords)[(size_t)gy * s.mwords + wi] = mw[threadIdx.x];
     }
 }
 

@@ -47,7 +47,13 @@ def test_detect_matches_std_sort_and_greedy_nms(detector, oracle, kitti_pair, tu
 
 
 def test_gaussian_blur_bytes(detector, oracle, kitti_pair, tum_pair):
-    for name, img in _images(kitti_pair, tum_pair).items():
+    imgs = dict(_images(kitti_pair, tum_pair))
+    rng = np.random.default_rng(11)
+    # white noise and near-flat images: many sums close to k + 0.5, i.e. the exact-path band of the rounding filter
+    imgs["noise"] = rng.integers(0, 256, (512, 768), dtype=np.uint8)
+    imgs["two_level"] = (rng.integers(0, 2, (300, 500)) * 255).astype(np.uint8)
+    imgs["small_range"] = rng.integers(100, 104, (257, 333), dtype=np.uint8)
+    for name, img in imgs.items():
         assert np.array_equal(detector.gaussian_blur(img), oracle.gaussian_blur(img)), name
 
 
