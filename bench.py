@@ -38,7 +38,7 @@ ROWS, COLS = 376, 1241
 GRID_PITCH = 14  # synthetic scene density; the achieved keypoint count is reported
 METRIC = "frames/s ORB extract+match @1241x376, 2k kp"
 UNIT = "frames/s"
-WORKLOAD = "KITTI-shape synthetic grayscale sequence 1241x376 (BASELINE.json configs[1])"
+WORKLOAD = "KITTI-shape synthetic grayscale sequence 1241x376 (BASELINE.json configs[1]: 1000 frames, 2000 ORB keypoints/frame, 8-level pyramid)"
 
 
 def make_frames(n, seed):
@@ -146,7 +146,7 @@ class ClockSampler:
         self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.proc = None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(gpu_index)], stdout=self.tmp, stderr=subprocess.DEVNULL)
         except OSError:
             self.proc = None
@@ -311,7 +311,6 @@ def run_ours(args, rank, world, local_rank):
     prof = ctx.profile_read()
     ctx.profile_enable(False)
     launches = ctx.launch_count - launches0
-    clocks = sampler.stop() if sampler else None
 
     # ---- end-to-end leg (host buffers, copies inside the timed region) ----
     for i in range(2):
@@ -330,6 +329,7 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     barrier()
+    clocks = sampler.stop() if sampler else None  # sampled across both timed regions
 
     t_res = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -438,9 +438,9 @@ def main():
     ap.add_argument("--mode", default="orb", choices=["orb", "reference"],
                     help="orb: the OpenCV-ORB-compatible path BASELINE.json's headline config names; "
                          "reference: the reference repo's own hand-written detector/matcher")
-    ap.add_argument("--frames", type=int, default=512, help="frames per GPU per step")
+    ap.add_argument("--frames", type=int, default=1000, help="frames per GPU per step (BASELINE.json configs[1]: a 1000-frame sequence)")
     ap.add_argument("--max-keypoints", type=int, default=2560)
-    ap.add_argument("--chunk", type=int, default=256, help="frames per pipeline stage of the end-to-end leg")
+    ap.add_argument("--chunk", type=int, default=250, help="frames per pipeline stage of the end-to-end leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
