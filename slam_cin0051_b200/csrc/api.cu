@@ -9,6 +9,8 @@
 #include <string>
 #include <vector>
 
+#include <cudaTypedefs.h>  // PFN_cuTensorMapEncodeTiled
+
 #include "common.cuh"
 #include "orb.cuh"
 
@@ -161,6 +163,7 @@ struct slamcu_sequence {
     int orb_levels = 0, orb_features = 0, orb_fast = 0;
     float orb_scale = 0.f;
     std::vector<void*> orb_owned;
+    OrbTmaps tmaps{};  // TMA descriptors of the pyramid levels (host copies; passed to the kernels as __grid_constant__)
 };
 
 struct slamcu_detector {
@@ -585,6 +588,31 @@ static int seq_ensure_orb(slamcu_sequence* s, slamcu_detector* det) {
         o.lv[l].yt = dy;
     }
     if (rc != SLAMCU_OK) return rc;
+    // TMA descriptors: rank-3 uint8 tensors (x = level width, y = level height, z = frame), zero fill outside.
+    // cuTensorMapEncodeTiled is a driver entry point; fetch it through the runtime so libcuda is not a link dependency.
+    s->tmaps.valid = false;
+    {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && fn &&
+            qres == cudaDriverEntryPointSuccess) {
+            auto encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(fn);
+            bool ok = true;
+            for (int l = 0; l < L && ok; l++) {
+                const OrbLevel& lv = o.lv[l];
+                void* base = l == 0 ? (void*)v.img : (void*)(o.pyr + lv.off);
+                const cuuint64_t dims[3] = {(cuuint64_t)lv.cols, (cuuint64_t)lv.rows, (cuuint64_t)s->max_frames};
+                const cuuint64_t strides[2] = {(cuuint64_t)lv.pitch, (cuuint64_t)(l == 0 ? v.frame_bytes : o.pyr_bytes)};
+                const cuuint32_t box[3] = {(cuuint32_t)kFastBoxW, (cuuint32_t)kFastBoxH, 1};
+                const cuuint32_t estr[3] = {1, 1, 1};
+                ok = encode(&s->tmaps.fast[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, base, dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+            }
+            s->tmaps.valid = ok;
+        }
+        cudaGetLastError();  // a failed query must not poison later launch checks
+    }
     s->has_orb = true;
     s->orb_levels = L;
     s->orb_features = det->max_features;
@@ -604,7 +632,7 @@ static int seq_extract_orb(slamcu_sequence* s, slamcu_detector* det, int first, 
         CU(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
         CU(ctx, cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
     }
-    ctx->launches += launch_orb_extract(s->v, s->orb, first, n, ctx->stream, ctx->s_aux, ctx->ev_fork, ctx->ev_join);
+    ctx->launches += launch_orb_extract(s->v, s->orb, first, n, ctx->stream, ctx->s_aux, ctx->ev_fork, ctx->ev_join, &s->tmaps);
     {
         const SeqView& v = s->v;
         ctx->launches += launch_desc_or(v.desc + (size_t)first * v.cap_kp * v.desc_words, v.n_kp + first, v.desc_words,

@@ -181,8 +181,38 @@ __device__ __forceinline__ unsigned swar_absdiff_gt(unsigned a, unsigned b, unsi
     return big ? (s & d) : (s | d);             // thr >= 128: needs bit 7 of d as well; else bit 7 of d suffices
 }
 
-__global__ void __launch_bounds__(256) fast9_mask_kernel(SeqView s, OrbView o, int first, int l) {
-    __shared__ __align__(16) uint8_t tile[FSH * FSW];
+// ---- TMA helpers (sm_90+ PTX): one thread arms an mbarrier with the box size and issues cp.async.bulk.tensor; the
+// hardware zero-fills the part of the box that lies outside the tensor, so the staging loop and its bounds tests go away
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int x, int y, int z, uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(smem_u32(dst)),
+        "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(phase)
+        : "memory");
+}
+
+template <bool kTma>
+__global__ void __launch_bounds__(256) fast9_mask_kernel(SeqView s, OrbView o, int first, int l, const __grid_constant__ CUtensorMap tmap) {
+    __shared__ __align__(128) uint8_t tile[FSH * FSW];
+    __shared__ __align__(8) uint64_t tma_bar;
     __shared__ __align__(16) uint8_t sc[SCH * SCW];
     __shared__ uint16_t list1[SCH * SCW];
     __shared__ uint16_t list2[SCH * SCW];
@@ -194,8 +224,13 @@ __global__ void __launch_bounds__(256) fast9_mask_kernel(SeqView s, OrbView o, i
     const int thr = o.fast_threshold;
     const uint8_t* img = level_ptr(s, o, f, l);
     // ---- phase 0
-    constexpr int VPR = FSW / 16;
-    {
+    if (kTma) {
+        if (threadIdx.x == 0) mbar_init(&tma_bar, 1);
+        __syncthreads();
+        if (threadIdx.x == 0) tma_load_3d(tile, &tmap, x0 - FHX, y0 - 4, f, &tma_bar, FSH * FSW);
+        for (int v = threadIdx.x; v < SCH * SCW / 16; v += 256) reinterpret_cast<uint4*>(sc)[v] = make_uint4(0, 0, 0, 0);
+    } else {
+        constexpr int VPR = FSW / 16;
         uint4 val[2];  // both 128-bit loads of a thread are in flight before the first store
 #pragma unroll
         for (int k = 0; k < 2; k++) {
@@ -215,6 +250,7 @@ __global__ void __launch_bounds__(256) fast9_mask_kernel(SeqView s, OrbView o, i
     }
     if (threadIdx.x < FTH * (FTW / 32)) mw[threadIdx.x] = 0;
     if (threadIdx.x == 0) { n1 = 0; n2 = 0; }
+    if (kTma) mbar_wait(&tma_bar, 0);
     __syncthreads();
     // ---- phase 1: a warp per score-grid row, a lane per 4-pixel group of the tile's 128 columns; the two ring
     // columns (x0-1, x0+128) skip the pre-test and go straight to list 1
@@ -795,7 +831,7 @@ void init_orb_attributes(int smem_optin) {
 }
 
 int launch_orb_extract(const SeqView& s, const OrbView& o, int first, int n, cudaStream_t st, cudaStream_t aux, cudaEvent_t ev_fork,
-                       cudaEvent_t ev_join) {
+                       cudaEvent_t ev_join, const OrbTmaps* tmaps) {
     int launches = 0;
     int max_rows = 0, max_capc = 0;
     for (int l = 0; l < o.nlevels; l++) {
@@ -824,7 +860,10 @@ int launch_orb_extract(const SeqView& s, const OrbView& o, int first, int n, cud
     if (forked) cudaEventRecord(ev_join, aux);
     for (int l = 0; l < o.nlevels; l++) {
         dim3 grid((o.lv[l].cols + FTW - 1) / FTW, (o.lv[l].rows + FTH - 1) / FTH, n);
-        SLAM_KERNEL("fast9_mask", st, fast9_mask_kernel<<<grid, 256, 0, st>>>(s, o, first, l));
+        if (tmaps && tmaps->valid)
+            SLAM_KERNEL("fast9_mask", st, fast9_mask_kernel<true><<<grid, 256, 0, st>>>(s, o, first, l, tmaps->fast[l]));
+        else
+            SLAM_KERNEL("fast9_mask", st, fast9_mask_kernel<false><<<grid, 256, 0, st>>>(s, o, first, l, CUtensorMap{}));
         launches++;
     }
     SLAM_KERNEL("orb_select", st,

@@ -1,5 +1,7 @@
 // orb.cuh -- device view of the ORB-compatible ("mode B") extractor's working set.
 #pragma once
+#include <cuda.h>  // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
+
 #include "common.cuh"
 
 namespace slamcu {
@@ -48,8 +50,16 @@ struct OrbView {
     const float2* patf;     // the same points as float2 (x, y)
 };
 
+// TMA descriptors of the pyramid levels of one sequence: rank-3 uint8 tensors (x, y, frame) with hardware zero fill
+// outside the level, box = the FAST tile with its halo.  valid == false -> the kernels stage tiles with LDG instead.
+struct OrbTmaps {
+    CUtensorMap fast[kMaxLevels];
+    bool valid = false;
+};
+constexpr int kFastBoxW = 160, kFastBoxH = 40;  // FSW x FSH of fast9_mask_kernel
+
 // aux / ev_fork / ev_join: optional second stream (and two events) on which the blur kernels run concurrently
 int launch_orb_extract(const SeqView& s, const OrbView& o, int first, int n, cudaStream_t st, cudaStream_t aux = nullptr,
-                       cudaEvent_t ev_fork = nullptr, cudaEvent_t ev_join = nullptr);
+                       cudaEvent_t ev_fork = nullptr, cudaEvent_t ev_join = nullptr, const OrbTmaps* tmaps = nullptr);
 
 }  // namespace slamcu
