@@ -98,3 +98,12 @@ def test_synthetic_sequence_is_deterministic_and_translating():
     assert a.dtype == np.uint8 and a.shape == (4, 120, 200) and np.array_equal(a, b)
     # frame f is the canvas shifted by (2f, f): true correspondences between consecutive frames
     assert np.array_equal(a[0][1:, 2:], a[1][:-1, :-2])
+
+
+def test_cmake_and_python_builds_list_the_same_sources():
+    from slam_cin0051_b200 import build
+    text = open(os.path.join(ROOT, "CMakeLists.txt")).read()
+    listed = set(re.findall(r"/(\w+\.cu)\b", text))
+    assert listed == set(build.SOURCES)
+    assert set(f for f in os.listdir(build.CSRC) if f.endswith(".cu")) == set(build.SOURCES)
+    assert "100a" in text and "-fmad=false" in text
