@@ -441,7 +441,7 @@ def main():
                          "reference: the reference repo's own hand-written detector/matcher")
     ap.add_argument("--frames", type=int, default=1000, help="frames per GPU per step (BASELINE.json configs[1]: a 1000-frame sequence)")
     ap.add_argument("--max-keypoints", type=int, default=2560)
-    ap.add_argument("--chunk", type=int, default=250, help="frames per pipeline stage of the end-to-end leg")
+    ap.add_argument("--chunk", type=int, default=500, help="frames per pipeline stage of the end-to-end leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
