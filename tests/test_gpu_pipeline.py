@@ -50,3 +50,32 @@ def test_process_equals_stepwise(gpu_ctx, mode):
                 assert np.array_equal(h_desc.numpy()[f, :k], wd), (chunk, f)
                 if wm is not None:
                     assert h_m.numpy()[f, :len(wm)].tobytes() == wm.tobytes(), (chunk, f)
+
+
+@pytest.mark.parametrize("mode", ["reference", "orb"])
+def test_sequence_with_empty_frames(gpu_ctx, mode):
+    """Frames without a single corner inside a sequence: zero keypoints, zero matches for the pairs they take part in,
+    no RANSAC result, and the neighbours are unaffected (the reference would throw "Empty descriptors provided." for such
+    a pair; the batched path reports n_matches = 0)."""
+    import slam_cin0051_b200 as s
+    from slam_cin0051_b200.synth import make_sequence
+    sfx = "_orb" if mode == "orb" else ""
+    det = s.FeatureDetector(os.path.join(DATA, f"feature_detector{sfx}.yml"), gpu_ctx)
+    mat = s.FeatureMatcher(os.path.join(DATA, f"feature_matcher{sfx}.yml"), gpu_ctx)
+    frames = make_sequence(240, 333, 5, pitch_px=14, seed=4)
+    frames[2] = 90  # flat
+    seq = s.FrameSequence(240, 333, 5, desc_bytes=32, max_keypoints=2048, context=gpu_ctx)
+    seq.upload(frames)
+    seq.extract(det)
+    seq.match_consecutive(mat, with_keypoints=(mode == "reference"))
+    seq.essential((300.0, 300.0, 166.0, 120.0))
+    c = seq.counts()
+    assert c[2, 0] == 0 and c[1, 1] == 0 and c[2, 1] == 0 and (c[:, 3] == 0).all()
+    assert c[0, 0] > 50 and c[0, 1] > 0 and c[3, 1] > 0
+    E, mask, good, iters = seq.essential_result(1)
+    assert E is None and good == 0 and len(mask) == 0
+    k0, d0 = seq.frame(0)
+    k0s, d0s = det.detect_and_compute(frames[0])
+    assert k0.tobytes() == k0s.tobytes() and np.array_equal(d0, d0s)
+    k2, d2 = seq.frame(2)
+    assert len(k2) == 0
