@@ -185,6 +185,15 @@ int slamcu_sequence_create(slamcu_context* ctx, int rows, int cols, int max_fram
 void slamcu_sequence_destroy(slamcu_sequence* seq);
 /* H2D copy of n frames from host memory (pinned for async) into slots [first, first+n). */
 int slamcu_sequence_upload(slamcu_sequence* seq, int first, int n, const uint8_t* host_frames, int stride);
+/* Preprocessor::yield for a batch (preprocessor.cpp:136-137), straight into slots [first, first+n): n host frames of
+ * rows x stride bytes with 1 (gray) or 3 (BGR, as cv::imread(IMREAD_COLOR) gives) channels are uploaded with one linear
+ * copy, converted with cv::cvtColor(BGR2GRAY)'s fixed-point formula and, when K4/D4 (fx,fy,cx,cy / k1,k2,p1,p2) are given,
+ * undistorted with Camera::undistortImage's forward map + nearest-neighbour gather (outside -> 0).  The result is the
+ * 8-bit image the detector consumes (the reference's value / 255.0 double image has no consumer).  Asynchronous. */
+int slamcu_sequence_prepare(slamcu_sequence* seq, int first, int n, const uint8_t* host_frames, int channels, int stride,
+                            const double* K4, const double* D4);
+/* The 8-bit frame in slot f as the detector sees it (after upload / prepare); synchronises. */
+int slamcu_sequence_image(slamcu_sequence* seq, int f, uint8_t* out, int out_stride);
 /* Device pointer / pitch of the frame store, for producers that already live on the device. */
 int slamcu_sequence_frames_device(slamcu_sequence* seq, void** dptr, int* pitch, int64_t* frame_bytes);
 /* detectAndCompute on frames [first, first+n). */

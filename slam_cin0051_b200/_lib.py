@@ -72,6 +72,8 @@ SYMBOLS = {
     "slamcu_sequence_create": (_i, [_vp, _i, _i, _i, _i, _i, _i, C.POINTER(_vp)]),
     "slamcu_sequence_destroy": (None, [_vp]),
     "slamcu_sequence_upload": (_i, [_vp, _i, _i, _u8p, _i]),
+    "slamcu_sequence_prepare": (_i, [_vp, _i, _i, _u8p, _i, _i, _f64p, _f64p]),
+    "slamcu_sequence_image": (_i, [_vp, _i, _u8p, _i]),
     "slamcu_sequence_frames_device": (_i, [_vp, C.POINTER(_vp), _ip, C.POINTER(C.c_int64)]),
     "slamcu_sequence_extract": (_i, [_vp, _vp, _i, _i]),
     "slamcu_sequence_match": (_i, [_vp, _vp, _i, _i, _i]),

@@ -151,6 +151,11 @@ struct slamcu_sequence {
     unsigned long long* sort_keys = nullptr;  // [F][cap_kp]
     int* h_counts = nullptr;                  // pinned [F][4]
     uint8_t* stage = nullptr;                 // [F][rows][cols] dense landing zone of linear H2D copies (lazy)
+    uint8_t* prep_stage = nullptr;            // landing zone of slamcu_sequence_prepare (gray or BGR host frames; lazy)
+    size_t prep_stage_bytes = 0;
+    int* undist_map = nullptr;                // per-camera gather map of Camera::undistortImage (lazy, keyed by K, D)
+    double undist_key[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    bool has_undist = false;
     cudaEvent_t ev_compute_done = nullptr;    // last kernel of the latest slamcu_sequence_process call
     cudaEvent_t ev_out_done = nullptr;        // last download of the latest slamcu_sequence_process call
     EssentialJob ess{};                       // per-pair two-view RANSAC working set (lazy)
@@ -411,6 +416,8 @@ void slamcu_sequence_destroy(slamcu_sequence* s) {
     for (void* p : s->owned) cudaFree(p);
     for (void* p : s->orb_owned) cudaFree(p);
     if (s->stage) cudaFree(s->stage);
+    if (s->prep_stage) cudaFree(s->prep_stage);
+    if (s->undist_map) cudaFree(s->undist_map);
     for (void* p : s->ess_owned) cudaFree(p);
     if (s->h_counts) cudaFreeHost(s->h_counts);
     delete s;
@@ -462,6 +469,53 @@ int slamcu_sequence_upload(slamcu_sequence* s, int first, int n, const uint8_t* 
         seq_repitch(s, first, n, ctx->stream);
         return check_launch(ctx, "repitch");
     }
+    return SLAMCU_OK;
+}
+
+int slamcu_sequence_prepare(slamcu_sequence* s, int first, int n, const uint8_t* host, int channels, int stride, const double* K4,
+                            const double* D4) {
+    if (!s || !host) return SLAMCU_INVALID_ARGUMENT;
+    slamcu_context* ctx = s->ctx;
+    const SeqView& v = s->v;
+    if (first < 0 || n < 0 || first + n > s->max_frames || (channels != 1 && channels != 3) || stride < v.cols * channels)
+        return fail(ctx, SLAMCU_INVALID_ARGUMENT, "prepare: bad range / channels / stride");
+    if ((K4 == nullptr) != (D4 == nullptr)) return fail(ctx, SLAMCU_INVALID_ARGUMENT, "prepare: K4 and D4 go together");
+    if (n == 0) return SLAMCU_OK;
+    CU(ctx, cudaSetDevice(ctx->device));
+    const size_t fb = (size_t)v.rows * stride, need = (size_t)n * fb;
+    if (s->prep_stage_bytes < need) {
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        if (s->prep_stage) cudaFree(s->prep_stage);
+        s->prep_stage = nullptr;
+        s->prep_stage_bytes = 0;
+        CU(ctx, cudaMalloc(reinterpret_cast<void**>(&s->prep_stage), need));
+        s->prep_stage_bytes = need;
+    }
+    ProfGuard pg(ctx);
+    if (K4) {
+        const double key[8] = {K4[0], K4[1], K4[2], K4[3], D4[0], D4[1], D4[2], D4[3]};
+        if (!s->has_undist || memcmp(key, s->undist_key, sizeof key) != 0) {
+            if (!s->undist_map) CU(ctx, cudaMalloc(reinterpret_cast<void**>(&s->undist_map), (size_t)v.rows * v.cols * sizeof(int)));
+            CamParams cam{K4[0], K4[1], K4[2], K4[3], D4[0], D4[1], D4[2], D4[3]};
+            ctx->launches += launch_undistort_map(v.rows, v.cols, cam, s->undist_map, ctx->stream);
+            memcpy(s->undist_key, key, sizeof key);
+            s->has_undist = true;
+        }
+    }
+    CU(ctx, cudaMemcpyAsync(s->prep_stage, host, need, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->launches += launch_prepare(s->prep_stage, channels, stride, fb, K4 ? s->undist_map : nullptr, v.img + (size_t)first * v.frame_bytes,
+                                    v.pitch, v.frame_bytes, v.rows, v.cols, n, ctx->stream);
+    return check_launch(ctx, "prepare kernels");
+}
+
+int slamcu_sequence_image(slamcu_sequence* s, int f, uint8_t* out, int out_stride) {
+    if (!s || !out) return SLAMCU_INVALID_ARGUMENT;
+    slamcu_context* ctx = s->ctx;
+    if (f < 0 || f >= s->max_frames || out_stride < s->v.cols) return fail(ctx, SLAMCU_INVALID_ARGUMENT, "bad frame index / stride");
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaMemcpy2DAsync(out, out_stride, s->v.img + (size_t)f * s->v.frame_bytes, s->v.pitch, s->v.cols, s->v.rows,
+                              cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
     return SLAMCU_OK;
 }
 

@@ -79,6 +79,8 @@ struct MatchJob {
 int launch_match(const MatchJob& job, int n_pairs, const MatchParams& p, bool emit_matches, int with_kp,
                  unsigned long long* sort_keys, cudaStream_t st, int n_seg = 1, int seg_len = 0, size_t seg_stride = 0);
 
+int launch_prepare(const uint8_t* src, int channels, int src_stride, size_t src_frame_bytes, const int* map, uint8_t* dst, int pitch,
+                   size_t dst_frame_bytes, int rows, int cols, int n, cudaStream_t st);
 int launch_repitch(const uint8_t* src, int stride, uint8_t* dst, int pitch, int cols, long long rows_total, cudaStream_t st);
 int launch_bgr2gray(const uint8_t* bgr, int rows, int cols, int stride, uint8_t* gray, int gstride, cudaStream_t st);
 struct CamParams { double fx, fy, cx, cy, k1, k2, p1, p2; };

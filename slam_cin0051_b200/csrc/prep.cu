@@ -65,7 +65,40 @@ __global__ void __launch_bounds__(256) repitch_kernel(const uint8_t* __restrict_
     }
 }
 
+// Batched Preprocessor::yield arithmetic (preprocessor.cpp:136-137) straight into the frame store: optional BGR2GRAY at
+// the gathered source pixel, optional undistortion gather through the per-camera map (-1 = outside -> 0).
+__global__ void __launch_bounds__(256) prepare_kernel(const uint8_t* __restrict__ src, int channels, int src_stride,
+                                                      size_t src_frame_bytes, const int* __restrict__ map, uint8_t* __restrict__ dst,
+                                                      int pitch, size_t dst_frame_bytes, int rows, int cols) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, f = blockIdx.z;
+    if (x >= pitch) return;
+    uint8_t v = 0;
+    if (x < cols) {
+        int sy = y, sx = x;
+        bool inside = true;
+        if (map) {
+            const int m = map[(size_t)y * cols + x];
+            inside = m >= 0;
+            sy = m / cols;
+            sx = m - sy * cols;
+        }
+        if (inside) {
+            const uint8_t* p = src + (size_t)f * src_frame_bytes + (size_t)sy * src_stride + (size_t)sx * channels;
+            v = channels == 3 ? (uint8_t)((3735u * p[0] + 19235u * p[1] + 9798u * p[2] + 16384u) >> 15) : p[0];
+        }
+    }
+    dst[(size_t)f * dst_frame_bytes + (size_t)y * pitch + x] = v;  // the pitch padding is written as zeros
+}
+
 }  // namespace
+
+int launch_prepare(const uint8_t* src, int channels, int src_stride, size_t src_frame_bytes, const int* map, uint8_t* dst, int pitch,
+                   size_t dst_frame_bytes, int rows, int cols, int n, cudaStream_t st) {
+    dim3 grid((pitch + 255) / 256, rows, n);
+    SLAM_KERNEL("prepare", st, prepare_kernel<<<grid, 256, 0, st>>>(src, channels, src_stride, src_frame_bytes, map, dst, pitch,
+                                                                    dst_frame_bytes, rows, cols));
+    return 1;
+}
 
 int launch_repitch(const uint8_t* src, int stride, uint8_t* dst, int pitch, int cols, long long rows_total, cudaStream_t st) {
     dim3 grid(min((pitch / 4 + 31) / 32, 4), (unsigned)((rows_total + 7) / 8));

@@ -45,6 +45,28 @@ class FrameSequence:
             raise RuntimeError("frames must be a C-contiguous (n, rows, cols) uint8 array")
         self.ctx.check(self.ctx.lib.slamcu_sequence_upload(self.handle, first, a.shape[0], a.ctypes.data, self.cols))
 
+    def prepare(self, frames: np.ndarray, camera=None, first: int = 0):
+        """Preprocessor::yield for a batch: frames (n, rows, cols) gray or (n, rows, cols, 3) BGR uint8; BGR2GRAY and, with a
+        Camera, undistortImage, written straight into the frame store."""
+        a = np.ascontiguousarray(frames)
+        if a.dtype != np.uint8 or a.ndim not in (3, 4) or a.shape[1:3] != (self.rows, self.cols) or (a.ndim == 4 and a.shape[3] != 3):
+            raise RuntimeError("frames must be (n, rows, cols) or (n, rows, cols, 3) uint8")
+        ch = 3 if a.ndim == 4 else 1
+        K4 = D4 = None
+        if camera is not None:
+            K4 = np.array([camera.fx, camera.fy, camera.cx, camera.cy], np.float64)
+            D4 = np.array([camera.k1, camera.k2, camera.p1, camera.p2], np.float64)
+        self.ctx.check(self.ctx.lib.slamcu_sequence_prepare(self.handle, first, a.shape[0], a.ctypes.data, ch, self.cols * ch,
+                                                            K4.ctypes.data if K4 is not None else None,
+                                                            D4.ctypes.data if D4 is not None else None))
+        self.ctx.synchronize()  # the host array may go away
+
+    def image(self, f: int) -> np.ndarray:
+        """The prepared 8-bit frame f as the detector sees it (device -> host)."""
+        out = np.zeros((self.rows, self.cols), np.uint8)
+        self.ctx.check(self.ctx.lib.slamcu_sequence_image(self.handle, f, out.ctypes.data, self.cols))
+        return out
+
     def upload_ptr(self, host_ptr: int, n: int, first: int = 0):
         self.ctx.check(self.ctx.lib.slamcu_sequence_upload(self.handle, first, n, C.c_void_p(host_ptr), self.cols))
 

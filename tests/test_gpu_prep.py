@@ -64,3 +64,29 @@ def test_undistort_other_cameras(gpu_ctx, oracle, tmp_path):
             assert (want == 0).mean() > 0.02
     with pytest.raises(RuntimeError, match="Could not find keys"):
         s.Camera(yml, 3, gpu_ctx)
+
+
+def test_sequence_prepare_batches_gray_and_undistort(gpu_ctx, oracle):
+    """slamcu_sequence_prepare == per-frame cvtColor + undistortImage gather, and extraction runs on the prepared frames."""
+    cv2 = pytest.importorskip("cv2")
+    import slam_cin0051_b200 as s
+    cam = s.Camera(os.path.join(DATA, "camera.yml"), 0, gpu_ctx)
+    rng = np.random.default_rng(5)
+    base = load_gray("images/0000000000.png")
+    bgr = np.stack([np.stack([np.roll(base, k, 1), base, np.roll(base, -k, 0)], -1) for k in (1, 2, 3)])  # 3 colour frames
+    bgr = (bgr.astype(np.int32) + rng.integers(-3, 4, bgr.shape)).clip(0, 255).astype(np.uint8)
+    seq = s.FrameSequence(512, 1392, 3, desc_bytes=32, max_keypoints=4096, max_raw_corners=65536, context=gpu_ctx)
+    K4, D4 = [cam.fx, cam.fy, cam.cx, cam.cy], [cam.k1, cam.k2, cam.p1, cam.p2]
+    seq.prepare(bgr, cam)
+    det = s.FeatureDetector(os.path.join(DATA, "feature_detector.yml"), gpu_ctx)
+    seq.extract(det)
+    for f in range(3):
+        gray = cv2.cvtColor(bgr[f], cv2.COLOR_BGR2GRAY)
+        _, mp = oracle.undistort(gray, K4, D4, want_map=True)
+        want = np.where(mp >= 0, gray.reshape(-1)[np.maximum(mp, 0)], 0).astype(np.uint8)
+        assert np.array_equal(seq.image(f), want), f
+        wk, wd = oracle.detect_and_compute(want)
+        gk, gd = seq.frame(f)
+        assert gk.tobytes() == wk.tobytes() and np.array_equal(gd, wd)
+    seq.prepare(bgr[:, :, :, 1].copy())  # gray, no camera: plain upload semantics
+    assert np.array_equal(seq.image(1), bgr[1, :, :, 1])
