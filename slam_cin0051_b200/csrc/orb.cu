@@ -509,38 +509,67 @@ __global__ void __launch_bounds__(128) harris_kernel(SeqView s, OrbView o, int f
 }
 
 // ---- B5: one block per (level, frame) --------------------------------------------------------------------
+// KeyPointsFilter::retainBest(quota): keep everything >= the quota-th largest response (ties kept).  The threshold is
+// found by an MSB-first radix select over the order-preserving integer image of the float responses (four 8-bit
+// passes with a shared-memory histogram) instead of counting, for every element, how many are larger.
+__device__ __forceinline__ uint32_t float_order_key(float v) {
+    uint32_t b = __float_as_uint(v);
+    if (b == 0x80000000u) b = 0u;  // -0.0 compares equal to +0.0
+    return b ^ ((b >> 31) ? 0xffffffffu : 0x80000000u);
+}
+
 __global__ void __launch_bounds__(256) orb_retain_kernel(SeqView s, OrbView o, int first, int smem_cap) {
-    extern __shared__ float sr[];
+    __shared__ int hist[256];
     __shared__ int warp_tot[8];
     __shared__ int carry;
+    __shared__ uint32_t sh_prefix;
+    __shared__ int sh_want;
     const int l = blockIdx.x, f = first + blockIdx.y;
     const OrbLevel& L = o.lv[l];
     const int n = o.n_sel[f * kMaxLevels + l];
     const size_t base_off = (size_t)f * o.cand_total + L.coff;
-    const float* gr = o.sresp + base_off;
+    const float* r = o.sresp + base_off;
     const uint32_t* sxy = o.sxy + base_off;
     uint32_t* fxy = o.fxy + base_off;
     float* fr = o.fresp + base_off;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const bool in_smem = n <= smem_cap;
-    if (in_smem)
-        for (int i = threadIdx.x; i < n; i += blockDim.x) sr[i] = gr[i];
+    const int want = L.quota;
+    (void)smem_cap;
+    uint32_t thr_key = 0u;  // keep everything
+    if (want <= 0) thr_key = 0xffffffffu;  // n_points == 0 -> nothing survives (keys never reach all ones: no NaNs)
+    else if (n > want) {
+        if (threadIdx.x == 0) { sh_prefix = 0u; sh_want = want; }
+        for (int pass = 0; pass < 4; pass++) {
+            const int shift = 24 - 8 * pass;
+            hist[threadIdx.x] = 0;
+            __syncthreads();
+            const uint32_t prefix = sh_prefix;
+            const uint32_t himask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+            for (int i = threadIdx.x; i < n; i += 256) {
+                const uint32_t k = float_order_key(r[i]);
+                if ((k & himask) == prefix) atomicAdd(&hist[(k >> shift) & 255], 1);
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {  // the digit in which the want-th largest key falls
+                int acc = 0, d = 255;
+                const int w = sh_want;
+                for (; d > 0; d--) {
+                    if (acc + hist[d] >= w) break;
+                    acc += hist[d];
+                }
+                sh_want = w - acc;
+                sh_prefix = prefix | ((uint32_t)d << shift);
+            }
+            __syncthreads();
+        }
+        thr_key = sh_prefix;
+    }
     if (threadIdx.x == 0) carry = 0;
     __syncthreads();
-    const float* r = in_smem ? sr : gr;
-    const int want = L.quota;
     for (int base = 0; base < n; base += 256) {
         const int i = base + threadIdx.x;
-        bool keep = false;
-        if (i < n) {
-            if (n <= want) keep = true;
-            else if (want > 0) {
-                const float v = r[i];
-                int greater = 0;
-                for (int j = 0; j < n; j++) greater += (r[j] > v) ? 1 : 0;
-                keep = greater < want;  // v >= the want-th largest (ties kept)
-            }
-        }
+        const float v = i < n ? r[i] : 0.f;
+        const bool keep = i < n && thr_key != 0xffffffffu && float_order_key(v) >= thr_key;
         const unsigned b = __ballot_sync(0xffffffffu, keep);
         if (lane == 0) warp_tot[warp] = __popc(b);
         __syncthreads();
@@ -549,7 +578,7 @@ __global__ void __launch_bounds__(256) orb_retain_kernel(SeqView s, OrbView o, i
         if (keep) {
             const int pos = off + __popc(b & lanemask_lt());
             fxy[pos] = sxy[i];
-            fr[pos] = r[i];
+            fr[pos] = v;
         }
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -871,9 +900,7 @@ int launch_orb_extract(const SeqView& s, const OrbView& o, int first, int n, cud
     int max_quota = 1;
     for (int l = 0; l < o.nlevels; l++) max_quota = max(max_quota, o.lv[l].quota);
     SLAM_KERNEL("harris", st, harris_kernel<<<dim3((2 * max_quota + 127) / 128, o.nlevels, n), 128, 0, st>>>(s, o, first));
-    const int retain_cap = 12 * 1024;
-    SLAM_KERNEL("orb_retain", st,
-                orb_retain_kernel<<<dim3(o.nlevels, n), 256, retain_cap * sizeof(float), st>>>(s, o, first, retain_cap));
+    SLAM_KERNEL("orb_retain", st, orb_retain_kernel<<<dim3(o.nlevels, n), 256, 0, st>>>(s, o, first, 0));
     SLAM_KERNEL("orb_assemble", st, orb_assemble_kernel<<<n, 256, 0, st>>>(s, o, first));
     launches += 4;
     if (forked) cudaStreamWaitEvent(st, ev_join, 0);
