@@ -587,7 +587,7 @@ static int seq_ensure_orb(slamcu_sequence* s, slamcu_detector* det) {
     const float factor = (float)(1.0 / sf);
     float ndesired = det->max_features * (1 - factor) / (1 - (float)std::pow((double)factor, (double)L));
     int sum = 0;
-    size_t pyr = 0, mw = 0, ct = 0;
+    size_t pyr = 0, mw = 0, ct = 0, sb = 0;
     for (int l = 0; l < L; l++) {
         OrbLevel& lv = o.lv[l];
         lv.scale = (float)std::pow(sf, (double)l);
@@ -600,6 +600,8 @@ static int seq_ensure_orb(slamcu_sequence* s, slamcu_detector* det) {
         else { lv.off = pyr; pyr += (size_t)lv.rows * lv.pitch; }
         lv.moff = mw;
         mw += (size_t)lv.rows * lv.mwords;
+        lv.soff = sb;
+        sb += (size_t)lv.rows * lv.pitch;
         if (l < L - 1) { lv.quota = (int)std::lrintf(ndesired); sum += lv.quota; ndesired *= factor; }
         else lv.quota = std::max(det->max_features - sum, 0);
         lv.capc = round_up(std::max(2048, lv.rows * lv.cols / 16), 32);
@@ -609,6 +611,7 @@ static int seq_ensure_orb(slamcu_sequence* s, slamcu_detector* det) {
     o.pyr_bytes = std::max<size_t>(pyr, 16);
     o.mask_words = mw;
     o.cand_total = ct;
+    o.score_bytes = sb;
     const size_t F = (size_t)s->max_frames;
     int rc = SLAMCU_OK;
     auto A = [&](auto** p, size_t count, bool zero) {
@@ -617,6 +620,7 @@ static int seq_ensure_orb(slamcu_sequence* s, slamcu_detector* det) {
     A(&o.pyr, F * o.pyr_bytes, true);
     A(&o.pyrb, F * o.pyr_bytes, true);
     A(&o.mask, F * o.mask_words, false);
+    A(&o.fscore, F * o.score_bytes, false);
     A(&o.cxy, F * ct, false);
     A(&o.cscore, F * ct, false);
     A(&o.sxy, F * ct, false);

@@ -85,7 +85,6 @@ __global__ void __launch_bounds__(256) pyr_down_kernel(SeqView s, OrbView o, int
 //   4  3x3 strict NMS + edgeThreshold border filter for the list-2 entries inside the tile -> bit mask
 constexpr int FTW = 128, FTH = 32, FHX = 16, FSW = FTW + 2 * FHX, FSH = FTH + 8;  // pixel tile with halo
 constexpr int SCW = FTW + 8, SCH = FTH + 2;  // score grid: x0-4 .. x0+131 (4-px groups), y0-1 .. y0+32
-constexpr int SCG = SCW / 4;
 
 __device__ __forceinline__ int fast9_ring_score(int v, const int (&p)[16], int thr) {
     // cornerScore of cv::FAST (9/16): max over the 16 arcs of 9 ring pixels of min |v - p| (one sign), minus 1.
@@ -328,8 +327,10 @@ __global__ void __launch_bounds__(256) fast9_mask_kernel(SeqView s, OrbView o, i
         const uint8_t* c = sc + idx;
         const int v = c[0];
         if (v > c[-1] && v > c[1] && v > c[-SCW - 1] && v > c[-SCW] && v > c[-SCW + 1] && v > c[SCW - 1] && v > c[SCW] &&
-            v > c[SCW + 1])
+            v > c[SCW + 1]) {
             atomicOr(&mw[r * (FTW / 32) + (lx >> 5)], 1u << (lx & 31));
+            (o.fscore + (size_t)f * o.score_bytes + L.soff)[(size_t)gy * L.pitch + gx] = (uint8_t)v;  // read back by orb_select
+        }
     }
     __syncthreads();
     if (threadIdx.x < FTH * (FTW / 32)) {
@@ -337,13 +338,6 @@ __global__ void __launch_bounds__(256) fast9_mask_kernel(SeqView s, OrbView o, i
         if (gy < L.rows && wi < L.mwords)
             (o.mask + (size_t)f * o.mask_words + L.moff)[(size_t)gy * L.mwords + wi] = mw[threadIdx.x];
     }
-}
-
-// global-memory version of the score for the list kernel (same arithmetic, pitch-strided)
-__device__ int fast9_score_global(const uint8_t* c, int pitch, int thr) {
-    int p[16];
-    fast9_load_ring(c, pitch, p);
-    return fast9_ring_score(c[0], p, thr);
 }
 
 // ---- B3: one block per (level, frame) ---------------------------------------------------------------
@@ -356,7 +350,7 @@ __global__ void __launch_bounds__(256) orb_select_kernel(SeqView s, OrbView o, i
     const int l = blockIdx.x, f = first + blockIdx.y;
     const OrbLevel& L = o.lv[l];
     const uint32_t* mask = o.mask + (size_t)f * o.mask_words + L.moff;
-    const uint8_t* img = level_ptr(s, o, f, l);
+    const uint8_t* fsc = o.fscore + (size_t)f * o.score_bytes + L.soff;
     uint32_t* cxy = o.cxy + (size_t)f * o.cand_total + L.coff;
     int* csc = o.cscore + (size_t)f * o.cand_total + L.coff;
     uint32_t* sxy = o.sxy + (size_t)f * o.cand_total + L.coff;
@@ -420,7 +414,7 @@ __global__ void __launch_bounds__(256) orb_select_kernel(SeqView s, OrbView o, i
     __syncthreads();
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const uint32_t p = cxy[i];
-        const int sc = fast9_score_global(img + (size_t)(p >> 16) * L.pitch + (p & 0xffff), L.pitch, o.fast_threshold);
+        const int sc = fsc[(size_t)(p >> 16) * L.pitch + (p & 0xffff)];  // written by fast9_mask_kernel for every survivor
         csc[i] = sc;
         atomicAdd(&hist[min(max(sc, 0), 255)], 1);
     }

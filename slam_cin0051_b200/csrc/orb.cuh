@@ -16,6 +16,7 @@ struct OrbLevel {
     size_t off;      // byte offset of this level inside a frame's pyramid block (level 0 lives in SeqView::img)
     size_t moff;     // word offset of this level's corner mask inside a frame's mask block
     size_t coff;     // element offset of this level's candidate lists inside a frame's candidate block
+    size_t soff;     // byte offset of this level inside a frame's FAST-score block (rows * pitch bytes per level)
     int capc;        // candidate capacity
     int quota;       // nfeaturesPerLevel
     float scale;     // (float)pow(scaleFactor, level)
@@ -35,6 +36,8 @@ struct OrbView {
     uint8_t* pyr;         // [F][pyr_bytes]
     uint8_t* pyrb;        // [F][pyr_bytes]   blurred levels 1..L-1 (level 0 -> SeqView::blur)
     uint32_t* mask;       // [F][mask_words]  FAST-9 + 3x3 NMS + border-filter survivors, 1 bit / pixel
+    uint8_t* fscore;      // [F][score_bytes] FAST score, defined only at the survivors' pixels
+    size_t score_bytes;   // per frame
     uint32_t* cxy;        // [F][cand_total]  candidates, raster order per level: (y << 16) | x
     int* cscore;          // [F][cand_total]  FAST score
     uint32_t* sxy;        // [F][cand_total]  after retainBest(2*quota)
