@@ -86,34 +86,11 @@ __global__ void __launch_bounds__(256) pyr_down_kernel(SeqView s, OrbView o, int
 constexpr int FTW = 128, FTH = 32, FHX = 16, FSW = FTW + 2 * FHX, FSH = FTH + 8;  // pixel tile with halo
 constexpr int SCW = FTW + 8, SCH = FTH + 2;  // score grid: x0-4 .. x0+131 (4-px groups), y0-1 .. y0+32
 
-__device__ __forceinline__ int fast9_ring_score(int v, const int (&p)[16], int thr) {
-    // cornerScore of cv::FAST (9/16): max over the 16 arcs of 9 ring pixels of min |v - p| (one sign), minus 1.
-    // With d = v - p:  min over an arc of d = v - max(p),  min of -d = min(p) - v, so the score needs the
-    // sliding-window (length 9, circular) min and max of the raw ring pixels: doubling steps 2, 4, 8, then +1.
-    // The subtraction from v is applied AFTER the min/max network on purpose: nvcc 12.9 folds
-    // max(a, -b) chains into VIMNMX3 for sm_100a and loses the negation ("toolchain findings").
-    int n2[16], x2[16], n4[16], x4[16];
-#pragma unroll
-    for (int i = 0; i < 16; i++) {
-        n2[i] = min(p[i], p[(i + 1) & 15]);
-        x2[i] = max(p[i], p[(i + 1) & 15]);
-    }
-#pragma unroll
-    for (int i = 0; i < 16; i++) {
-        n4[i] = min(n2[i], n2[(i + 2) & 15]);
-        x4[i] = max(x2[i], x2[(i + 2) & 15]);
-    }
-    int brightest_min = 0, darkest_max = 255;
-#pragma unroll
-    for (int i = 0; i < 16; i++) {
-        const int n9 = min(min(n4[i], n4[(i + 4) & 15]), p[(i + 8) & 15]);
-        const int x9 = max(max(x4[i], x4[(i + 4) & 15]), p[(i + 8) & 15]);
-        brightest_min = max(brightest_min, n9);  // best arc whose pixels are all brighter than v
-        darkest_max = min(darkest_max, x9);      // best arc whose pixels are all darker than v
-    }
-    const int bright = brightest_min - v, dark = v - darkest_max;
-    return max(thr, max(bright, dark)) - 1;
-}
+// cornerScore of cv::FAST (9/16) = max over the 16 arcs of 9 ring pixels of min |v - p| (one sign), minus 1.
+// With d = v - p:  min over an arc of d = v - max(p),  min of -d = min(p) - v, so the score needs the sliding-window
+// (length 9, circular) min or max of the raw ring pixels: doubling steps 2, 4, 8, then +1 (fast9_ring_score_kind below).
+// The subtraction from v is applied AFTER the min/max network on purpose: nvcc 12.9 folds max(a, -b) chains into
+// VIMNMX3 for sm_100a and loses the negation ("toolchain finding").
 
 // ring of radius 3, OpenCV order; only the set of arcs matters
 __device__ __forceinline__ void fast9_load_ring(const uint8_t* t, int stride, int (&p)[16]) {
