@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(256) pyr_down_kernel(SeqView s, OrbView o, int
 }
 
 // ---- B2 ------------------------------------------------------------------------------------------
-// FAST-9/16 + cornerScore + 3x3 NMS + border filter, one 128x32 output tile per block, in compacting phases so
+// FAST-9/16 + cornerScore + 3x3 NMS + border filter, one 128x48 output tile per block, in compacting phases so
 // that every phase runs with full warps (the one-thread-per-pixel form spent half its issue slots diverged):
 //   0  stage the tile (+16 px / 4 row halo) in shared memory with aligned 128-bit loads; clear the score grid
 //   1  SWAR pre-test, 4 pixels per thread on packed bytes: a 9-arc contains two ring pixels 90 degrees apart
@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(256) pyr_down_kernel(SeqView s, OrbView o, int
 //   2  segment test on list 1 (16-bit brighter / darker ring masks, run of 9 by shift-AND) -> corners to list 2
 //   3  cornerScore for list 2 -> dense score grid (1 px ring around the tile for the NMS)
 //   4  3x3 strict NMS + edgeThreshold border filter for the list-2 entries inside the tile -> bit mask
-constexpr int FTW = 128, FTH = 32, FHX = 16, FSW = FTW + 2 * FHX, FSH = FTH + 8;  // pixel tile with halo
+constexpr int FTW = 128, FTH = 48, FHX = 16, FSW = FTW + 2 * FHX, FSH = FTH + 8;  // pixel tile with halo
 constexpr int SCW = FTW + 8, SCH = FTH + 2;  // score grid: x0-4 .. x0+131 (4-px groups), y0-1 .. y0+32
 
 // cornerScore of cv::FAST (9/16) = max over the 16 arcs of 9 ring pixels of min |v - p| (one sign), minus 1.
@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(256) fast9_mask_kernel(SeqView s, OrbView o, i
         }
     }
     __syncthreads();
-    // ---- phase 2: segment test (list-2 entries carry the polarity in bits 13-14)
+    // ---- phase 2: segment test (list-2 entries carry the polarity in bits 14-15)
     const int c1 = n1;
     for (int e = threadIdx.x; e < c1; e += 256) {
         const int idx = list1[e];
@@ -278,14 +278,14 @@ __global__ void __launch_bounds__(256) fast9_mask_kernel(SeqView s, OrbView o, i
         int p[16];
         fast9_load_ring(t, FSW, p);
         const int kind = fast9_corner_kind(t[0], p, thr);
-        if (kind) list2[atomicAdd(&n2, 1)] = (uint16_t)(idx | (kind << 13));
+        if (kind) list2[atomicAdd(&n2, 1)] = (uint16_t)(idx | (kind << 14));
     }
     __syncthreads();
     // ---- phase 3: scores
     const int c2 = n2;
     for (int e = threadIdx.x; e < c2; e += 256) {
         const int ent = list2[e];
-        const int idx = ent & 0x1fff, kind = ent >> 13;
+        const int idx = ent & 0x3fff, kind = ent >> 14;
         const int ry = idx / SCW, cx = idx - ry * SCW;
         const uint8_t* t = tile + (ry + 3) * FSW + (FHX - 4) + cx;
         int p[16];
@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(256) fast9_mask_kernel(SeqView s, OrbView o, i
     __syncthreads();
     // ---- phase 4: NMS + border filter
     for (int e = threadIdx.x; e < c2; e += 256) {
-        const int idx = list2[e] & 0x1fff;
+        const int idx = list2[e] & 0x3fff;
         const int ry = idx / SCW, cx = idx - ry * SCW;
         const int r = ry - 1, lx = cx - 4;
         if ((unsigned)r >= (unsigned)FTH || (unsigned)lx >= (unsigned)FTW) continue;

@@ -59,7 +59,7 @@ struct OrbTmaps {
     CUtensorMap fast[kMaxLevels];
     bool valid = false;
 };
-constexpr int kFastBoxW = 160, kFastBoxH = 40;  // FSW x FSH of fast9_mask_kernel
+constexpr int kFastBoxW = 160, kFastBoxH = 56;  // FSW x FSH of fast9_mask_kernel
 
 // aux / ev_fork / ev_join: optional second stream (and two events) on which the blur kernels run concurrently
 int launch_orb_extract(const SeqView& s, const OrbView& o, int first, int n, cudaStream_t st, cudaStream_t aux = nullptr,
