@@ -116,7 +116,9 @@ public:
         if (fs.has("NumLevels") || fs.has("MaxFeatures") || fs.has("ScaleFactor")) {
             if (!fs.has("OrbPatternFile"))
                 throw std::runtime_error("ORB mode needs OrbPatternFile (256x4 int32 rBRIEF pattern, raw little-endian).");
-            std::ifstream pf(fs.getString("OrbPatternFile"), std::ios::binary);
+            std::filesystem::path pat(fs.getString("OrbPatternFile"));
+            if (pat.is_relative()) pat = configPath.parent_path() / pat;  // relative to the YAML file
+            std::ifstream pf(pat, std::ios::binary);
             m_orbPattern.resize(1024);
             pf.read(reinterpret_cast<char*>(m_orbPattern.data()), 4096);
             if (pf.gcount() != 4096) throw std::runtime_error("Could not read OrbPatternFile.");

@@ -52,9 +52,11 @@ double now() {
 
 int main(int argc, char** argv) {
     std::string det_cfg, mat_cfg, raw;
-    int rows = 376, cols = 1241, frames = 256, steps = 5, warmup = 3, with_kp = 0, max_kp = 2560, chunk = 128;
+    int rows = 376, cols = 1241, frames = 256, steps = 5, warmup = 3, with_kp = 0, max_kp = 2560, chunk = 128, pitch_px = 14;
+    bool ransac = false;
+    double K4[4] = {525.0, 525.0, 319.5, 239.5};
     int opt;
-    while ((opt = getopt(argc, argv, "hc:m:W:H:f:s:w:kr:K:C:")) != -1) {
+    while ((opt = getopt(argc, argv, "hc:m:W:H:f:s:w:kr:K:C:e:p:")) != -1) {
         switch (opt) {
             case 'c': det_cfg = optarg; break;
             case 'm': mat_cfg = optarg; break;
@@ -67,8 +69,13 @@ int main(int argc, char** argv) {
             case 'r': raw = optarg; break;
             case 'K': max_kp = std::atoi(optarg); break;
             case 'C': chunk = std::atoi(optarg); break;
+            case 'p': pitch_px = std::atoi(optarg); break;
+            case 'e':  // -e fx,fy,cx,cy : also run findEssentialMat(RANSAC) on every consecutive pair
+                ransac = std::sscanf(optarg, "%lf,%lf,%lf,%lf", &K4[0], &K4[1], &K4[2], &K4[3]) == 4;
+                if (!ransac) { std::fprintf(stderr, "slam_bench: -e expects fx,fy,cx,cy\n"); return 2; }
+                break;
             default:
-                std::printf("usage: %s -c detector.yml -m matcher.yml [-W cols -H rows -f frames -s steps -w warmup -k -r raw.u8 -K max_kp -C chunk]\n", argv[0]);
+                std::printf("usage: %s -c detector.yml -m matcher.yml [-W cols -H rows -f frames -s steps -w warmup -k -r raw.u8 -K max_kp -C chunk -p scene_pitch -e fx,fy,cx,cy]\n", argv[0]);
                 return opt == 'h' ? 0 : 2;
         }
     }
@@ -89,7 +96,7 @@ int main(int argc, char** argv) {
             if (!f || std::fread(host, 1, fb * frames, f) != fb * frames) throw std::runtime_error("could not read " + raw);
             std::fclose(f);
         } else {
-            for (int f0 = 0; f0 < frames; f0 += 16) make_frames(host + fb * f0, std::min(16, frames - f0), rows, cols, 14, 1000 + f0 / 16);
+            for (int f0 = 0; f0 < frames; f0 += 16) make_frames(host + fb * f0, std::min(16, frames - f0), rows, cols, pitch_px, 1000 + f0 / 16);
         }
         slamcu_sequence* seq = nullptr;
         ctx.check(slamcu_sequence_create(ctx.get(), rows, cols, frames, 0, max_kp, det.descriptorBytes(), &seq));
@@ -101,11 +108,13 @@ int main(int argc, char** argv) {
         auto resident = [&]() {
             ctx.check(slamcu_sequence_extract(seq, det.handle(), 0, frames));
             ctx.check(slamcu_sequence_match(seq, mat.handle(), 0, frames - 1, with_kp));
+            if (ransac) ctx.check(slamcu_sequence_essential(seq, 0, frames - 1, K4, 0.999, 1.0, 1000));
         };
         auto e2e = [&]() {
             ctx.check(slamcu_sequence_process(seq, det.handle(), mat.handle(), host, cols, frames, chunk, with_kp,
                                               static_cast<slamcu_keypoint*>(hk), static_cast<uint8_t*>(hd),
                                               static_cast<slamcu_dmatch*>(hm), static_cast<int32_t*>(hc)));
+            if (ransac) ctx.check(slamcu_sequence_essential(seq, 0, frames - 1, K4, 0.999, 1.0, 1000));
             ctx.check(slamcu_synchronize(ctx.get()));
         };
         ctx.check(slamcu_sequence_upload(seq, 0, frames, host, cols));
@@ -122,15 +131,22 @@ int main(int argc, char** argv) {
         for (int i = 0; i < steps; i++) e2e();
         const double t_e2e = now() - t0;
         const int32_t* c = static_cast<const int32_t*>(hc);
-        long kp = 0, nm = 0, bad = 0;
+        long kp = 0, nm = 0, bad = 0, inl = 0, its = 0;
         for (int f = 0; f < frames; f++) { kp += c[4 * f]; nm += c[4 * f + 1]; bad += c[4 * f + 3] != 0; }
+        if (ransac)
+            for (int f = 0; f + 1 < frames; f += std::max(1, (frames - 1) / 16)) {  // sample 16 pairs
+                int ni = 0, nit = 0;
+                ctx.check(slamcu_sequence_essential_read(seq, f, nullptr, &ni, &nit, nullptr, 0, nullptr));
+                inl += ni; its += nit;
+            }
         std::printf("{\"tool\": \"slam_bench\", \"rows\": %d, \"cols\": %d, \"frames_per_step\": %d, \"steps\": %d, "
                     "\"frames_per_s_resident\": %.1f, \"frames_per_s_e2e\": %.1f, \"ms_per_step_resident\": %.3f, "
                     "\"ms_per_step_e2e\": %.3f, \"keypoints_per_frame\": %.1f, \"matches_per_pair\": %.1f, "
-                    "\"overflowed_frames\": %ld, \"gpu_launches\": %lld}\n",
+                    "\"overflowed_frames\": %ld, \"gpu_launches\": %lld, \"ransac\": %s, \"ransac_inliers_sampled_sum\": %ld, "
+                    "\"ransac_iterations_sampled_sum\": %ld}\n",
                     rows, cols, frames, steps, frames * steps / t_res, frames * steps / t_e2e, 1e3 * t_res / steps,
                     1e3 * t_e2e / steps, static_cast<double>(kp) / frames, static_cast<double>(nm) / std::max(frames - 1, 1), bad,
-                    static_cast<long long>(launches));
+                    static_cast<long long>(launches), ransac ? "true" : "false", inl, its);
         slamcu_sequence_destroy(seq);
         slamcu_free_pinned(hk); slamcu_free_pinned(hd); slamcu_free_pinned(hm); slamcu_free_pinned(hc); slamcu_free_pinned(host);
     } catch (const std::exception& e) {
