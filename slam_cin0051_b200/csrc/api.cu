@@ -1539,12 +1539,13 @@ int slamcu_find_essential(slamcu_context* ctx, const float* p1, const float* p2,
     CU(ctx, cudaSetDevice(ctx->device));
     const size_t b_pts = ((size_t)n * 16 + 255) / 256 * 256, b_in = ((size_t)n * 8 + 255) / 256 * 256;
     const size_t b_mask = ((size_t)n + 255) / 256 * 256;
-    int rc = ensure_scratch(ctx, 2 * b_pts + 2 * b_in + b_mask + 1024);
+    int rc = ensure_scratch(ctx, 2 * b_pts + 2 * b_in + b_mask + 1024 + essential_model_scratch_doubles() * 8);
     if (rc != SLAMCU_OK) return rc;
     uint8_t* base = static_cast<uint8_t*>(ctx->scratch);
     EssentialJob j{};
     j.x1 = reinterpret_cast<double2*>(base);
     j.x2 = reinterpret_cast<double2*>(base + b_pts);
+    j.models = reinterpret_cast<double*>(base + 2 * b_pts + 2 * b_in + b_mask + 1024);
     float* d_p1 = reinterpret_cast<float*>(base + 2 * b_pts);
     float* d_p2 = reinterpret_cast<float*>(base + 2 * b_pts + b_in);
     j.mask = base + 2 * b_pts + 2 * b_in;
@@ -1661,6 +1662,7 @@ int slamcu_sequence_essential(slamcu_sequence* s, int first, int n_pairs, const 
         A(&e.n_inliers, F);
         A(&e.n_iters, F);
         A(&e.mask, F * v.cap_kp);
+        A(&e.models, F * essential_model_scratch_doubles());
         if (rc != SLAMCU_OK) return rc;
         e.pt_stride = v.cap_kp;
         s->has_ess = true;

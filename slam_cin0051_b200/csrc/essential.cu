@@ -8,22 +8,24 @@
 // same mathematics (Nister) with its own null-space basis and root finder: candidates agree with OpenCV's to
 // rounding, their order inside one sample may differ (that only matters for exact ties at the maximum).
 //
-// essential_ransac_kernel: one block per frame pair, adaptive like the original loop but in waves of WAVE samples:
-//   thread 0 draws the wave's subsets from the sequential RNG; one thread per sample runs the minimal solver;
+// essential_ransac_kernel: one block (RT threads) per frame pair, adaptive like the original loop but in waves that
+// grow 16, 32, 64, 128, 256, 256, ... samples (most pairs finish inside the first wave: niters drops to ~10 after the
+// first good model; a wave costs one solver latency whatever its size, so a pair that needs all 1000 iterations takes 7):
+//   one thread per sample runs the minimal solver while an otherwise idle thread draws the NEXT wave's subsets from
+//   the sequential RNG (drawing past the end of the loop is harmless: nothing consumes the stream afterwards);
 //   one warp per hypothesis scores all correspondences (ballot + popc inlier count); thread 0 replays the
 //   sequential accept / niters rule over the wave; the loop ends as soon as the replay reaches niters.
 // Finally the block writes the winner's inlier mask.
 #include "common.cuh"
+#include "fivept.cuh"
 
 namespace slamcu {
 namespace {
 
-constexpr int WAVE = 64;      // samples solved per wave (= threads per block)
-constexpr int MAXM = 10;      // essential matrices per sample
-
-__constant__ int kT11[4][4] = {{0, 3, 4, 6}, {3, 1, 5, 7}, {4, 5, 2, 8}, {6, 7, 8, 9}};
-__constant__ int kT21[10][4] = {{0, 2, 4, 5},    {3, 1, 6, 7},    {10, 13, 16, 17}, {2, 3, 8, 9},     {4, 8, 10, 11},
-                                {8, 6, 13, 14},  {5, 9, 11, 12},  {9, 7, 14, 15},   {11, 14, 17, 18}, {12, 15, 18, 19}};
+constexpr int RT = 256;       // threads per block (scoring warps: RT / 32)
+constexpr int WAVE = RT;      // most samples solved per wave (one thread each)
+constexpr int WAVE0 = 16;     // first wave
+constexpr int MAXM = kMaxModels;
 
 struct CvRng {
     unsigned long long s;
@@ -32,248 +34,6 @@ struct CvRng {
         return (unsigned)s;
     }
 };
-
-// linear polynomial (x, y, z, 1) products; monomial orders documented in DESIGN.md (x, y, z, 1 | xx, yy, zz, xy, xz, yz, x, y, z, 1 | Nister order)
-__device__ void mul11(const double* a, const double* b, double* out /*10, accumulated*/, double sign) {
-#pragma unroll
-    for (int i = 0; i < 4; i++)
-#pragma unroll
-        for (int j = 0; j < 4; j++) out[kT11[i][j]] += sign * (a[i] * b[j]);
-}
-__device__ void mul21(const double* a, const double* b, double* out /*20, accumulated*/) {
-    for (int i = 0; i < 10; i++)
-#pragma unroll
-        for (int j = 0; j < 4; j++) out[kT21[i][j]] += a[i] * b[j];
-}
-
-// c = a * b for dense univariate polynomials, highest power first; na, nb = number of coefficients
-__device__ void polymul(const double* a, int na, const double* b, int nb, double* c, double sign, bool clear) {
-    if (clear)
-        for (int i = 0; i < na + nb - 1; i++) c[i] = 0.0;
-    for (int i = 0; i < na; i++)
-        for (int j = 0; j < nb; j++) c[i + j] += sign * (a[i] * b[j]);
-}
-
-__device__ double polyval(const double* a, int n, double x) {
-    double v = a[0];
-    for (int i = 1; i < n; i++) v = v * x + a[i];
-    return v;
-}
-
-// Real roots of a real polynomial (highest power first, n coefficients): Durand-Kerner in complex double
-// ((0.4 + 0.9i)^k start, Gauss-Seidel sweeps), then Newton polishing of the near-real roots.
-__device__ int real_roots(const double* c_in, int n_in, double* out) {
-    int lead = 0;
-    while (lead < n_in && c_in[lead] == 0.0) lead++;
-    const int n = n_in - lead - 1;  // degree
-    if (n < 1) return 0;
-    double a[11];
-    for (int i = 0; i <= n; i++) a[i] = c_in[lead + i] / c_in[lead];
-    double re[10], im[10];
-    {
-        double pr = 1.0, pi = 0.0;
-        for (int k = 0; k < n; k++) {
-            re[k] = pr;
-            im[k] = pi;
-            const double nr = pr * 0.4 - pi * 0.9, ni = pr * 0.9 + pi * 0.4;
-            pr = nr;
-            pi = ni;
-        }
-    }
-    for (int iter = 0; iter < 500; iter++) {
-        double delta = 0.0, big = 1.0;
-        for (int i = 0; i < n; i++) {
-            const double pr = re[i], pi = im[i];
-            double nr = a[0], ni = 0.0;  // Horner in complex
-            for (int k = 1; k <= n; k++) {
-                const double tr = nr * pr - ni * pi + a[k];
-                ni = nr * pi + ni * pr;
-                nr = tr;
-            }
-            double dr = 1.0, di = 0.0;
-            for (int j = 0; j < n; j++) {
-                if (j == i) continue;
-                const double qr = pr - re[j], qi = pi - im[j];
-                const double tr = dr * qr - di * qi;
-                di = dr * qi + di * qr;
-                dr = tr;
-            }
-            const double den = dr * dr + di * di;
-            if (den == 0.0) continue;
-            const double ur = (nr * dr + ni * di) / den, ui = (ni * dr - nr * di) / den;
-            re[i] = pr - ur;
-            im[i] = pi - ui;
-            delta = fmax(delta, sqrt(ur * ur + ui * ui));
-        }
-        for (int i = 0; i < n; i++) big = fmax(big, sqrt(re[i] * re[i] + im[i] * im[i]));
-        if (delta < 1e-15 * big) break;
-    }
-    double da[10], aa[11];
-    for (int i = 0; i < n; i++) da[i] = a[i] * (double)(n - i);
-    for (int i = 0; i <= n; i++) aa[i] = fabs(a[i]);
-    int cnt = 0;
-    for (int i = 0; i < n; i++) {
-        const double scale = fmax(1.0, fabs(re[i]));
-        if (fabs(im[i]) > 1e-6 * scale) continue;
-        double x = re[i];
-        for (int k = 0; k < 3; k++) {
-            const double f = polyval(a, n + 1, x), df = polyval(da, n, x);
-            if (df != 0.0) x -= f / df;
-        }
-        if (fabs(im[i]) <= 1e-10 * scale || fabs(polyval(a, n + 1, x)) < 1e-9 * (1.0 + polyval(aa, n + 1, fabs(x))))
-            out[cnt++] = x;
-    }
-    return cnt;
-}
-
-// Nister's 5-point solver.  x1, x2: 5 normalised correspondences.  models: up to MAXM row-major 3x3, |E|_F = 1.
-__device__ int five_point(const double (*x1)[2], const double (*x2)[2], double* models) {
-    // ---- null space of the 5x9 epipolar system (row-major E), full-pivot Gauss-Jordan + twice MGS
-    double Q[5][9];
-    int cols[9];
-    for (int p = 0; p < 5; p++) {
-        const double a[3] = {x1[p][0], x1[p][1], 1.0}, b[3] = {x2[p][0], x2[p][1], 1.0};
-        for (int i = 0; i < 3; i++)
-            for (int j = 0; j < 3; j++) Q[p][3 * i + j] = b[i] * a[j];
-    }
-    for (int k = 0; k < 9; k++) cols[k] = k;
-    for (int r = 0; r < 5; r++) {
-        int pr = r, pc = r;
-        double best = -1.0;
-        for (int i = r; i < 5; i++)
-            for (int j = r; j < 9; j++)
-                if (fabs(Q[i][j]) > best) { best = fabs(Q[i][j]); pr = i; pc = j; }
-        if (best <= 0.0) return 0;
-        for (int j = 0; j < 9; j++) { const double t = Q[r][j]; Q[r][j] = Q[pr][j]; Q[pr][j] = t; }
-        for (int i = 0; i < 5; i++) { const double t = Q[i][r]; Q[i][r] = Q[i][pc]; Q[i][pc] = t; }
-        { const int t = cols[r]; cols[r] = cols[pc]; cols[pc] = t; }
-        const double piv = Q[r][r];
-        for (int j = 0; j < 9; j++) Q[r][j] = Q[r][j] / piv;
-        for (int k = 0; k < 5; k++) {
-            if (k == r) continue;
-            const double fct = Q[k][r];
-            for (int j = 0; j < 9; j++) Q[k][j] = Q[k][j] - fct * Q[r][j];
-        }
-    }
-    double B4[4][9];
-    for (int k = 0; k < 4; k++) {
-        for (int j = 0; j < 9; j++) B4[k][j] = 0.0;
-        for (int r = 0; r < 5; r++) B4[k][cols[r]] = -Q[r][5 + k];
-        B4[k][cols[5 + k]] = 1.0;
-    }
-    for (int rep = 0; rep < 2; rep++)
-        for (int k = 0; k < 4; k++) {
-            for (int j = 0; j < k; j++) {
-                double d = 0.0;
-                for (int t = 0; t < 9; t++) d += B4[k][t] * B4[j][t];
-                for (int t = 0; t < 9; t++) B4[k][t] = B4[k][t] - d * B4[j][t];
-            }
-            double nn = 0.0;
-            for (int t = 0; t < 9; t++) nn += B4[k][t] * B4[k][t];
-            nn = sqrt(nn);
-            for (int t = 0; t < 9; t++) B4[k][t] = B4[k][t] / nn;
-        }
-    // ---- the ten cubic constraints: det(E) and (E E' - tr(E E')/2 I) E, for E = x B0 + y B1 + z B2 + B3
-    double A[10][20];
-    for (int i = 0; i < 10; i++)
-        for (int j = 0; j < 20; j++) A[i][j] = 0.0;
-    double Ep[9][4];
-    for (int e = 0; e < 9; e++)
-        for (int k = 0; k < 4; k++) Ep[e][k] = B4[k][e];
-    {
-        double t2[10];
-        for (int j = 0; j < 10; j++) t2[j] = 0.0;
-        mul11(Ep[1], Ep[5], t2, 1.0); mul11(Ep[2], Ep[4], t2, -1.0); mul21(t2, Ep[6], A[0]);
-        for (int j = 0; j < 10; j++) t2[j] = 0.0;
-        mul11(Ep[2], Ep[3], t2, 1.0); mul11(Ep[0], Ep[5], t2, -1.0); mul21(t2, Ep[7], A[0]);
-        for (int j = 0; j < 10; j++) t2[j] = 0.0;
-        mul11(Ep[0], Ep[4], t2, 1.0); mul11(Ep[1], Ep[3], t2, -1.0); mul21(t2, Ep[8], A[0]);
-    }
-    {
-        double L[3][3][10];
-        for (int i = 0; i < 3; i++)
-            for (int j = 0; j < 3; j++) {
-                for (int t = 0; t < 10; t++) L[i][j][t] = 0.0;
-                for (int k = 0; k < 3; k++) mul11(Ep[3 * i + k], Ep[3 * j + k], L[i][j], 1.0);
-            }
-        double tr[10];
-        for (int t = 0; t < 10; t++) tr[t] = (L[0][0][t] + L[1][1][t]) + L[2][2][t];
-        for (int i = 0; i < 3; i++)
-            for (int t = 0; t < 10; t++) L[i][i][t] = L[i][i][t] - 0.5 * tr[t];
-        for (int i = 0; i < 3; i++)
-            for (int j = 0; j < 3; j++)
-                for (int k = 0; k < 3; k++) mul21(L[i][k], Ep[3 * k + j], A[1 + 3 * i + j]);
-    }
-    // ---- Gauss-Jordan on the first ten columns, partial pivoting
-    for (int col = 0; col < 10; col++) {
-        int piv = col;
-        double best = fabs(A[col][col]);
-        for (int r = col + 1; r < 10; r++)
-            if (fabs(A[r][col]) > best) { best = fabs(A[r][col]); piv = r; }
-        if (best == 0.0) return 0;
-        if (piv != col)
-            for (int j = 0; j < 20; j++) { const double t = A[col][j]; A[col][j] = A[piv][j]; A[piv][j] = t; }
-        const double d = A[col][col];
-        for (int j = 0; j < 20; j++) A[col][j] = A[col][j] / d;
-        for (int r = 0; r < 10; r++) {
-            if (r == col) continue;
-            const double fct = A[r][col];
-            if (fct == 0.0) continue;
-            for (int j = 0; j < 20; j++) A[r][j] = A[r][j] - fct * A[col][j];
-        }
-    }
-    // ---- rows x^2z - z x^2, y^2z - z y^2, xyz - z xy  ->  B(z) (3 x 3 polynomial matrix), det B(z) of degree 10
-    double bx[3][4], by[3][4], b1[3][5];
-    for (int i = 0; i < 3; i++) {
-        const double* a = &A[4 + 2 * i][10];
-        const double* b = &A[5 + 2 * i][10];
-        bx[i][0] = 0.0 - b[0]; bx[i][1] = a[0] - b[1]; bx[i][2] = a[1] - b[2]; bx[i][3] = a[2] - 0.0;
-        by[i][0] = 0.0 - b[3]; by[i][1] = a[3] - b[4]; by[i][2] = a[4] - b[5]; by[i][3] = a[5] - 0.0;
-        b1[i][0] = 0.0 - b[6]; b1[i][1] = a[6] - b[7]; b1[i][2] = a[7] - b[8]; b1[i][3] = a[8] - b[9]; b1[i][4] = a[9] - 0.0;
-    }
-    double det[11], m[7];
-    polymul(bx[1], 4, by[2], 4, m, 1.0, true); polymul(by[1], 4, bx[2], 4, m, -1.0, false);
-    polymul(b1[0], 5, m, 7, det, 1.0, true);
-    polymul(bx[0], 4, by[2], 4, m, 1.0, true); polymul(by[0], 4, bx[2], 4, m, -1.0, false);
-    polymul(b1[1], 5, m, 7, det, -1.0, false);
-    polymul(bx[0], 4, by[1], 4, m, 1.0, true); polymul(by[0], 4, bx[1], 4, m, -1.0, false);
-    polymul(b1[2], 5, m, 7, det, 1.0, false);
-    double zs[10];
-    const int nz = real_roots(det, 11, zs);
-    int count = 0;
-    for (int k = 0; k < nz && count < MAXM; k++) {
-        const double z = zs[k];
-        const double z2 = z * z, z3 = z2 * z, z4 = z3 * z;
-        double Bz[3][3];
-        for (int i = 0; i < 3; i++) {
-            Bz[i][0] = ((bx[i][0] * z3 + bx[i][1] * z2) + bx[i][2] * z) + bx[i][3];
-            Bz[i][1] = ((by[i][0] * z3 + by[i][1] * z2) + by[i][2] * z) + by[i][3];
-            Bz[i][2] = (((b1[i][0] * z4 + b1[i][1] * z3) + b1[i][2] * z2) + b1[i][3] * z) + b1[i][4];
-        }
-        // null vector of the rank-2 matrix: the largest cross product of two rows
-        double v[3] = {0, 0, 0}, vn = -1.0;
-        const int pa[3] = {0, 0, 1}, pb[3] = {1, 2, 2};
-        for (int c = 0; c < 3; c++) {
-            const double* r0 = Bz[pa[c]];
-            const double* r1 = Bz[pb[c]];
-            const double cx = r0[1] * r1[2] - r0[2] * r1[1], cy = r0[2] * r1[0] - r0[0] * r1[2],
-                         cz = r0[0] * r1[1] - r0[1] * r1[0];
-            const double nn = (cx * cx + cy * cy) + cz * cz;
-            if (nn > vn) { vn = nn; v[0] = cx; v[1] = cy; v[2] = cz; }
-        }
-        if (fabs(v[2]) < 1e-10 * sqrt(vn)) continue;
-        const double x = v[0] / v[2], y = v[1] / v[2];
-        double e[9], nn = 0.0;
-        for (int t = 0; t < 9; t++) {
-            e[t] = ((x * B4[0][t] + y * B4[1][t]) + z * B4[2][t]) + B4[3][t];
-            nn += e[t] * e[t];
-        }
-        nn = sqrt(nn);
-        for (int t = 0; t < 9; t++) models[count * 9 + t] = e[t] / nn;
-        count++;
-    }
-    return count;
-}
 
 // EMEstimatorCallback::computeError for one correspondence; Matx products accumulate left to right (no FMA)
 __device__ __forceinline__ bool sampson_inlier(const double* E, double ax, double ay, double bx, double by, float thr2) {
@@ -298,12 +58,26 @@ __device__ int update_num_iters(double p, double ep, int model_points, int max_i
     return (denom >= 0 || -num >= max_iters * (-denom)) ? max_iters : __double2int_rn(num / denom);
 }
 
-__global__ void __launch_bounds__(WAVE) essential_ransac_kernel(EssentialJob job) {
-    extern __shared__ __align__(16) unsigned char esm[];
-    double* models = reinterpret_cast<double*>(esm);                 // [WAVE][MAXM][9]
-    int* nmod = reinterpret_cast<int*>(models + WAVE * MAXM * 9);   // [WAVE]
-    int* counts = nmod + WAVE;                                      // [WAVE][MAXM]
-    int* sidx = counts + WAVE * MAXM;                               // [WAVE][5]
+// getSubset for `count` samples: 5 distinct indices each, redraw on duplicates
+__device__ void draw_subsets(CvRng& rng, int n, int count, int* sidx) {
+    for (int s = 0; s < count; s++) {
+        int* id = sidx + s * 5;
+        for (int i = 0; i < 5;) {
+            const int v = (int)(rng.next() % (unsigned)n);
+            int j = 0;
+            for (; j < i; j++)
+                if (id[j] == v) break;
+            if (j < i) continue;
+            id[i++] = v;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(RT, 2) essential_ransac_kernel(EssentialJob job) {
+    __shared__ int nmod[WAVE];             // models per sample
+    __shared__ int counts[WAVE * MAXM];    // inliers per hypothesis
+    __shared__ int sidx[2 * WAVE * 5];     // subsets, double buffered
+    double* models = job.models + (size_t)blockIdx.x * WAVE * MAXM * 9;  // [WAVE][MAXM][9] in HBM/L2
     __shared__ double bestE[9];
     __shared__ int sh_best, sh_niters, sh_done, sh_it;
     __shared__ CvRng rng;
@@ -319,36 +93,31 @@ __global__ void __launch_bounds__(WAVE) essential_ransac_kernel(EssentialJob job
         sh_it = 0;
         rng.s = 0xFFFFFFFFFFFFFFFFULL;
         for (int t = 0; t < 9; t++) bestE[t] = 0.0;
+        if (!sh_done) draw_subsets(rng, n, WAVE0, sidx);
     }
     __syncthreads();
+    int sched = WAVE0, buf = 0;
     while (!sh_done) {
         const int it0 = sh_it;
-        const int wave = min(WAVE, sh_niters - it0);
-        if (tid == 0) {  // getSubset: 5 distinct indices per sample, redraw on duplicates
-            for (int s = 0; s < wave; s++) {
-                int* id = sidx + s * 5;
-                for (int i = 0; i < 5;) {
-                    const int v = (int)(rng.next() % (unsigned)n);
-                    int j = 0;
-                    for (; j < i; j++)
-                        if (id[j] == v) break;
-                    if (j < i) continue;
-                    id[i++] = v;
-                }
-            }
-        }
-        __syncthreads();
+        const int wave = min(sched, sh_niters - it0);
+        const int next_sched = min(2 * sched, WAVE);
+        const int* cur = sidx + buf * WAVE * 5;
         if (tid < wave) {
             double a[5][2], b[5][2];
             for (int i = 0; i < 5; i++) {
-                const double2 p = x1[sidx[tid * 5 + i]], q = x2[sidx[tid * 5 + i]];
+                const double2 p = x1[cur[tid * 5 + i]], q = x2[cur[tid * 5 + i]];
                 a[i][0] = p.x; a[i][1] = p.y; b[i][0] = q.x; b[i][1] = q.y;
             }
             nmod[tid] = five_point(a, b, models + (size_t)tid * MAXM * 9);
         }
+        if (tid == RT - 1) {  // the last thread solves only in full waves; it draws the next wave's subsets afterwards
+            CvRng r = rng;
+            draw_subsets(r, n, next_sched, sidx + (buf ^ 1) * WAVE * 5);
+            rng = r;
+        }
         __syncthreads();
         // score: one warp per hypothesis
-        for (int h = warp; h < wave * MAXM; h += WAVE / 32) {
+        for (int h = warp; h < wave * MAXM; h += RT / 32) {
             const int s = h / MAXM, k = h - s * MAXM;
             if (k >= nmod[s]) continue;
             const double* E = models + (size_t)h * 9;
@@ -382,6 +151,8 @@ __global__ void __launch_bounds__(WAVE) essential_ransac_kernel(EssentialJob job
             sh_it = it;
             sh_done = it >= niters ? 1 : 0;
         }
+        sched = next_sched;
+        buf ^= 1;
         __syncthreads();
     }
     // outputs: E (row-major, zeros if no model was accepted), inlier count, mask
@@ -392,7 +163,7 @@ __global__ void __launch_bounds__(WAVE) essential_ransac_kernel(EssentialJob job
         job.n_iters[pair] = sh_it;
     }
     const bool have = sh_best > 0;
-    for (int i = tid; i < n; i += WAVE) {
+    for (int i = tid; i < n; i += RT) {
         bool in = false;
         if (have) {
             const double2 p = x1[i], q = x2[i];
@@ -439,13 +210,11 @@ __global__ void fivept_probe_kernel(const double* x1, const double* x2, int n_sa
     counts[s] = five_point(a, b, models + (size_t)s * MAXM * 9);
 }
 
-size_t essential_smem_bytes() { return (size_t)WAVE * MAXM * 9 * 8 + (size_t)WAVE * 4 + (size_t)WAVE * MAXM * 4 + (size_t)WAVE * 5 * 4; }
 
 }  // namespace
 
-void init_essential_attributes() {
-    cudaFuncSetAttribute(essential_ransac_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)essential_smem_bytes());
-}
+void init_essential_attributes() {}
+size_t essential_model_scratch_doubles() { return (size_t)WAVE * MAXM * 9; }
 
 int launch_essential_gather(const SeqView& s, int first, int n_pairs, const EssentialJob& job, const double* K4, cudaStream_t st) {
     SLAM_KERNEL("essential_gather", st,
@@ -459,7 +228,7 @@ int launch_essential_normalise(const float* p1, const float* p2, int n, const Es
 }
 
 int launch_essential_ransac(const EssentialJob& job, int n_pairs, cudaStream_t st) {
-    SLAM_KERNEL("essential_ransac", st, essential_ransac_kernel<<<n_pairs, WAVE, essential_smem_bytes(), st>>>(job));
+    SLAM_KERNEL("essential_ransac", st, essential_ransac_kernel<<<n_pairs, RT, 0, st>>>(job));
     return 1;
 }
 

@@ -107,3 +107,20 @@ extern "C" void hx_model_sort_keys_desc(uint32_t* a, int n) {
         }
     }
 }
+
+// ---- host build of the five-point solver (slam_cin0051_b200/csrc/fivept.cuh) ------------------------------------------
+#include "../../slam_cin0051_b200/csrc/fivept.cuh"
+extern "C" int hx_real_roots(const double* coeffs_high_first, int n_coeffs, double* out) {
+    return slamcu::real_roots(coeffs_high_first, n_coeffs, out);
+}
+// x1, x2: [n_samples][5][2]; models: [n_samples][10][9]; counts: [n_samples]
+extern "C" void hx_five_point(const double* x1, const double* x2, int n_samples, double* models, int* counts) {
+    for (int s = 0; s < n_samples; s++) {
+        double a[5][2], b[5][2];
+        for (int i = 0; i < 5; i++) {
+            a[i][0] = x1[(s * 5 + i) * 2]; a[i][1] = x1[(s * 5 + i) * 2 + 1];
+            b[i][0] = x2[(s * 5 + i) * 2]; b[i][1] = x2[(s * 5 + i) * 2 + 1];
+        }
+        counts[s] = slamcu::five_point(a, b, models + (size_t)s * 90);
+    }
+}

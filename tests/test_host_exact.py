@@ -15,8 +15,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 def hx():
     so = os.path.join(HERE, "native", "libhost_exact.so")
     src = os.path.join(HERE, "native", "host_exact.cpp")
-    hdr = os.path.join(HERE, "..", "slam_cin0051_b200", "csrc", "exact.cuh")
-    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+    hdrs = [os.path.join(HERE, "..", "slam_cin0051_b200", "csrc", h) for h in ("exact.cuh", "fivept.cuh")]
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(p) for p in [src, *hdrs]):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", so, src])
     L = C.CDLL(so)
     L.hx_check_atanf_bits.restype = C.c_longlong
