@@ -161,6 +161,8 @@ struct slamcu_sequence {
     EssentialJob ess{};                       // per-pair two-view RANSAC working set (lazy)
     bool has_ess = false;
     std::vector<void*> ess_owned;
+    void* ess_work = nullptr;                 // per-launch RANSAC working set (essential_work_bytes_per_pair)
+    size_t ess_work_bytes = 0;
     std::vector<void*> owned;
     // ORB-mode working set, allocated on first use and keyed by the detector parameters
     bool has_orb = false;
@@ -419,6 +421,7 @@ void slamcu_sequence_destroy(slamcu_sequence* s) {
     if (s->prep_stage) cudaFree(s->prep_stage);
     if (s->undist_map) cudaFree(s->undist_map);
     for (void* p : s->ess_owned) cudaFree(p);
+    if (s->ess_work) cudaFree(s->ess_work);
     if (s->h_counts) cudaFreeHost(s->h_counts);
     delete s;
 }
@@ -1539,13 +1542,13 @@ int slamcu_find_essential(slamcu_context* ctx, const float* p1, const float* p2,
     CU(ctx, cudaSetDevice(ctx->device));
     const size_t b_pts = ((size_t)n * 16 + 255) / 256 * 256, b_in = ((size_t)n * 8 + 255) / 256 * 256;
     const size_t b_mask = ((size_t)n + 255) / 256 * 256;
-    int rc = ensure_scratch(ctx, 2 * b_pts + 2 * b_in + b_mask + 1024 + essential_model_scratch_doubles() * 8);
+    int rc = ensure_scratch(ctx, 2 * b_pts + 2 * b_in + b_mask + 1024 + essential_work_bytes_per_pair(max_iters));
     if (rc != SLAMCU_OK) return rc;
     uint8_t* base = static_cast<uint8_t*>(ctx->scratch);
     EssentialJob j{};
     j.x1 = reinterpret_cast<double2*>(base);
     j.x2 = reinterpret_cast<double2*>(base + b_pts);
-    j.models = reinterpret_cast<double*>(base + 2 * b_pts + 2 * b_in + b_mask + 1024);
+    j.work = base + 2 * b_pts + 2 * b_in + b_mask + 1024;
     float* d_p1 = reinterpret_cast<float*>(base + 2 * b_pts);
     float* d_p2 = reinterpret_cast<float*>(base + 2 * b_pts + b_in);
     j.mask = base + 2 * b_pts + 2 * b_in;
@@ -1662,12 +1665,21 @@ int slamcu_sequence_essential(slamcu_sequence* s, int first, int n_pairs, const 
         A(&e.n_inliers, F);
         A(&e.n_iters, F);
         A(&e.mask, F * v.cap_kp);
-        A(&e.models, F * essential_model_scratch_doubles());
         if (rc != SLAMCU_OK) return rc;
         e.pt_stride = v.cap_kp;
         s->has_ess = true;
     }
+    const size_t work_bytes = (size_t)n_pairs * essential_work_bytes_per_pair(max_iters);
+    if (work_bytes > s->ess_work_bytes) {  // RANSAC working set of one launch; grows with n_pairs * max_iters
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        if (s->ess_work) cudaFree(s->ess_work);
+        s->ess_work = nullptr;
+        s->ess_work_bytes = 0;
+        CU(ctx, cudaMalloc(&s->ess_work, work_bytes));
+        s->ess_work_bytes = work_bytes;
+    }
     EssentialJob j = s->ess;
+    j.work = static_cast<unsigned char*>(s->ess_work);
     j.x1 += (size_t)first * v.cap_kp;
     j.x2 += (size_t)first * v.cap_kp;
     j.n_pts += first;

@@ -97,13 +97,13 @@ struct EssentialJob {
     double* E;                       // [pairs][9] row-major, |E|_F = 1 (zeros when no model was accepted)
     int* n_inliers; int* n_iters;    // [pairs]
     uint8_t* mask;                   // [pairs][pt_stride]
-    double* models;                  // [pairs in one launch][essential_model_scratch_doubles()] solver output of a wave
+    unsigned char* work;             // [pairs in one launch][essential_work_bytes_per_pair(max_iters)] RANSAC working set
     int pt_stride, max_iters;
     double prob;
     float thr2;                      // (float)(t * t), t = threshold / ((fx + fy) / 2)
 };
 void init_essential_attributes();
-size_t essential_model_scratch_doubles();
+size_t essential_work_bytes_per_pair(int max_iters);
 int launch_essential_gather(const SeqView& s, int first, int n_pairs, const EssentialJob& job, const double* K4, cudaStream_t st);
 int launch_essential_normalise(const float* p1, const float* p2, int n, const EssentialJob& job, const double* K4, cudaStream_t st);
 int launch_essential_ransac(const EssentialJob& job, int n_pairs, cudaStream_t st);

@@ -8,23 +8,27 @@
 // same mathematics (Nister) with its own null-space basis and root finder: candidates agree with OpenCV's to
 // rounding, their order inside one sample may differ (that only matters for exact ties at the maximum).
 //
-// essential_ransac_kernel: one block (RT threads) per frame pair, adaptive like the original loop but in waves that
-// grow 16, 32, 64, 128, 256, 256, ... samples (most pairs finish inside the first wave: niters drops to ~10 after the
-// first good model; a wave costs one solver latency whatever its size, so a pair that needs all 1000 iterations takes 7):
-//   one thread per sample runs the minimal solver while an otherwise idle thread draws the NEXT wave's subsets from
-//   the sequential RNG (drawing past the end of the loop is harmless: nothing consumes the stream afterwards);
-//   one warp per hypothesis scores all correspondences (ballot + popc inlier count); thread 0 replays the
-//   sequential accept / niters rule over the wave; the loop ends as soon as the replay reaches niters.
-// Finally the block writes the winner's inlier mask.
+// Two phases, both with ONE WARP PER SAMPLE running the minimal solver (fivept_warp.cuh):
+//   essential_ransac_kernel   one block per frame pair, adaptive like the original loop in waves of 8, 16, 32 samples:
+//       warps take samples from a shared counter (the last warp first draws the NEXT wave's subsets from the
+//       sequential RNG), one warp per hypothesis scores all correspondences (ballot + popc inlier count), thread 0
+//       replays the sequential accept / niters rule.  Most pairs end here (niters drops to ~10 after the first good
+//       model).  A pair still running after 56 iterations draws the subsets of ALL remaining iterations and stops.
+//   essential_spec_kernel     the whole grid works on the unfinished pairs: one warp solves one remaining sample and
+//       scores its own hypotheses (speculative: iterations past the final niters are simply ignored later).
+//   essential_finish_kernel   per unfinished pair: the sequential replay over the recorded inlier counts picks exactly
+//       the model the original loop would have accepted last; one warp re-solves that sample; mask and E are written.
 #include "common.cuh"
-#include "fivept.cuh"
+#include "fivept_warp.cuh"
 
 namespace slamcu {
 namespace {
 
-constexpr int RT = 256;       // threads per block (scoring warps: RT / 32)
-constexpr int WAVE = RT;      // most samples solved per wave (one thread each)
-constexpr int WAVE0 = 16;     // first wave
+constexpr int RT = 256;       // threads per block
+constexpr int NW = RT / 32;   // warps: one sample / one hypothesis each at a time
+constexpr int WAVE0 = 8;      // first wave of the adaptive phase
+constexpr int WAVE = 32;      // its largest wave
+constexpr int P1_ITERS = 56;  // the adaptive phase hands over to the speculative one after 8 + 16 + 32 iterations
 constexpr int MAXM = kMaxModels;
 
 struct CvRng {
@@ -60,28 +64,100 @@ __device__ int update_num_iters(double p, double ep, int model_points, int max_i
 
 // getSubset for `count` samples: 5 distinct indices each, redraw on duplicates
 __device__ void draw_subsets(CvRng& rng, int n, int count, int* sidx) {
+    const double inv = 1.0 / (double)n;
     for (int s = 0; s < count; s++) {
         int* id = sidx + s * 5;
         for (int i = 0; i < 5;) {
-            const int v = (int)(rng.next() % (unsigned)n);
+            const unsigned x = rng.next();
+            long long v = (long long)x - (long long)__double2uint_rz((double)x * inv) * n;  // x % n (quotient off by <= 1)
+            if (v < 0) v += n;
+            if (v >= n) v -= n;
             int j = 0;
             for (; j < i; j++)
-                if (id[j] == v) break;
+                if (id[j] == (int)v) break;
             if (j < i) continue;
-            id[i++] = v;
+            id[i++] = (int)v;
         }
     }
 }
 
+// per-pair work area: [models of one wave][state][subsets][hypothesis counts][models per sample]
+struct PairWork {
+    double* models;          // [WAVE][MAXM][9]
+    int* state;              // done, it, best, niters
+    unsigned long long* rng; // RNG state after the adaptive phase
+    int* subsets;            // [max_iters][5]   (entries from state.it on)
+    int* cnt;                // [max_iters][MAXM]
+    int* nmod;               // [max_iters]
+};
+__host__ __device__ inline size_t pair_work_bytes(int max_iters) {
+    const size_t mi = (size_t)(max_iters > 0 ? max_iters : 0);
+    return (size_t)WAVE * MAXM * 9 * 8 + 64 + mi * (5 + MAXM + 1) * 4 + 64;
+}
+__device__ inline PairWork pair_work(const EssentialJob& job, int pair) {
+    unsigned char* base = job.work + (size_t)pair * pair_work_bytes(job.max_iters);
+    const size_t mi = (size_t)max(job.max_iters, 0);
+    PairWork w;
+    w.models = reinterpret_cast<double*>(base);
+    base += (size_t)WAVE * MAXM * 9 * 8;
+    w.state = reinterpret_cast<int*>(base);
+    w.rng = reinterpret_cast<unsigned long long*>(base + 32);
+    base += 64;
+    w.subsets = reinterpret_cast<int*>(base);
+    w.cnt = w.subsets + mi * 5;
+    w.nmod = w.cnt + mi * MAXM;
+    return w;
+}
+
+// one warp counts the inliers of one hypothesis
+__device__ __forceinline__ int score_model(const double* E9, const double2* x1, const double2* x2, int n, float thr2, int lane) {
+    double E[9];
+#pragma unroll
+    for (int t = 0; t < 9; t++) E[t] = E9[t];
+    int good = 0;
+    for (int base = 0; base < n; base += 32) {
+        const int i = base + lane;
+        bool in = false;
+        if (i < n) {
+            const double2 p = x1[i], q = x2[i];
+            in = sampson_inlier(E, p.x, p.y, q.x, q.y, thr2);
+        }
+        good += __popc(__ballot_sync(0xffffffffu, in));
+    }
+    return good;
+}
+
+__device__ void write_result(const EssentialJob& job, int pair, const double* bestE, int best, int it, int n, const double2* x1,
+                             const double2* x2) {
+    uint8_t* mask = job.mask + (size_t)pair * job.pt_stride;
+    const int tid = threadIdx.x;
+    if (tid < 9) job.E[(size_t)pair * 9 + tid] = bestE[tid];
+    if (tid == 0) {
+        job.n_inliers[pair] = best;
+        job.n_iters[pair] = it;
+    }
+    const bool have = best > 0;
+    for (int i = tid; i < n; i += blockDim.x) {
+        bool in = false;
+        if (have) {
+            const double2 p = x1[i], q = x2[i];
+            in = sampson_inlier(bestE, p.x, p.y, q.x, q.y, job.thr2);
+        }
+        mask[i] = in ? 1 : 0;
+    }
+}
+
 __global__ void __launch_bounds__(RT, 2) essential_ransac_kernel(EssentialJob job) {
+    extern __shared__ __align__(16) double fp_scratch[];  // [NW][kFiveptScratchDoubles]
     __shared__ int nmod[WAVE];             // models per sample
     __shared__ int counts[WAVE * MAXM];    // inliers per hypothesis
     __shared__ int sidx[2 * WAVE * 5];     // subsets, double buffered
-    double* models = job.models + (size_t)blockIdx.x * WAVE * MAXM * 9;  // [WAVE][MAXM][9] in HBM/L2
     __shared__ double bestE[9];
-    __shared__ int sh_best, sh_niters, sh_done, sh_it;
+    __shared__ int sh_best, sh_niters, sh_done, sh_it, sh_next;
     __shared__ CvRng rng;
     const int pair = blockIdx.x;
+    const PairWork wk = pair_work(job, pair);
+    double* models = wk.models;
     const int n = job.n_pts[pair];
     const double2* x1 = job.x1 + (size_t)pair * job.pt_stride;
     const double2* x2 = job.x2 + (size_t)pair * job.pt_stride;
@@ -91,46 +167,40 @@ __global__ void __launch_bounds__(RT, 2) essential_ransac_kernel(EssentialJob jo
         sh_niters = job.max_iters;
         sh_done = (n < 6 || job.max_iters <= 0) ? 1 : 0;
         sh_it = 0;
+        sh_next = 0;
         rng.s = 0xFFFFFFFFFFFFFFFFULL;
         for (int t = 0; t < 9; t++) bestE[t] = 0.0;
         if (!sh_done) draw_subsets(rng, n, WAVE0, sidx);
     }
     __syncthreads();
     int sched = WAVE0, buf = 0;
-    while (!sh_done) {
+    while (!sh_done && sh_it < P1_ITERS) {
         const int it0 = sh_it;
         const int wave = min(sched, sh_niters - it0);
         const int next_sched = min(2 * sched, WAVE);
         const int* cur = sidx + buf * WAVE * 5;
-        if (tid < wave) {
-            double a[5][2], b[5][2];
-            for (int i = 0; i < 5; i++) {
-                const double2 p = x1[cur[tid * 5 + i]], q = x2[cur[tid * 5 + i]];
-                a[i][0] = p.x; a[i][1] = p.y; b[i][0] = q.x; b[i][1] = q.y;
+        if (warp == NW - 1 && it0 + wave < P1_ITERS) {  // the last warp joins the solve after drawing the next wave's subsets
+            if (lane == 0) {
+                CvRng r = rng;
+                draw_subsets(r, n, next_sched, sidx + (buf ^ 1) * WAVE * 5);
+                rng = r;
             }
-            nmod[tid] = five_point(a, b, models + (size_t)tid * MAXM * 9);
+            __syncwarp();
         }
-        if (tid == RT - 1) {  // the last thread solves only in full waves; it draws the next wave's subsets afterwards
-            CvRng r = rng;
-            draw_subsets(r, n, next_sched, sidx + (buf ^ 1) * WAVE * 5);
-            rng = r;
+        for (;;) {
+            int s = 0;
+            if (lane == 0) s = atomicAdd(&sh_next, 1);
+            s = __shfl_sync(0xffffffffu, s, 0);
+            if (s >= wave) break;
+            const int cnt = five_point_warp(x1, x2, cur + s * 5, fp_scratch + warp * kFiveptScratchDoubles,
+                                            models + (size_t)s * MAXM * 9);
+            if (lane == 0) nmod[s] = cnt;
         }
         __syncthreads();
-        // score: one warp per hypothesis
-        for (int h = warp; h < wave * MAXM; h += RT / 32) {
+        for (int h = warp; h < wave * MAXM; h += NW) {  // score: one warp per hypothesis
             const int s = h / MAXM, k = h - s * MAXM;
             if (k >= nmod[s]) continue;
-            const double* E = models + (size_t)h * 9;
-            int good = 0;
-            for (int base = 0; base < n; base += 32) {
-                const int i = base + lane;
-                bool in = false;
-                if (i < n) {
-                    const double2 p = x1[i], q = x2[i];
-                    in = sampson_inlier(E, p.x, p.y, q.x, q.y, job.thr2);
-                }
-                good += __popc(__ballot_sync(0xffffffffu, in));
-            }
+            const int good = score_model(models + (size_t)h * 9, x1, x2, n, job.thr2, lane);
             if (lane == 0) counts[h] = good;
         }
         __syncthreads();
@@ -150,27 +220,93 @@ __global__ void __launch_bounds__(RT, 2) essential_ransac_kernel(EssentialJob jo
             sh_niters = niters;
             sh_it = it;
             sh_done = it >= niters ? 1 : 0;
+            sh_next = 0;
         }
         sched = next_sched;
         buf ^= 1;
         __syncthreads();
     }
-    // outputs: E (row-major, zeros if no model was accepted), inlier count, mask
-    uint8_t* mask = job.mask + (size_t)pair * job.pt_stride;
+    if (sh_done) {
+        if (tid == 0) wk.state[0] = 1;
+        write_result(job, pair, bestE, sh_best, sh_it, n, x1, x2);
+        return;
+    }
+    // hand over to the speculative phase: state + the subsets of every remaining iteration
     if (tid < 9) job.E[(size_t)pair * 9 + tid] = bestE[tid];
     if (tid == 0) {
-        job.n_inliers[pair] = sh_best;
-        job.n_iters[pair] = sh_it;
+        wk.state[0] = 0;
+        wk.state[1] = sh_it;
+        wk.state[2] = sh_best;
+        wk.state[3] = sh_niters;
+        CvRng r = rng;
+        draw_subsets(r, n, sh_niters - sh_it, wk.subsets + (size_t)sh_it * 5);
+        *wk.rng = r.s;
     }
-    const bool have = sh_best > 0;
-    for (int i = tid; i < n; i += RT) {
-        bool in = false;
-        if (have) {
-            const double2 p = x1[i], q = x2[i];
-            in = sampson_inlier(bestE, p.x, p.y, q.x, q.y, job.thr2);
+}
+
+// grid (ceil(max_iters / NW), pairs): warp -> one remaining sample of an unfinished pair
+__global__ void __launch_bounds__(RT, 2) essential_spec_kernel(EssentialJob job) {
+    extern __shared__ __align__(16) double fp_scratch[];  // [NW][kFiveptScratchDoubles + MAXM * 9]
+    const int pair = blockIdx.y;
+    const PairWork wk = pair_work(job, pair);
+    if (wk.state[0]) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int s = wk.state[1] + blockIdx.x * NW + warp;
+    if (s >= wk.state[3]) return;  // past niters as it stood after the adaptive phase (it can only shrink)
+    const int n = job.n_pts[pair];
+    const double2* x1 = job.x1 + (size_t)pair * job.pt_stride;
+    const double2* x2 = job.x2 + (size_t)pair * job.pt_stride;
+    double* S = fp_scratch + warp * (kFiveptScratchDoubles + MAXM * 9);
+    double* models = S + kFiveptScratchDoubles;
+    const int cnt = five_point_warp(x1, x2, wk.subsets + (size_t)s * 5, S, models);
+    __syncwarp();
+    for (int k = 0; k < cnt; k++) {
+        const int good = score_model(models + k * 9, x1, x2, n, job.thr2, lane);
+        if (lane == 0) wk.cnt[(size_t)s * MAXM + k] = good;
+    }
+    if (lane == 0) wk.nmod[s] = cnt;
+}
+
+__global__ void __launch_bounds__(RT) essential_finish_kernel(EssentialJob job) {
+    __shared__ __align__(16) double fp_scratch[kFiveptScratchDoubles + MAXM * 9];
+    __shared__ double bestE[9];
+    __shared__ int sh_best, sh_it, sh_ws, sh_wk;
+    const int pair = blockIdx.x;
+    const PairWork wk = pair_work(job, pair);
+    if (wk.state[0]) return;
+    const int n = job.n_pts[pair];
+    const double2* x1 = job.x1 + (size_t)pair * job.pt_stride;
+    const double2* x2 = job.x2 + (size_t)pair * job.pt_stride;
+    const int tid = threadIdx.x;
+    if (tid < 9) bestE[tid] = job.E[(size_t)pair * 9 + tid];
+    if (tid == 0) {
+        int it = wk.state[1], best = wk.state[2], niters = wk.state[3], ws = -1, wkk = 0;
+        for (; it < niters; it++) {
+            const int nm = wk.nmod[it];
+            for (int k = 0; k < nm; k++) {
+                const int good = wk.cnt[(size_t)it * MAXM + k];
+                if (good > max(best, 4)) {
+                    best = good;
+                    ws = it;
+                    wkk = k;
+                    niters = update_num_iters(job.prob, (double)(n - good) / n, 5, niters);
+                }
+            }
         }
-        mask[i] = in ? 1 : 0;
+        sh_best = best;
+        sh_it = it;
+        sh_ws = ws;
+        sh_wk = wkk;
     }
+    __syncthreads();
+    if (sh_ws >= 0 && tid < 32) {  // re-solve the winning sample (deterministic: the same models in the same order)
+        double* models = fp_scratch + kFiveptScratchDoubles;
+        five_point_warp(x1, x2, wk.subsets + (size_t)sh_ws * 5, fp_scratch, models);
+        __syncwarp();
+        if (tid < 9) bestE[tid] = models[sh_wk * 9 + tid];
+    }
+    __syncthreads();
+    write_result(job, pair, bestE, sh_best, sh_it, n, x1, x2);
 }
 
 // gather matched keypoint coordinates and normalise by K: x = ((double)px - cx) / fx  (findEssentialMat's preamble)
@@ -199,22 +335,26 @@ __global__ void __launch_bounds__(256) essential_normalise_kernel(const float* p
     job.x2[i] = make_double2(((double)p2[2 * i] - cx) / fx, ((double)p2[2 * i + 1] - cy) / fy);
 }
 
-__global__ void fivept_probe_kernel(const double* x1, const double* x2, int n_samples, double* models, int* counts) {
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+// slamcu_fivept_solve: x1, x2 = [n_samples][5][2] doubles; one warp per sample
+__global__ void __launch_bounds__(128) fivept_probe_kernel(const double* x1, const double* x2, int n_samples, double* models, int* counts) {
+    __shared__ __align__(16) double scratch[4 * kFiveptScratchDoubles];
+    __shared__ int ident[5];
+    if (threadIdx.x < 5) ident[threadIdx.x] = threadIdx.x;
+    __syncthreads();
+    const int s = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (s >= n_samples) return;
-    double a[5][2], b[5][2];
-    for (int i = 0; i < 5; i++) {
-        a[i][0] = x1[(s * 5 + i) * 2]; a[i][1] = x1[(s * 5 + i) * 2 + 1];
-        b[i][0] = x2[(s * 5 + i) * 2]; b[i][1] = x2[(s * 5 + i) * 2 + 1];
-    }
-    counts[s] = five_point(a, b, models + (size_t)s * MAXM * 9);
+    const int cnt = five_point_warp(reinterpret_cast<const double2*>(x1) + (size_t)s * 5, reinterpret_cast<const double2*>(x2) + (size_t)s * 5,
+                                    ident, scratch + (threadIdx.x >> 5) * kFiveptScratchDoubles, models + (size_t)s * MAXM * 9);
+    if ((threadIdx.x & 31) == 0) counts[s] = cnt;
 }
-
 
 }  // namespace
 
-void init_essential_attributes() {}
-size_t essential_model_scratch_doubles() { return (size_t)WAVE * MAXM * 9; }
+void init_essential_attributes() {
+    cudaFuncSetAttribute(essential_ransac_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NW * kFiveptScratchDoubles * 8);
+    cudaFuncSetAttribute(essential_spec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NW * (kFiveptScratchDoubles + MAXM * 9) * 8);
+}
+size_t essential_work_bytes_per_pair(int max_iters) { return pair_work_bytes(max_iters); }
 
 int launch_essential_gather(const SeqView& s, int first, int n_pairs, const EssentialJob& job, const double* K4, cudaStream_t st) {
     SLAM_KERNEL("essential_gather", st,
@@ -228,12 +368,17 @@ int launch_essential_normalise(const float* p1, const float* p2, int n, const Es
 }
 
 int launch_essential_ransac(const EssentialJob& job, int n_pairs, cudaStream_t st) {
-    SLAM_KERNEL("essential_ransac", st, essential_ransac_kernel<<<n_pairs, RT, 0, st>>>(job));
-    return 1;
+    SLAM_KERNEL("essential_ransac", st, essential_ransac_kernel<<<n_pairs, RT, NW * kFiveptScratchDoubles * 8, st>>>(job));
+    if (job.max_iters <= P1_ITERS) return 1;
+    const int spec_blocks = (job.max_iters - P1_ITERS + NW - 1) / NW;  // an unfinished pair has done P1_ITERS iterations
+    SLAM_KERNEL("essential_spec", st,
+                essential_spec_kernel<<<dim3(spec_blocks, n_pairs), RT, NW * (kFiveptScratchDoubles + MAXM * 9) * 8, st>>>(job));
+    SLAM_KERNEL("essential_finish", st, essential_finish_kernel<<<n_pairs, RT, 0, st>>>(job));
+    return 3;
 }
 
 int launch_fivept_probe(const double* x1, const double* x2, int n_samples, double* models, int* counts, cudaStream_t st) {
-    fivept_probe_kernel<<<(n_samples + 31) / 32, 32, 0, st>>>(x1, x2, n_samples, models, counts);
+    fivept_probe_kernel<<<(n_samples + 3) / 4, 128, 0, st>>>(x1, x2, n_samples, models, counts);
     return 1;
 }
 

@@ -49,15 +49,54 @@ def test_fivept_solver_equals_oracle(gpu_ctx):
     rng = np.random.default_rng(2)
     idx = np.stack([rng.choice(len(x1), 5, replace=False) for _ in range(200)])
     got = s.fivept_solve(x1[idx], x2[idx], context=gpu_ctx)
-    total = close = 0
+    total = close = same = 0
     for i in range(len(idx)):
         want = eo.five_point(x1[idx[i]], x2[idx[i]])
-        assert abs(len(got[i]) - len(want)) <= 1
+        # the two solvers use different null-space bases: a sample whose degree-10 polynomial has a tight root cluster
+        # in one basis can lose (or gain) a close pair of real roots in the other
+        assert abs(len(got[i]) - len(want)) <= 2
+        same += len(got[i]) == len(want)
         for M in got[i]:
             total += 1
             close += min((e_diff(M, W) for W in want), default=9.0) < 1e-8
             assert abs(np.sqrt((M * M).sum()) - 1.0) < 1e-12
-    assert total > 400 and close >= 0.99 * total
+    assert total > 400 and close >= 0.99 * total and same >= 0.98 * len(idx)
+
+
+def test_fivept_warp_solver_equals_host_build_of_the_thread_solver(gpu_ctx):
+    """The warp-cooperative solver (fivept_warp.cuh) against the g++ build of fivept.cuh (tests/native/host_exact.cpp)
+    on samples of every golden case: same model counts, models within 1e-8 except for ill-conditioned samples."""
+    import ctypes as C
+    import subprocess
+    import slam_cin0051_b200 as s
+    from oracle import essential_oracle as eo
+    here = os.path.dirname(os.path.abspath(__file__))
+    so = os.path.join(here, "native", "libhost_exact.so")
+    if not os.path.exists(so):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", so, os.path.join(here, "native", "host_exact.cpp")])
+    hx = C.CDLL(so)
+    total = close = samples = same_count = 0
+    for gi, path in enumerate(GOLD):
+        g = np.load(path)
+        x1, x2 = eo.normalise(g["p1"], k4(g["K"])), eo.normalise(g["p2"], k4(g["K"]))
+        rng = np.random.default_rng(100 + gi)
+        S = 300
+        idx = np.stack([rng.choice(len(x1), 5, replace=False) for _ in range(S)])
+        a, b = np.ascontiguousarray(x1[idx]), np.ascontiguousarray(x2[idx])
+        want = np.zeros((S, 10, 9))
+        wcnt = np.zeros(S, np.int32)
+        hx.hx_five_point(a.ctypes.data, b.ctypes.data, S, want.ctypes.data, wcnt.ctypes.data)
+        got = s.fivept_solve(a, b, context=gpu_ctx)
+        for i in range(S):
+            samples += 1
+            same_count += len(got[i]) == wcnt[i]
+            assert abs(len(got[i]) - wcnt[i]) <= 2
+            for M in got[i]:
+                total += 1
+                close += min((e_diff(M, want[i, k].reshape(3, 3)) for k in range(wcnt[i])), default=9.0) < 1e-8
+                assert abs(np.sqrt((M * M).sum()) - 1.0) < 1e-12
+                assert max(abs(np.array([*x2[j], 1.0]) @ M @ np.array([*x1[j], 1.0])) for j in idx[i]) < 1e-11
+    assert total > 6000 and close >= 0.97 * total and same_count >= 0.99 * samples
 
 
 @pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p)[10:-4] for p in GOLD])
