@@ -1539,6 +1539,7 @@ int slamcu_find_essential(slamcu_context* ctx, const float* p1, const float* p2,
     if (!ctx) return SLAMCU_INVALID_ARGUMENT;
     if (!p1 || !p2 || !K4 || !E9 || n < 0) return fail(ctx, SLAMCU_INVALID_ARGUMENT, "bad arguments");
     if (n < 6) return fail(ctx, SLAMCU_EMPTY_INPUT, "findEssentialMat needs more than 5 correspondences (got %d)", n);
+    if (max_iters > kEssentialMaxIters) return fail(ctx, SLAMCU_INVALID_ARGUMENT, "maxIters above %d is not supported", kEssentialMaxIters);
     CU(ctx, cudaSetDevice(ctx->device));
     const size_t b_pts = ((size_t)n * 16 + 255) / 256 * 256, b_in = ((size_t)n * 8 + 255) / 256 * 256;
     const size_t b_mask = ((size_t)n + 255) / 256 * 256;
@@ -1649,6 +1650,7 @@ int slamcu_sequence_essential(slamcu_sequence* s, int first, int n_pairs, const 
     slamcu_context* ctx = s->ctx;
     if (first < 0 || n_pairs < 0 || first + n_pairs + 1 > s->max_frames) return fail(ctx, SLAMCU_INVALID_ARGUMENT, "bad pair range");
     if (n_pairs == 0) return SLAMCU_OK;
+    if (max_iters > kEssentialMaxIters) return fail(ctx, SLAMCU_INVALID_ARGUMENT, "maxIters above %d is not supported", kEssentialMaxIters);
     CU(ctx, cudaSetDevice(ctx->device));
     const SeqView& v = s->v;
     if (!s->has_ess) {

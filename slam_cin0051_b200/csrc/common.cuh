@@ -102,6 +102,7 @@ struct EssentialJob {
     double prob;
     float thr2;                      // (float)(t * t), t = threshold / ((fx + fy) / 2)
 };
+constexpr int kEssentialMaxIters = 50000;  // largest maxIters accepted (the replay keeps one word per iteration in smem)
 void init_essential_attributes();
 size_t essential_work_bytes_per_pair(int max_iters);
 int launch_essential_gather(const SeqView& s, int first, int n_pairs, const EssentialJob& job, const double* K4, cudaStream_t st);

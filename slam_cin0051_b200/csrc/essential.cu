@@ -238,10 +238,56 @@ __global__ void __launch_bounds__(RT, 2) essential_ransac_kernel(EssentialJob jo
         wk.state[1] = sh_it;
         wk.state[2] = sh_best;
         wk.state[3] = sh_niters;
-        CvRng r = rng;
-        draw_subsets(r, n, sh_niters - sh_it, wk.subsets + (size_t)sh_it * 5);
-        *wk.rng = r.s;
     }
+    // getSubset for every remaining iteration.  Only the generator itself is sequential (~10 cycles per output), so
+    // thread 0 fills a chunk of raw outputs, the block reduces them modulo n in parallel, and thread 0 strings the
+    // values into 5-subsets (redraw on duplicates).  Outputs generated past the last subset are never consumed.
+    unsigned* raw = reinterpret_cast<unsigned*>(fp_scratch);
+    constexpr int CHUNK = NW * kFiveptScratchDoubles * 2;  // 32-bit words in the solver scratch
+    __shared__ int sh_s, sh_i, sh_id[5];
+    if (tid == 0) { sh_s = sh_it; sh_i = 0; }
+    __syncthreads();
+    const double inv = 1.0 / (double)n;
+    while (sh_s < sh_niters) {
+        const int want = min(CHUNK, (sh_niters - sh_s) * 5 + 64);
+        if (tid == 0) {
+            CvRng r = rng;
+            for (int t = 0; t < want; t++) raw[t] = r.next();
+            rng = r;
+        }
+        __syncthreads();
+        for (int t = tid; t < want; t += RT) {
+            const unsigned x = raw[t];
+            long long v = (long long)x - (long long)__double2uint_rz((double)x * inv) * n;  // x % n (quotient off by <= 1)
+            if (v < 0) v += n;
+            if (v >= n) v -= n;
+            raw[t] = (unsigned)v;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int s = sh_s, i = sh_i, id[5];
+            for (int t = 0; t < 5; t++) id[t] = sh_id[t];
+            const int last = sh_niters;
+            for (int t = 0; t < want && s < last; t++) {
+                const int v = (int)raw[t];
+                bool dup = false;
+                for (int j = 0; j < 5; j++) dup |= j < i && id[j] == v;
+                if (dup) continue;
+                id[i++] = v;
+                if (i == 5) {
+                    int* out = wk.subsets + (size_t)s * 5;
+                    for (int j = 0; j < 5; j++) out[j] = id[j];
+                    s++;
+                    i = 0;
+                }
+            }
+            sh_s = s;
+            sh_i = i;
+            for (int t = 0; t < 5; t++) sh_id[t] = id[t];
+        }
+        __syncthreads();
+    }
+    if (tid == 0) *wk.rng = rng.s;
 }
 
 // grid (ceil(max_iters / NW), pairs): warp -> one remaining sample of an unfinished pair
@@ -268,7 +314,9 @@ __global__ void __launch_bounds__(RT, 2) essential_spec_kernel(EssentialJob job)
 }
 
 __global__ void __launch_bounds__(RT) essential_finish_kernel(EssentialJob job) {
-    __shared__ __align__(16) double fp_scratch[kFiveptScratchDoubles + MAXM * 9];
+    extern __shared__ __align__(16) unsigned char fin_smem[];
+    double* fp_scratch = reinterpret_cast<double*>(fin_smem);                          // [kFiveptScratchDoubles + MAXM * 9]
+    int* mx = reinterpret_cast<int*>(fp_scratch + kFiveptScratchDoubles + MAXM * 9);   // [niters - it0] best count of the iteration
     __shared__ double bestE[9];
     __shared__ int sh_best, sh_it, sh_ws, sh_wk;
     const int pair = blockIdx.x;
@@ -278,19 +326,29 @@ __global__ void __launch_bounds__(RT) essential_finish_kernel(EssentialJob job) 
     const double2* x1 = job.x1 + (size_t)pair * job.pt_stride;
     const double2* x2 = job.x2 + (size_t)pair * job.pt_stride;
     const int tid = threadIdx.x;
+    const int it0 = wk.state[1], niters0 = wk.state[3];
     if (tid < 9) bestE[tid] = job.E[(size_t)pair * 9 + tid];
+    // within one iteration the strictly-greater accept rule ends at the first hypothesis with the largest count, and
+    // RANSACUpdateNumIters is monotone in the count, so the replay only needs (max count, its first index) per iteration
+    for (int i = it0 + tid; i < niters0; i += RT) {
+        const int nm = wk.nmod[i];
+        int best = -1, bk = 0;
+        for (int k = 0; k < nm; k++) {
+            const int good = wk.cnt[(size_t)i * MAXM + k];
+            if (good > best) { best = good; bk = k; }
+        }
+        mx[i - it0] = (best << 4) | bk;
+    }
+    __syncthreads();
     if (tid == 0) {
-        int it = wk.state[1], best = wk.state[2], niters = wk.state[3], ws = -1, wkk = 0;
+        int it = it0, best = wk.state[2], niters = niters0, ws = -1, wkk = 0;
         for (; it < niters; it++) {
-            const int nm = wk.nmod[it];
-            for (int k = 0; k < nm; k++) {
-                const int good = wk.cnt[(size_t)it * MAXM + k];
-                if (good > max(best, 4)) {
-                    best = good;
-                    ws = it;
-                    wkk = k;
-                    niters = update_num_iters(job.prob, (double)(n - good) / n, 5, niters);
-                }
+            const int v = mx[it - it0], good = v >> 4;
+            if (good > max(best, 4)) {
+                best = good;
+                ws = it;
+                wkk = v & 15;
+                niters = update_num_iters(job.prob, (double)(n - good) / n, 5, niters);
             }
         }
         sh_best = best;
@@ -353,6 +411,8 @@ __global__ void __launch_bounds__(128) fivept_probe_kernel(const double* x1, con
 void init_essential_attributes() {
     cudaFuncSetAttribute(essential_ransac_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NW * kFiveptScratchDoubles * 8);
     cudaFuncSetAttribute(essential_spec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NW * (kFiveptScratchDoubles + MAXM * 9) * 8);
+    cudaFuncSetAttribute(essential_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (kFiveptScratchDoubles + MAXM * 9) * 8 + kEssentialMaxIters * 4);
 }
 size_t essential_work_bytes_per_pair(int max_iters) { return pair_work_bytes(max_iters); }
 
@@ -373,7 +433,8 @@ int launch_essential_ransac(const EssentialJob& job, int n_pairs, cudaStream_t s
     const int spec_blocks = (job.max_iters - P1_ITERS + NW - 1) / NW;  // an unfinished pair has done P1_ITERS iterations
     SLAM_KERNEL("essential_spec", st,
                 essential_spec_kernel<<<dim3(spec_blocks, n_pairs), RT, NW * (kFiveptScratchDoubles + MAXM * 9) * 8, st>>>(job));
-    SLAM_KERNEL("essential_finish", st, essential_finish_kernel<<<n_pairs, RT, 0, st>>>(job));
+    const size_t fin_smem = (size_t)(kFiveptScratchDoubles + MAXM * 9) * 8 + (size_t)job.max_iters * 4;
+    SLAM_KERNEL("essential_finish", st, essential_finish_kernel<<<n_pairs, RT, fin_smem, st>>>(job));
     return 3;
 }
 
