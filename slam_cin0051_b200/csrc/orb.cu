@@ -34,7 +34,7 @@ __device__ __forceinline__ uint8_t* blur_ptr(const SeqView& s, const OrbView& o,
 // ---- B1 ------------------------------------------------------------------------------------------
 // INTER_LINEAR_EXACT: out = ((256-ay) * ((256-ax) s00 + ax s01) + ay * ((256-ax) s10 + ax s11) + 32768) >> 16,
 // written as a + w (b - a) on 8.8 / 16.16 integers (identical values: everything is exact in int32).
-__global__ void __launch_bounds__(256) pyr_down_kernel(SeqView s, OrbView o, int first, int l) {
+__global__ void __launch_bounds__(256) pyr_down_gather_kernel(SeqView s, OrbView o, int first, int l) {
     const int f = first + blockIdx.z;
     const OrbLevel& d = o.lv[l];
     const OrbLevel& p = o.lv[l - 1];
@@ -72,6 +72,83 @@ __global__ void __launch_bounds__(256) pyr_down_kernel(SeqView s, OrbView o, int
         }
     }
     *reinterpret_cast<uint32_t*>(dst + (size_t)y * d.pitch + x) = packed;
+}
+
+
+// The same arithmetic with the source staged through shared memory: one block produces a 128 x 64 tile of level l from
+// the (128 s + 2) x (64 s + 2) source window of level l-1, loaded once with aligned 128-bit loads.  A thread walks
+// 4 columns down 8 output rows and keeps the horizontally interpolated source row it shares with the next output row
+// (consecutive output rows are 1.2 source rows apart, so most rows cost one new source row, not two).
+constexpr int PT_W = 128, PT_H = 64;        // output tile
+constexpr int PS_PITCH = 192, PS_ROWS = 84;  // source window held in shared memory (bytes per row, rows)
+__global__ void __launch_bounds__(256) pyr_down_kernel(SeqView s, OrbView o, int first, int l) {
+    __shared__ __align__(16) uint8_t tile[PS_ROWS * PS_PITCH];
+    const int f = first + blockIdx.z;
+    const OrbLevel& d = o.lv[l];
+    const OrbLevel& p = o.lv[l - 1];
+    const int x0 = blockIdx.x * PT_W, y0 = blockIdx.y * PT_H;
+    const int rows_here = min(PT_H, d.rows - y0);
+    const uint8_t* src = level_ptr(s, o, f, l - 1);
+    uint8_t* dst = level_ptr_w(s, o, f, l);
+    const int x = x0 + (threadIdx.x & 31) * 4;
+    const int yw = y0 + (threadIdx.x >> 5) * 8;  // first of this thread's 8 output rows
+    if (x0 >= d.cols) {  // a block in the row padding: zeros, like the gather kernel writes them
+        if (x < d.pitch)
+            for (int r = 0; r < 8 && yw + r < d.rows; r++) *reinterpret_cast<uint32_t*>(dst + (size_t)(yw + r) * d.pitch + x) = 0u;
+        return;
+    }
+    const int sy_lo = (int)(__ldg(d.yt + y0) >> 8);
+    const int sy_hi = min((int)(__ldg(d.yt + y0 + rows_here - 1) >> 8) + 1, p.rows - 1);
+    const int sx_lo = (int)(__ldg(d.xt + x0) >> 8) & ~15;
+    const int sx_hi = min((int)(__ldg(d.xt + min(x0 + PT_W, d.cols) - 1) >> 8) + 1, p.cols - 1);
+    const int nrows = sy_hi - sy_lo + 1, nvec = (sx_hi - sx_lo) / 16 + 1;  // host guarantees nrows <= PS_ROWS, nvec * 16 <= PS_PITCH
+    for (int i = threadIdx.x; i < nrows * nvec; i += 256) {
+        const int r = i / nvec, c = i - r * nvec;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (sx_lo + c * 16 < p.pitch) v = __ldg(reinterpret_cast<const uint4*>(src + (size_t)(sy_lo + r) * p.pitch + sx_lo + c * 16));
+        *reinterpret_cast<uint4*>(tile + r * PS_PITCH + c * 16) = v;
+    }
+    __syncthreads();
+    if (x >= d.pitch || yw >= d.rows) return;
+    int oa[4], ob[4], ax[4];
+    int nvalid = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const bool ok = x + k < d.cols;
+        const uint32_t t = ok ? __ldg(d.xt + x + k) : 0u;
+        const int sx0 = ok ? (int)(t >> 8) : sx_lo;
+        oa[k] = sx0 - sx_lo;
+        ob[k] = min(sx0 + 1, p.cols - 1) - sx_lo;
+        ax[k] = (int)(t & 255u);
+        nvalid += ok;
+    }
+    int hrow = -1;  // source row whose horizontal interpolation is cached in hc
+    int hc[4] = {0, 0, 0, 0};
+    for (int r = 0; r < 8 && yw + r < d.rows; r++) {
+        const uint32_t ty = __ldg(d.yt + yw + r);
+        const int sy0 = (int)(ty >> 8), ay = (int)(ty & 255u), sy1 = min(sy0 + 1, p.rows - 1);
+        int h0[4], h1[4];
+        const uint8_t* r0 = tile + (sy0 - sy_lo) * PS_PITCH;
+        const uint8_t* r1 = tile + (sy1 - sy_lo) * PS_PITCH;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (sy0 == hrow) h0[k] = hc[k];
+            else {
+                const int a = r0[oa[k]], b = r0[ob[k]];
+                h0[k] = (a << 8) + ax[k] * (b - a);
+            }
+            const int a = r1[oa[k]], b = r1[ob[k]];
+            h1[k] = (a << 8) + ax[k] * (b - a);
+        }
+        uint32_t packed = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (k < nvalid) packed |= (uint32_t)(((h0[k] << 8) + ay * (h1[k] - h0[k]) + 32768) >> 16) << (8 * k);
+            hc[k] = h1[k];
+        }
+        hrow = sy1;
+        *reinterpret_cast<uint32_t*>(dst + (size_t)(yw + r) * d.pitch + x) = packed;
+    }
 }
 
 // ---- B2 ------------------------------------------------------------------------------------------
@@ -839,8 +916,16 @@ int launch_orb_extract(const SeqView& s, const OrbView& o, int first, int n, cud
         max_capc = max(max_capc, o.lv[l].capc);
     }
     for (int l = 1; l < o.nlevels; l++) {
-        dim3 grid((o.lv[l].pitch + 127) / 128, (o.lv[l].rows + 7) / 8, n);
-        SLAM_KERNEL("pyr_down", st, pyr_down_kernel<<<grid, 256, 0, st>>>(s, o, first, l));
+        // source window of one output tile: (tile * step + 2) pixels, + 15 for the 16-byte alignment of its left edge
+        const double sx = (double)o.lv[l - 1].cols / o.lv[l].cols, sy = (double)o.lv[l - 1].rows / o.lv[l].rows;
+        const bool fits = PT_W * sx + 3 + 15 + 16 <= PS_PITCH && PT_H * sy + 4 <= PS_ROWS;
+        if (fits) {
+            dim3 grid((o.lv[l].pitch + PT_W - 1) / PT_W, (o.lv[l].rows + PT_H - 1) / PT_H, n);
+            SLAM_KERNEL("pyr_down", st, pyr_down_kernel<<<grid, 256, 0, st>>>(s, o, first, l));
+        } else {  // steep scale factors: per-pixel gather
+            dim3 grid((o.lv[l].pitch + 127) / 128, (o.lv[l].rows + 7) / 8, n);
+            SLAM_KERNEL("pyr_down", st, pyr_down_gather_kernel<<<grid, 256, 0, st>>>(s, o, first, l));
+        }
         launches++;
     }
     // The blurred levels depend only on the pyramid: they run on the auxiliary stream next to the corner chain
