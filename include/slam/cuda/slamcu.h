@@ -264,7 +264,8 @@ int slamcu_fivept_solve(slamcu_context* ctx, const double* x1, const double* x2,
                         int32_t* counts);
 /* Batched: findEssentialMat on the matches of pairs (f, f+1), f in [first, first + n_pairs), of a sequence
  * (keypoints of match.queryIdx / match.trainIdx, as PoseEstimator::estimate gathers them, pose_estimator.cpp:30-35).
- * One thread block per pair; asynchronous. */
+ * Adaptive waves in one thread block per pair (one warp per 5-point sample); pairs that need more than 56 iterations are
+ * finished speculatively by the whole grid and replayed exactly.  max_iters <= 50000.  Asynchronous. */
 int slamcu_sequence_essential(slamcu_sequence* seq, int first, int n_pairs, const double* K4, double prob,
                               double threshold, int max_iters);
 /* Result of one pair: E9, inlier count, RANSAC iterations run, inlier mask over the pair's matches; synchronises. */

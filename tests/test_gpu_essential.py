@@ -109,6 +109,36 @@ def test_find_essential_equals_cv2_golden(gpu_ctx, path):
     assert e_diff(E, g["E"]) < E_TOL
 
 
+@pytest.mark.parametrize("max_iters", [1, 8, 9, 30, 56, 57, 64, 200, 1000])
+def test_find_essential_iteration_limits_equal_oracle(gpu_ctx, max_iters):
+    """maxIters on both sides of the hand-over between the adaptive per-pair phase (56 iterations) and the speculative
+    grid-wide phase, on the low-inlier case that keeps RANSAC running: masks and counts equal the oracle loop driven by
+    the g++ build of the same solver."""
+    import ctypes as C
+    import subprocess
+    import slam_cin0051_b200 as s
+    from oracle import essential_oracle as eo
+    here = os.path.dirname(os.path.abspath(__file__))
+    so = os.path.join(here, "native", "libhost_exact.so")
+    if not os.path.exists(so):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", so, os.path.join(here, "native", "host_exact.cpp")])
+    hx = C.CDLL(so)
+
+    def solver(a, b):
+        a = np.ascontiguousarray(a, np.float64).reshape(1, 5, 2)
+        b = np.ascontiguousarray(b, np.float64).reshape(1, 5, 2)
+        models = np.zeros((1, 10, 9))
+        counts = np.zeros(1, np.int32)
+        hx.hx_five_point(a.ctypes.data, b.ctypes.data, 1, models.ctypes.data, counts.ctypes.data)
+        return [models[0, k].reshape(3, 3).copy() for k in range(counts[0])]
+
+    g = np.load([p for p in GOLD if p.endswith("essential_syn60.npz")][0])
+    E, mask, good = s.find_essential(g["p1"], g["p2"], k4(g["K"]), max_iters=max_iters, context=gpu_ctx)
+    wE, wmask, wgood = eo.find_essential(g["p1"], g["p2"], k4(g["K"]), max_iters=max_iters, solver=solver)
+    assert good == wgood and np.array_equal(mask, wmask)
+    assert (E is None and wE is None) or e_diff(E, wE) < 1e-8
+
+
 def test_find_essential_edge_cases(gpu_ctx):
     import slam_cin0051_b200 as s
     g = np.load(GOLD[0])
