@@ -122,32 +122,38 @@ __global__ void __launch_bounds__(256) pyr_down_kernel(SeqView s, OrbView o, int
         ax[k] = (int)(t & 255u);
         nvalid += ok;
     }
+    uint32_t tys[8];  // the 8 row-table entries up front: independent loads instead of one dependent load per row
+#pragma unroll
+    for (int r = 0; r < 8; r++) tys[r] = __ldg(d.yt + min(yw + r, d.rows - 1));
+    const int prows1 = p.rows - 1, dpitch = d.pitch, nrow = min(8, d.rows - yw);
+    uint8_t* out = dst + (size_t)yw * dpitch + x;
     int hrow = -1;  // source row whose horizontal interpolation is cached in hc
     int hc[4] = {0, 0, 0, 0};
-    for (int r = 0; r < 8 && yw + r < d.rows; r++) {
-        const uint32_t ty = __ldg(d.yt + yw + r);
-        const int sy0 = (int)(ty >> 8), ay = (int)(ty & 255u), sy1 = min(sy0 + 1, p.rows - 1);
-        int h0[4], h1[4];
-        const uint8_t* r0 = tile + (sy0 - sy_lo) * PS_PITCH;
-        const uint8_t* r1 = tile + (sy1 - sy_lo) * PS_PITCH;
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            if (sy0 == hrow) h0[k] = hc[k];
-            else {
+    for (int r = 0; r < 8; r++) {
+        if (r >= nrow) break;
+        const int sy0 = (int)(tys[r] >> 8), ay = (int)(tys[r] & 255u), sy1 = min(sy0 + 1, prows1);
+        const uint8_t* r1 = tile + (sy1 - sy_lo) * PS_PITCH;
+        if (sy0 != hrow) {
+            const uint8_t* r0 = tile + (sy0 - sy_lo) * PS_PITCH;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
                 const int a = r0[oa[k]], b = r0[ob[k]];
-                h0[k] = (a << 8) + ax[k] * (b - a);
+                hc[k] = (a << 8) + ax[k] * (b - a);
             }
-            const int a = r1[oa[k]], b = r1[ob[k]];
-            h1[k] = (a << 8) + ax[k] * (b - a);
         }
         uint32_t packed = 0;
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            if (k < nvalid) packed |= (uint32_t)(((h0[k] << 8) + ay * (h1[k] - h0[k]) + 32768) >> 16) << (8 * k);
-            hc[k] = h1[k];
+            const int a = r1[oa[k]], b = r1[ob[k]];
+            const int h1 = (a << 8) + ax[k] * (b - a);
+            const uint32_t v = (uint32_t)(((hc[k] << 8) + ay * (h1 - hc[k]) + 32768) >> 16);
+            if (k < nvalid) packed |= v << (8 * k);
+            hc[k] = h1;
         }
         hrow = sy1;
-        *reinterpret_cast<uint32_t*>(dst + (size_t)(yw + r) * d.pitch + x) = packed;
+        *reinterpret_cast<uint32_t*>(out) = packed;
+        out += dpitch;
     }
 }
 
