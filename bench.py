@@ -39,6 +39,21 @@ GRID_PITCH = 14  # synthetic scene density; the achieved keypoint
 METRIC = "frames/s ORB extract+match @1241x376, 2k kp"
 UNIT = "frames/s"
 WORKLOAD = "KITTI-shape synthetic grayscale sequence 1241x376 (BASELINE.json configs[1]: 1000 frames, 2000 ORB keypoints/frame, 8-level pyramid)"
+NFEATURES = 2000
+RANSAC_K4 = None  # (fx, fy, cx, cy): also run findEssentialMat(RANSAC) on every consecutive pair
+# The default (`kitti`) is the configuration BASELINE.json's metric is quoted on; the other two are BASELINE.json's
+# configs[2] / configs[3] at full size, selectable for extra measured lines (ORB mode only).
+WORKLOADS = {
+    "kitti": dict(rows=376, cols=1241, pitch_px=14, nfeatures=2000, frames=1000, max_kp=2560, chunk=500, metric=METRIC, text=WORKLOAD, k4=None),
+    "tum": dict(rows=480, cols=640, pitch_px=17, nfeatures=1000, frames=1000, max_kp=1280, chunk=500,
+                metric="frames/s ORB extract+match+findEssentialMat @640x480, 1k kp",
+                text="TUM-RGB-D-shape 640x480 synthetic sequence (BASELINE.json configs[2]: 1000 keypoints/frame, consecutive-frame matching + RANSAC essential matrix per pair)",
+                k4=(525.0, 525.0, 319.5, 239.5)),
+    "4k": dict(rows=2160, cols=3840, pitch_px=28, nfeatures=10000, frames=48, max_kp=12288, chunk=24,
+               metric="frames/s ORB extract+match @3840x2160, 10k kp",
+               text="4K 3840x2160 synthetic sequence (BASELINE.json configs[3]: 10000 keypoints/frame, sharded by frame range across the GPUs)",
+               k4=None),
+}
 
 
 def make_frames(n, seed):
@@ -67,37 +82,45 @@ def cpu_reference_run(frames, threads):
     return sec, counts
 
 
-def cpu_orb_run(frames, threads, nfeatures=2000, ratio=0.75):
-    """OpenCV's own ORB + BFMatcher(k=2) + ratio test on the host cores, frame-parallel (cv2 releases the GIL).
-    Returns (seconds, counts[n, 2] = keypoints, matches(f, f+1))."""
+def cpu_orb_run(frames, threads, nfeatures=None, ratio=0.75):
+    """OpenCV's own ORB + BFMatcher(k=2) + ratio test (+ findEssentialMat when the workload has it) on the host cores,
+    frame-parallel (cv2 releases the GIL).  Returns (seconds, counts[n, 2] = keypoints, matches(f, f+1))."""
     import concurrent.futures as cf
 
     import cv2
     cv2.setNumThreads(1)
     n = len(frames)
+    nfeatures = nfeatures or NFEATURES
+    k4 = RANSAC_K4
 
     def extract(i):
         orb = cv2.ORB_create(nfeatures=nfeatures, scaleFactor=1.2, nlevels=8, edgeThreshold=31, firstLevel=0, WTA_K=2,
                              scoreType=cv2.ORB_HARRIS_SCORE, patchSize=31, fastThreshold=20)
         k, d = orb.detectAndCompute(frames[i], None)
-        return d if d is not None else np.zeros((0, 32), np.uint8)
+        pts = np.float32([p.pt for p in k]).reshape(-1, 2)
+        return (d if d is not None else np.zeros((0, 32), np.uint8)), pts
 
     def match(i):
-        if len(desc[i]) == 0 or len(desc[i + 1]) < 2:
+        (d1, p1), (d2, p2) = feats[i], feats[i + 1]
+        if len(d1) == 0 or len(d2) < 2:
             return 0
-        m = cv2.BFMatcher(cv2.NORM_HAMMING).knnMatch(desc[i], desc[i + 1], k=2)
-        return sum(1 for a, b in m if not (a.distance >= np.float32(ratio) * np.float32(b.distance)))
+        m = cv2.BFMatcher(cv2.NORM_HAMMING).knnMatch(d1, d2, k=2)
+        good = [a for a, b in m if not (a.distance >= np.float32(ratio) * np.float32(b.distance))]
+        if k4 is not None and len(good) >= 8:  # PoseEstimator::estimate's guard (pose_estimator.cpp:22-26)
+            K = np.array([[k4[0], 0, k4[2]], [0, k4[1], k4[3]], [0, 0, 1.0]])
+            cv2.findEssentialMat(p1[[a.queryIdx for a in good]], p2[[a.trainIdx for a in good]], K, cv2.RANSAC, 0.999, 1.0, 1000)
+        return len(good)
 
     t0 = time.perf_counter()
     with cf.ThreadPoolExecutor(max_workers=threads) as ex:
-        desc = list(ex.map(extract, range(n)))
+        feats = list(ex.map(extract, range(n)))
         nm = list(ex.map(match, range(n - 1))) + [0]
     sec = time.perf_counter() - t0
-    return sec, np.array([[len(d), m] for d, m in zip(desc, nm)], np.int64)
+    return sec, np.array([[len(f[0]), m] for f, m in zip(feats, nm)], np.int64)
 
 
 MODE_TEXT = {
-    "orb": "OpenCV-ORB-compatible: 8-level pyramid, FAST-9 + Harris, 2000-keypoint budget, rBRIEF-256, BF Hamming kNN k=2 + ratio 0.75",
+    "orb": "OpenCV-ORB-compatible: 8-level pyramid, FAST-9 + Harris, keypoint budget per frame as the workload names, rBRIEF-256, BF Hamming kNN k=2 + ratio 0.75",
     "reference": "reference algorithm (FAST-12 + SAD NMS + BRIEF + BF Hamming with keypoint penalty)",
 }
 
@@ -120,7 +143,7 @@ def run_reference(args, rank, world):
     value = n * args.steps / t
     if orb:
         import cv2
-        kind, how = "reference", f"cv2 {cv2.__version__} ORB_create(2000).detectAndCompute + BFMatcher(NORM_HAMMING).knnMatch(k=2) + ratio 0.75, frame-parallel thread pool, cv2.setNumThreads(1) per call"
+        kind, how = "reference", f"cv2 {cv2.__version__} ORB_create({NFEATURES}).detectAndCompute + BFMatcher(NORM_HAMMING).knnMatch(k=2) + ratio 0.75, frame-parallel thread pool, cv2.setNumThreads(1) per call"
     else:
         kind, how = "port", "frame-parallel std::thread pool, oracle/ref_frontend.cpp (g++ -O2)"
     line = {
@@ -244,7 +267,11 @@ def run_ours(args, rank, world, local_rank):
     orb = args.mode == "orb"
     sfx = "_orb" if orb else ""
     with_kp = not orb  # the reference's matcher applies its image-distance penalty; BFMatcher has none
-    det = S.FeatureDetector(os.path.join(data, f"feature_detector{sfx}.yml"), ctx)
+    det_cfg = os.path.join(data, f"feature_detector{sfx}.yml")
+    if orb and NFEATURES != 2000:
+        from slam_cin0051_b200.config import read_yaml
+        det_cfg = {**read_yaml(det_cfg), "MaxFeatures": NFEATURES}
+    det = S.FeatureDetector(det_cfg, ctx)
     mat = S.FeatureMatcher(os.path.join(data, f"feature_matcher{sfx}.yml"), ctx)
     max_kp = args.max_keypoints
     seq = S.FrameSequence(ROWS, COLS, B, desc_bytes=det.descriptor_bytes, max_keypoints=max_kp, context=ctx)
@@ -265,6 +292,8 @@ def run_ours(args, rank, world, local_rank):
     def step_resident():
         seq.extract(det, 0, B)
         seq.match_consecutive(mat, 0, B - 1, with_keypoints=with_kp)
+        if RANSAC_K4:
+            seq.essential(RANSAC_K4, 0, B - 1)
 
     # end-to-end leg: two sequences double-buffer, so step k+1's H2D runs under step k's kernels (a streaming
     # deployment); every step still uploads its frames from pinned host memory and downloads all its results
@@ -277,6 +306,8 @@ def run_ours(args, rank, world, local_rank):
         k, d, m, c = outs[i % 2]
         seqs[i % 2].process_ptrs(det, mat, host_frames.data_ptr(), B, chunk=args.chunk, with_keypoints=with_kp,
                                  kps_ptr=k.data_ptr(), desc_ptr=d.data_ptr(), matches_ptr=m.data_ptr(), counts_ptr=c.data_ptr())
+        if RANSAC_K4:  # E, inlier masks and counts stay on the device (read per pair with essential_result)
+            seqs[i % 2].essential(RANSAC_K4, 0, B - 1)
 
     def collect_e2e(i):
         seqs[i % 2].wait()  # the step's results are now in host memory; read them
@@ -370,7 +401,7 @@ def run_ours(args, rank, world, local_rank):
                 peak = gpopc / (4.0 if orb else 2.0)
                 kernels.append({**common, "bound": "popc", "peak": peak, "unit": "Gcmp/s (256-bit)", "frac": ach / peak})
         try:
-            ncu = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_dram_per_frame.json")))["dram_bytes_per_frame"] if orb else {}
+            ncu = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_dram_per_frame.json")))["dram_bytes_per_frame"] if orb and (ROWS, COLS, NFEATURES) == (376, 1241, 2000) else {}
         except OSError:
             ncu = {}
         for k in kernels:  # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu --set full capture
@@ -418,7 +449,7 @@ def run_ours(args, rank, world, local_rank):
             if orb:
                 import cv2
                 kind = "reference"
-                what = f"cv2 {cv2.__version__} ORB_create(2000) + BFMatcher.knnMatch(k=2) + ratio 0.75 (the OpenCV path BASELINE.json names)"
+                what = f"cv2 {cv2.__version__} ORB_create({NFEATURES}) + BFMatcher.knnMatch(k=2) + ratio 0.75{' + findEssentialMat(RANSAC) per pair' if RANSAC_K4 else ''} (the OpenCV path BASELINE.json names)"
             else:
                 kind, what = "port", "oracle/ref_frontend.cpp (port of the reference's src/frontend, g++ -O2)"
             line["cpu_baseline"] = {"value": n_s / sec, "unit": UNIT, "cores": threads, "kind": kind,
@@ -439,11 +470,21 @@ def main():
     ap.add_argument("--mode", default="orb", choices=["orb", "reference"],
                     help="orb: the OpenCV-ORB-compatible path BASELINE.json's headline config names; "
                          "reference: the reference repo's own hand-written detector/matcher")
-    ap.add_argument("--frames", type=int, default=1000, help="frames per GPU per step (BASELINE.json configs[1]: a 1000-frame sequence)")
-    ap.add_argument("--max-keypoints", type=int, default=2560)
-    ap.add_argument("--chunk", type=int, default=500, help="frames per pipeline stage of the end-to-end leg")
+    ap.add_argument("--workload", default="kitti", choices=sorted(WORKLOADS),
+                    help="kitti: BASELINE.json configs[1], the configuration the metric is quoted on (default); tum / 4k: configs[2] / configs[3]")
+    ap.add_argument("--frames", type=int, default=None, help="frames per GPU per step (default: the workload's; kitti = a 1000-frame sequence)")
+    ap.add_argument("--max-keypoints", type=int, default=None)
+    ap.add_argument("--chunk", type=int, default=None, help="frames per pipeline stage of the end-to-end leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    global ROWS, COLS, GRID_PITCH, METRIC, WORKLOAD, NFEATURES, RANSAC_K4
+    w = WORKLOADS[args.workload]
+    if args.workload != "kitti" and args.mode != "orb":
+        ap.error("--workload tum / 4k are ORB-mode workloads (the reference algorithm has no keypoint budget)")
+    ROWS, COLS, GRID_PITCH, METRIC, WORKLOAD, NFEATURES, RANSAC_K4 = w["rows"], w["cols"], w["pitch_px"], w["metric"], w["text"], w["nfeatures"], w["k4"]
+    args.frames = args.frames or w["frames"]
+    args.max_keypoints = args.max_keypoints or w["max_kp"]
+    args.chunk = args.chunk or w["chunk"]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
