@@ -95,6 +95,20 @@ def test_against_live_cv2_on_other_inputs(gpu_ctx, orb_det):
     assert len(k) == 0 and d.shape == (0, 0)
 
 
+@pytest.mark.parametrize("scale,levels", [(1.1, 8), (1.3, 6), (1.45, 5), (2.0, 4)])
+def test_pyramid_scale_factors_against_live_cv2(gpu_ctx, scale, levels):
+    """Both pyramid kernels (shared-memory tiles while the source window of a 128x64 tile fits, the per-pixel gather for
+    steeper factors) over sizes that leave partial tiles on both axes."""
+    pytest.importorskip("cv2")
+    import slam_cin0051_b200 as s
+    from tools_golden import orb_canonical
+    from slam_cin0051_b200.synth import make_sequence
+    det = s.FeatureDetector({**ORB_CFG, "NumLevels": levels, "ScaleFactor": scale, "MaxFeatures": 1500}, gpu_ctx)
+    for rows, cols, seed in ((376, 1241, 21), (517, 903, 22), (130, 257, 23)):
+        img = make_sequence(rows, cols, 1, pitch_px=13, seed=seed)[0]
+        assert_orb_equal(gpu_orb(det, img), orb_canonical(img, nfeatures=1500, nlevels=levels, scale=scale))
+
+
 def test_knn2_and_ratio_matches(orb_mat):
     for a, b in (("kitti0", "kitti1"), ("synK0", "synK1")):
         g = gold(f"knn2_{a}_{b}.npz")
