@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(QT) match_kernel(MatchJob job, int with_kp, in
             for (int j = 0; j < cnt; j++) {
                 const uint2 a = *reinterpret_cast<const uint2*>(tile + j * 8);
                 int d = __popc(qd[0] ^ a.x) + __popc(qd[W > 1 ? 1 : 0] ^ a.y);
-                if (with_kp) d = penalise(d, qx, qy, txy[j].x, txy[j].y);
+                if (with_kp && d < t.second) d = penalise(d, qx, qy, txy[j].x, txy[j].y);  // the penalty only grows d: skipped when d cannot enter the top 2
                 top2_update(t, d, t0 + j);
             }
         } else if (W == 8) {
@@ -156,14 +156,14 @@ __global__ void __launch_bounds__(QT) match_kernel(MatchJob job, int with_kp, in
                         __popc(qd[W > 3 ? 3 : 0] ^ a.w) + __popc(qd[W > 4 ? 4 : 0] ^ b.x) +
                         __popc(qd[W > 5 ? 5 : 0] ^ b.y) + __popc(qd[W > 6 ? 6 : 0] ^ b.z) +
                         __popc(qd[W > 7 ? 7 : 0] ^ b.w);
-                if (with_kp) d = penalise(d, qx, qy, txy[j].x, txy[j].y);
+                if (with_kp && d < t.second) d = penalise(d, qx, qy, txy[j].x, txy[j].y);  // the penalty only grows d: skipped when d cannot enter the top 2
                 top2_update(t, d, t0 + j);
             }
         } else {
             for (int j = 0; j < cnt; j++) {
                 int d = 0;
                 for (int w = 0; w < wmax; w++) d += __popc(dq[(size_t)q * dw + w] ^ tile[j * dw + w]);
-                if (with_kp) d = penalise(d, qx, qy, txy[j].x, txy[j].y);
+                if (with_kp && d < t.second) d = penalise(d, qx, qy, txy[j].x, txy[j].y);  // the penalty only grows d: skipped when d cannot enter the top 2
                 top2_update(t, d, t0 + j);
             }
         }
