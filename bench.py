@@ -207,7 +207,7 @@ def orb_level_pixels(rows, cols, nlevels=8, sf=1.2):
     out = []
     for l in range(nlevels):
         s = np.float32(np.power(np.float64(np.float32(sf)), float(l)))
-        out.append(int(np.rint(np.float32(rows) / s)) * int(np.rint(np.float32(cols) / s)))
+        out.append(int(np.rint(np.float32(rows) * (np.float32(1) / s))) * int(np.rint(np.float32(cols) * (np.float32(1) / s))))
     return out
 
 

@@ -37,8 +37,9 @@ def level_scales(nlevels=8, scale_factor=1.2):
 def level_sizes(rows, cols, scales):
     out = []
     for s in scales:
-        w = int(np.rint(F32(cols) / s))  # cvRound(float): round half to even
-        h = int(np.rint(F32(rows) / s))
+        inv = F32(1.0) / F32(s)  # ORB_Impl: inv_scale = 1.0f / scale; Size(cvRound(cols * inv_scale), cvRound(rows * inv_scale))
+        w = int(np.rint(F32(cols) * inv))  # cvRound(float): round half to even.  NOT cols / scale: the two differ for
+        h = int(np.rint(F32(rows) * inv))  # 81 (size, level) combinations below 2200 px (e.g. 477 -> 398, not 397)
         out.append((h, w))
     return out
 

@@ -585,7 +585,8 @@ static int seq_ensure_orb(slamcu_sequence* s, slamcu_detector* det) {
     o.fast_threshold = det->fast_threshold;
     o.pattern = det->d_orb_pattern;
     o.patf = det->d_orb_patf;
-    // ORB_Impl: scale = (float)pow(scaleFactor, level); size = cvRound(dim / scale); quotas by geometric series
+    // ORB_Impl: scale = (float)pow(scaleFactor, level); inv_scale = 1.0f / scale; size = cvRound(dim * inv_scale) -- the
+    // product, not the quotient: they differ for 81 (size, level) pairs below 2200 px; quotas by geometric series
     const double sf = (double)det->scale_factor;
     const float factor = (float)(1.0 / sf);
     float ndesired = det->max_features * (1 - factor) / (1 - (float)std::pow((double)factor, (double)L));
@@ -594,9 +595,17 @@ static int seq_ensure_orb(slamcu_sequence* s, slamcu_detector* det) {
     for (int l = 0; l < L; l++) {
         OrbLevel& lv = o.lv[l];
         lv.scale = (float)std::pow(sf, (double)l);
-        lv.cols = (int)std::lrintf((float)v.cols / lv.scale);
-        lv.rows = (int)std::lrintf((float)v.rows / lv.scale);
-        if (lv.rows < 8 || lv.cols < 8) return fail(ctx, SLAMCU_INVALID_ARGUMENT, "pyramid level %d is %dx%d: too small", l, lv.cols, lv.rows);
+        const float inv_scale = 1.0f / lv.scale;
+        lv.cols = (int)std::lrintf((float)v.cols * inv_scale);
+        lv.rows = (int)std::lrintf((float)v.rows * inv_scale);
+        if (lv.rows < 1 || lv.cols < 1) return fail(ctx, SLAMCU_INVALID_ARGUMENT, "pyramid level %d is %dx%d: too small", l, lv.cols, lv.rows);
+        if (lv.rows < 8 || lv.cols < 8) {
+            // OpenCV still builds such a level, but nothing in it (nor in the smaller ones after it) survives the 31-px
+            // border filter and the per-level quotas are fixed up front: the remaining levels are simply not processed
+            if (l == 0) return fail(ctx, SLAMCU_INVALID_ARGUMENT, "image is %dx%d: too small", lv.cols, lv.rows);
+            o.nlevels = l;
+            break;
+        }
         lv.pitch = round_up(lv.cols, 128);
         lv.mwords = (lv.cols + 31) / 32;
         if (l == 0) lv.off = 0;
@@ -607,7 +616,9 @@ static int seq_ensure_orb(slamcu_sequence* s, slamcu_detector* det) {
         sb += (size_t)lv.rows * lv.pitch;
         if (l < L - 1) { lv.quota = (int)std::lrintf(ndesired); sum += lv.quota; ndesired *= factor; }
         else lv.quota = std::max(det->max_features - sum, 0);
-        lv.capc = round_up(std::max(2048, lv.rows * lv.cols / 16), 32);
+        // FAST survivors of the strict 3x3 NMS are never adjacent: at most a quarter of the pixels.  A one-frame
+        // workspace (the single-image calls) holds that bound; sequences keep 1/16 (status bit on overflow)
+        lv.capc = round_up(std::max(2048, lv.rows * lv.cols / (s->max_frames == 1 ? 4 : 16) + 64), 32);
         lv.coff = ct;
         ct += lv.capc;
     }
@@ -635,7 +646,7 @@ static int seq_ensure_orb(slamcu_sequence* s, slamcu_detector* det) {
     A(&o.n_fin, F * kMaxLevels, true);
     A(&o.octave, F * v.cap_kp, true);
     A(&o.lxy, F * v.cap_kp, true);
-    for (int l = 1; l < L && rc == SLAMCU_OK; l++) {
+    for (int l = 1; l < o.nlevels && rc == SLAMCU_OK; l++) {
         std::vector<uint32_t> tx, ty;
         resize_table(o.lv[l].cols, o.lv[l - 1].cols, tx);
         resize_table(o.lv[l].rows, o.lv[l - 1].rows, ty);
@@ -659,7 +670,7 @@ static int seq_ensure_orb(slamcu_sequence* s, slamcu_detector* det) {
             qres == cudaDriverEntryPointSuccess) {
             auto encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(fn);
             bool ok = true;
-            for (int l = 0; l < L && ok; l++) {
+            for (int l = 0; l < o.nlevels && ok; l++) {
                 const OrbLevel& lv = o.lv[l];
                 void* base = l == 0 ? (void*)v.img : (void*)(o.pyr + lv.off);
                 const cuuint64_t dims[3] = {(cuuint64_t)lv.cols, (cuuint64_t)lv.rows, (cuuint64_t)s->max_frames};
@@ -1105,9 +1116,11 @@ static int detector_workspace(slamcu_detector* d, int rows, int cols, int min_kp
         d->one = nullptr;
     }
     const long long px = (long long)rows * cols;
-    // single calls favour safety over footprint: room for one corner per 4 pixels
-    int cap_raw = (int)std::min<long long>(std::max<long long>(px / 4, 8192), kMaxRawCap);
-    int cap_kp = d->p.nms ? (int)std::min<long long>(std::max<long long>(px / 16, 4096), kMaxRawCap) : cap_raw;
+    // single calls favour safety over footprint: every pixel may be a raw corner (noise, low thresholds); after the
+    // greedy NMS the survivors are pairwise >= window apart (densest packing 2 / (sqrt(3) w^2) per pixel, + margin)
+    int cap_raw = (int)std::min<long long>(std::max<long long>(px, 8192), kMaxRawCap);
+    const long long w2 = std::max(1LL, (long long)d->p.window * d->p.window);
+    int cap_kp = d->p.nms ? (int)std::min<long long>(std::max<long long>(px * 8 / (5 * w2) + 4096, 4096), cap_raw) : cap_raw;
     if (d->mode == SLAMCU_MODE_ORB) { cap_raw = 8192; cap_kp = std::max(4096, 2 * d->max_features); }
     cap_kp = std::max(cap_kp, min_kp);
     return slamcu_sequence_create(ctx, rows, cols, 1, cap_raw, cap_kp, desc_bytes, &d->one);

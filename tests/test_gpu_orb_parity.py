@@ -88,6 +88,16 @@ def test_against_live_cv2_on_other_inputs(gpu_ctx, orb_det):
              np.full((240, 320), 77, np.uint8)]                             # flat: no corners at all
     for img in cases:
         assert_orb_equal(gpu_orb(orb_det, img), orb_canonical(img))
+    # 477 columns: level 1 is 398 wide (cvRound(477 * (1.0f / 1.2f)) = cvRound(397.5)), not 397 (found by tools/soak_parity.py)
+    det5 = s.FeatureDetector({**ORB_CFG, "NumLevels": 5, "MaxFeatures": 1000}, gpu_ctx)
+    odd = make_sequence(306, 477, 1, pitch_px=15, seed=31)[0]
+    assert_orb_equal(gpu_orb(det5, odd), orb_canonical(odd, nfeatures=1000, nlevels=5))
+    # more levels than the image can hold: the tiny ones have no keypoints (31-px border) and are not processed
+    small = make_sequence(90, 140, 1, pitch_px=11, seed=32)[0]
+    assert_orb_equal(gpu_orb(orb_det, small), orb_canonical(small))
+    # white noise at a low threshold: a quarter of the pixels are FAST candidates
+    det_lo = s.FeatureDetector({**ORB_CFG, "FastThreshold": 5, "MaxFeatures": 5000}, gpu_ctx)
+    assert_orb_equal(gpu_orb(det_lo, cases[2]), orb_canonical(cases[2], nfeatures=5000, fast=5))
     det = s.FeatureDetector({**ORB_CFG, "MaxFeatures": 10000}, gpu_ctx)
     big = make_sequence(1080, 1920, 1, pitch_px=28, seed=4)[0]
     assert_orb_equal(gpu_orb(det, big), orb_canonical(big, nfeatures=10000))
@@ -155,5 +165,8 @@ def test_orb_mode_errors(gpu_ctx):
     with pytest.raises(RuntimeError, match="ORB mode requires"):
         s.FeatureDetector({**ORB_CFG, "NumBRIEFPairs": 128}, gpu_ctx)
     det = s.FeatureDetector(ORB_CFG, gpu_ctx)
+    # levels below 8 px are not processed (nothing in them survives the 31-px border): no keypoints, like cv2
+    k, d = det.detect_and_compute(np.zeros((20, 20), np.uint8))
+    assert len(k) == 0
     with pytest.raises(s.SlamcuError):
-        det.detect_and_compute(np.zeros((20, 20), np.uint8))  # coarsest level would be < 8 px
+        det.detect_and_compute(np.zeros((5, 40), np.uint8))  # the image itself is below the FAST support

@@ -85,3 +85,24 @@ def test_stages_against_live_cv2():
     # the golden fixtures are what the installed cv2 still produces
     from tools_golden import orb_canonical
     assert_orb_equal(orb_canonical(img), gold("orb_tum0.npz"))
+
+
+def test_level_sizes_use_the_reciprocal_scale():
+    """ORB_Impl sizes level l as cvRound(dim * (1.0f / scale)), not cvRound(dim / scale): 477 px at scale 1.2f is
+    397.49997 as a quotient (-> 397) and exactly 397.5 as a product (-> 398, half to even).  Checked against cv2 itself:
+    its octave-1 keypoints are FAST corners of the 398-wide level, not of the 397-wide one."""
+    cv2 = pytest.importorskip("cv2")
+    from oracle import orb_oracle as oo
+    scales = oo.level_scales(2, 1.2)
+    assert oo.level_sizes(306, 477, scales)[1] == (255, 398)
+    assert oo.level_sizes(200, 117, scales)[1][1] == 98 and oo.level_sizes(376, 1241, scales)[1] == (313, 1034)
+    rng = np.random.default_rng(0)
+    img = cv2.GaussianBlur(rng.integers(0, 256, (200, 477), dtype=np.uint8), (0, 0), 1.2)
+    orb = cv2.ORB_create(nfeatures=3000, scaleFactor=1.2, nlevels=2, edgeThreshold=31, firstLevel=0, WTA_K=2,
+                         scoreType=cv2.ORB_HARRIS_SCORE, patchSize=31, fastThreshold=10)
+    pts = {(int(round(k.pt[0] / 1.2000000476837158)), int(round(k.pt[1] / 1.2000000476837158))) for k in orb.detect(img, None) if k.octave == 1}
+    assert len(pts) > 100
+    lv = oo.build_pyramid(img, 2, 1.2)[0][1]
+    assert lv.shape == (167, 398)
+    corners = {(int(p.pt[0]), int(p.pt[1])) for p in cv2.FastFeatureDetector_create(10, True).detect(lv)}
+    assert pts <= corners

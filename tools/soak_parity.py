@@ -1,0 +1,163 @@
+"""Randomised parity soak on a GPU box: random sizes, contents and parameters through the C ABI in both modes, compared
+bit for bit with live cv2 (ORB mode, kNN) and with the C++ restatement of the reference (reference mode); RANSAC against
+the oracle loop driven by the g++ build of the device solver.  usage: python tools/soak_parity.py [seconds] [seed]
+Prints one JSON line: cases run per family and every mismatch (seed + parameters, enough to reproduce)."""
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import cv2  # noqa: E402
+
+import slam_cin0051_b200 as S  # noqa: E402
+from oracle import essential_oracle as eo  # noqa: E402
+from oracle import ref_oracle  # noqa: E402
+from slam_cin0051_b200.synth import make_sequence  # noqa: E402
+from tools_golden import knn2 as cv_knn2  # noqa: E402
+from tools_golden import orb_canonical  # noqa: E402
+
+budget = float(sys.argv[1]) if len(sys.argv) > 1 else 120.0
+seed0 = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+ctx = S.Context(0)
+ref_oracle.build()
+so = os.path.join(ROOT, "tests", "native", "libhost_exact.so")
+if not os.path.exists(so):
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", so, os.path.join(ROOT, "tests", "native", "host_exact.cpp")])
+hx = C.CDLL(so)
+kitti = cv2.imread(os.path.join(ROOT, "test", "data", "images", "0000000000.png"), 0)
+
+
+def image(rng, rows, cols):
+    kind = rng.integers(0, 4)
+    if kind == 0:
+        return make_sequence(rows, cols, 1, pitch_px=int(rng.integers(9, 30)), seed=int(rng.integers(1 << 30)))[0], "scene"
+    if kind == 1:
+        return rng.integers(0, 256, (rows, cols), dtype=np.uint8), "noise"
+    if kind == 2 and rows <= kitti.shape[0] and cols <= kitti.shape[1]:
+        y, x = rng.integers(0, kitti.shape[0] - rows + 1), rng.integers(0, kitti.shape[1] - cols + 1)
+        return np.ascontiguousarray(kitti[y:y + rows, x:x + cols]), "kitti-crop"
+    g = cv2.GaussianBlur(rng.integers(0, 256, (rows, cols), dtype=np.uint8), (0, 0), float(rng.uniform(0.8, 3.0)))
+    return cv2.normalize(g, None, 0, 255, cv2.NORM_MINMAX).astype(np.uint8), "smooth-noise"
+
+
+def orb_case(rng):
+    rows, cols = int(rng.integers(70, 700)), int(rng.integers(70, 1300))
+    p = dict(NumLevels=int(rng.integers(1, 9)), ScaleFactor=float(rng.choice([1.1, 1.2, 1.25, 1.3, 1.5, 2.0])),
+             MaxFeatures=int(rng.choice([50, 300, 1000, 2000, 5000])), FastThreshold=int(rng.choice([5, 10, 20, 40])))
+    img, kind = image(rng, rows, cols)
+    det = S.FeatureDetector(dict(IntensityThreshold=20, ContiguousPixelsThreshold=9, NonMaxSuppression=1, SuppressionWindowSize=3,
+                                 PatchSize=31, NumBRIEFPairs=256, **p), ctx)
+    k, d = det.detect_and_compute(img)
+    got = {"x": k["x"], "y": k["y"], "size": k["size"], "angle": k["angle"], "response": k["response"],
+           "octave": det.last_octaves(len(k)), "desc": d}
+    want = orb_canonical(img, nfeatures=p["MaxFeatures"], nlevels=p["NumLevels"], scale=p["ScaleFactor"], fast=p["FastThreshold"])
+    ok = len(got["x"]) == len(want["x"])
+    if ok:
+        for f in ("x", "y", "size", "angle", "response"):
+            ok &= np.asarray(got[f], np.float32).tobytes() == np.asarray(want[f], np.float32).tobytes()
+        ok &= np.array_equal(got["octave"], want["octave"]) and np.array_equal(got["desc"].reshape(len(k), -1) if len(k) else np.zeros((0, 32), np.uint8),
+                                                                                want["desc"].reshape(len(k), -1) if len(k) else np.zeros((0, 32), np.uint8))
+    return bool(ok), dict(rows=rows, cols=cols, kind=kind, n=int(len(k)), **p)
+
+
+def ref_case(rng):
+    rows, cols = int(rng.integers(40, 520)), int(rng.integers(40, 900))
+    cfg = dict(IntensityThreshold=int(rng.choice([10, 20, 35])), ContiguousPixelsThreshold=int(rng.choice([0, 5, 9, 12, 16])),
+               NonMaxSuppression=int(rng.integers(0, 2)), SuppressionWindowSize=int(rng.choice([3, 7, 12, 20])),
+               PatchSize=int(rng.choice([9, 15, 31, 41])), NumBRIEFPairs=int(rng.choice([8, 64, 256, 512])))
+    img, kind = image(rng, rows, cols)
+    img2, _ = image(rng, rows, cols)
+    det = S.FeatureDetector(cfg, ctx)
+    gk, gd = det.detect_and_compute(img)
+    wk, wd = ref_oracle.detect_and_compute(img, cfg)
+    # no keypoints: the reference returns DescriptorMatrix(0, 0) (feature_detector.cpp:22-25), the oracle wrapper (0, 32)
+    ok = gk.tobytes() == wk.tobytes() and (np.array_equal(gd, wd) if len(wk) else gd.size == 0)
+    if ok and len(wk) > 0:
+        wk2, wd2 = ref_oracle.detect_and_compute(img2, cfg)
+        if len(wk2) > 0:
+            mcfg = dict(DistanceType="HAMMING", FilterMatches=int(rng.integers(0, 2)), GoodMatchesCount=int(rng.choice([5, 20, 500])),
+                        UseRatioTest=int(rng.integers(0, 2)), RatioTestThreshold=float(rng.choice([0.5, 0.75, 0.9])))
+            m = S.FeatureMatcher(mcfg, ctx)
+            with_kp = bool(rng.integers(0, 2))
+            got = m.match(wd, wd2, wk if with_kp else None, wk2 if with_kp else None)
+            q, t, d = ref_oracle.match(wd, wd2, wk if with_kp else None, wk2 if with_kp else None, cfg=mcfg, stage=1)
+            ok = len(got) == len(q) and np.array_equal(got["queryIdx"], q) and np.array_equal(got["trainIdx"], t) and \
+                np.array_equal(got["distance"].view(np.uint32), np.asarray(d, np.float32).view(np.uint32))
+            cfg = {**cfg, **mcfg, "with_kp": with_kp}
+    return bool(ok), dict(rows=rows, cols=cols, kind=kind, n=int(len(wk)), **cfg)
+
+
+def knn_case(rng):
+    nq, nt = int(rng.integers(1, 3000)), int(rng.integers(2, 3000))
+    dq = rng.integers(0, 256, (nq, 32), dtype=np.uint8)
+    dt = rng.integers(0, 256, (nt, 32), dtype=np.uint8)
+    if rng.integers(0, 2):  # plant near-duplicates and exact ties
+        k = min(nq, nt) // 2
+        dt[:k] = dq[:k]
+        dt[k // 2:k, 0] ^= 1
+    mat = S.FeatureMatcher(dict(DistanceType="HAMMING", FilterMatches=0, GoodMatchesCount=1, UseRatioTest=1, RatioTestThreshold=0.75), ctx)
+    got = mat.knn2(dq, dt)
+    idx, dist = cv_knn2(dq, dt)
+    ok = np.array_equal(got["trainIdx0"], idx[:, 0]) and np.array_equal(got["trainIdx1"], idx[:, 1]) and \
+        np.array_equal(got["distance0"], dist[:, 0].astype(np.float32)) and np.array_equal(got["distance1"], dist[:, 1].astype(np.float32))
+    return bool(ok), dict(nq=nq, nt=nt)
+
+
+def solver(a, b):
+    a = np.ascontiguousarray(a, np.float64).reshape(1, 5, 2)
+    b = np.ascontiguousarray(b, np.float64).reshape(1, 5, 2)
+    models = np.zeros((1, 10, 9))
+    counts = np.zeros(1, np.int32)
+    hx.hx_five_point(a.ctypes.data, b.ctypes.data, 1, models.ctypes.data, counts.ctypes.data)
+    return [models[0, k].reshape(3, 3).copy() for k in range(counts[0])]
+
+
+def ransac_case(rng):
+    n = int(rng.integers(8, 400))
+    inl = float(rng.uniform(0.3, 0.95))
+    K4 = (float(rng.uniform(300, 900)),) * 2 + (320.0, 240.0)
+    K = np.array([[K4[0], 0, K4[2]], [0, K4[1], K4[3]], [0, 0, 1.0]])
+    X = np.c_[rng.uniform(-3, 3, n), rng.uniform(-2, 2, n), rng.uniform(4, 12, n)]
+    rv = rng.normal(0, 0.08, 3)
+    R, _ = cv2.Rodrigues(rv)
+    t = rng.normal(0, 0.4, 3)
+    p1 = (K @ X.T).T
+    p2 = (K @ (X @ R.T + t).T).T
+    p1, p2 = p1[:, :2] / p1[:, 2:], p2[:, :2] / p2[:, 2:]
+    p2 = p2 + rng.normal(0, 0.4, p2.shape)
+    bad = rng.random(n) > inl
+    p2[bad] = rng.uniform(0, 640, (int(bad.sum()), 2))
+    p1, p2 = p1.astype(np.float32), p2.astype(np.float32)
+    max_iters = int(rng.choice([20, 56, 100, 1000]))
+    E, mask, good = S.find_essential(p1, p2, K4, max_iters=max_iters, context=ctx)
+    wE, wmask, wgood = eo.find_essential(p1, p2, K4, max_iters=max_iters, solver=solver)
+    ok = good == wgood and np.array_equal(mask, wmask)
+    if ok and E is not None:
+        ok = min(np.abs(E - wE).max(), np.abs(E + wE).max()) < 1e-5  # conditioning of the winning sample; masks are the exact part
+    return bool(ok), dict(n=n, inlier_ratio=round(inl, 2), max_iters=max_iters, good=int(good), want=int(wgood))
+
+
+families = {"orb_vs_cv2": orb_case, "reference_vs_cpp_restatement": ref_case, "knn2_vs_cv2": knn_case, "ransac_vs_oracle_loop": ransac_case}
+runs = {k: 0 for k in families}
+fails = []
+t_end = time.time() + budget
+i = 0
+while time.time() < t_end:
+    name = list(families)[i % len(families)]
+    seed = seed0 * 1000003 + i
+    try:
+        ok, info = families[name](np.random.default_rng(seed))
+    except Exception as e:  # a crash is a finding too
+        ok, info = False, {"exception": repr(e)[:200]}
+    runs[name] += 1
+    if not ok:
+        fails.append({"family": name, "seed": seed, **info})
+    i += 1
+print(json.dumps({"tool": "soak_parity", "seconds": budget, "seed0": seed0, "cases": runs, "mismatches": len(fails), "details": fails[:20]}))
