@@ -144,7 +144,74 @@ def ransac_case(rng):
     return bool(ok), dict(n=n, inlier_ratio=round(inl, 2), max_iters=max_iters, good=int(good), want=int(wgood))
 
 
-families = {"orb_vs_cv2": orb_case, "reference_vs_cpp_restatement": ref_case, "knn2_vs_cv2": knn_case, "ransac_vs_oracle_loop": ransac_case}
+def sequence_case(rng):
+    """Batched device-resident path and the pipelined host-buffer path against the single-image calls (all on the GPU)."""
+    import torch
+    from slam_cin0051_b200.sequence import FrameSequence
+    orb = bool(rng.integers(0, 2))
+    rows, cols, n = int(rng.integers(80, 420)), int(rng.integers(100, 700)), int(rng.integers(2, 10))
+    frames = np.stack([image(rng, rows, cols)[0] if rng.integers(0, 4) else np.full((rows, cols), 90, np.uint8) for _ in range(n)])
+    if orb:
+        det = S.FeatureDetector(dict(IntensityThreshold=20, ContiguousPixelsThreshold=9, NonMaxSuppression=1, SuppressionWindowSize=3,
+                                     PatchSize=31, NumBRIEFPairs=256, NumLevels=int(rng.integers(1, 7)), ScaleFactor=1.2,
+                                     MaxFeatures=int(rng.choice([200, 1000])), FastThreshold=20), ctx)
+        mat = S.FeatureMatcher(os.path.join(ROOT, "test", "data", "feature_matcher_orb.yml"), ctx)
+    else:
+        det = S.FeatureDetector(os.path.join(ROOT, "test", "data", "feature_detector.yml"), ctx)
+        mat = S.FeatureMatcher(os.path.join(ROOT, "test", "data", "feature_matcher.yml"), ctx)
+    cap, raw = 8192, rows * cols
+    singles = [det.detect_and_compute(f) for f in frames]
+    if max(len(k) for k, _ in singles) > cap:
+        return True, dict(skipped="more keypoints than the sequence capacity")
+    chunk = int(rng.choice([1, 2, 3, 64]))
+    seq = FrameSequence(rows, cols, n, desc_bytes=32, max_raw_corners=raw, max_keypoints=cap, context=ctx)
+    h_frames = torch.empty((n, rows, cols), dtype=torch.uint8, pin_memory=True)
+    h_frames.numpy()[:] = frames
+    h_kps = torch.zeros((n, cap, 5), dtype=torch.float32, pin_memory=True)
+    h_desc = torch.zeros((n, cap, 32), dtype=torch.uint8, pin_memory=True)
+    h_m = torch.zeros((n, cap, 3), dtype=torch.int32, pin_memory=True)
+    h_c = torch.zeros((n, 4), dtype=torch.int32, pin_memory=True)
+    seq.process_ptrs(det, mat, h_frames.data_ptr(), n, chunk=chunk, with_keypoints=not orb, kps_ptr=h_kps.data_ptr(),
+                     desc_ptr=h_desc.data_ptr(), matches_ptr=h_m.data_ptr(), counts_ptr=h_c.data_ptr())
+    ctx.synchronize()
+    c = h_c.numpy()
+    if (c[:, 3] != 0).any():
+        return True, dict(skipped="candidate-list overflow reported by the sequence (status bits)")
+    ok = True
+    for f, (k, d) in enumerate(singles):
+        ok &= int(c[f, 0]) == len(k) and h_kps.numpy()[f, :len(k)].tobytes() == k.tobytes()
+        ok &= len(k) == 0 or np.array_equal(h_desc.numpy()[f, :len(k)], d)
+        if f + 1 < n:
+            k2, d2 = singles[f + 1]
+            if len(k) and len(k2):
+                m = mat.match(d, d2, None if orb else k, None if orb else k2)
+                ok &= int(c[f, 1]) == len(m) and h_m.numpy()[f, :len(m)].tobytes() == m.tobytes()
+            else:
+                ok &= int(c[f, 1]) == 0
+    return bool(ok), dict(orb=orb, rows=rows, cols=cols, n=n, chunk=chunk)
+
+
+def prep_case(rng):
+    """cv::cvtColor(BGR2GRAY) against cv2 and Camera::undistortImage against the C++ restatement."""
+    rows, cols = int(rng.integers(8, 500)), int(rng.integers(8, 900))
+    bgr = rng.integers(0, 256, (rows, cols, 3), dtype=np.uint8)
+    ok = np.array_equal(S.bgr_to_gray(bgr, ctx), cv2.cvtColor(bgr, cv2.COLOR_BGR2GRAY))
+    gray = rng.integers(0, 256, (rows, cols), dtype=np.uint8)
+    K4 = (float(rng.uniform(200, 1200)), float(rng.uniform(200, 1200)), cols / 2 + float(rng.normal(0, 5)), rows / 2 + float(rng.normal(0, 5)))
+    D4 = tuple(float(x) for x in rng.normal(0, [0.2, 0.05, 0.002, 0.002]))
+    out = np.zeros((rows, cols), np.uint8)
+    outf = np.zeros((rows, cols), np.float64)
+    k = np.array(K4, np.float64)
+    dd = np.array(D4, np.float64)
+    ctx.check(ctx.lib.slamcu_undistort(ctx.handle, gray.ctypes.data, rows, cols, cols, k.ctypes.data, dd.ctypes.data, out.ctypes.data,
+                                       outf.ctypes.data))
+    want = ref_oracle.undistort(gray, K4, D4)  # the reference's double image in [0, 1]
+    ok &= np.array_equal(outf, want) and np.array_equal(out.astype(np.float64) / 255.0, want)
+    return bool(ok), dict(rows=rows, cols=cols, K4=K4, D4=D4)
+
+
+families = {"orb_vs_cv2": orb_case, "reference_vs_cpp_restatement": ref_case, "knn2_vs_cv2": knn_case, "ransac_vs_oracle_loop": ransac_case,
+            "sequence_vs_single_calls": sequence_case, "prep_vs_cv2_and_restatement": prep_case}
 runs = {k: 0 for k in families}
 fails = []
 t_end = time.time() + budget
