@@ -264,7 +264,7 @@ int slamcu_fivept_solve(slamcu_context* ctx, const double* x1, const double* x2,
                         int32_t* counts);
 /* Batched: findEssentialMat on the matches of pairs (f, f+1), f in [first, first + n_pairs), of a sequence
  * (keypoints of match.queryIdx / match.trainIdx, as PoseEstimator::estimate gathers them, pose_estimator.cpp:30-35).
- * Adaptive waves in one thread block per pair (one warp per 5-point sample); pairs that need more than 56 iterations are
+ * Adaptive waves in one thread block per pair (one warp per 5-point sample); pairs that need more than 24 iterations are
  * finished speculatively by the whole grid and replayed exactly.  max_iters <= 50000.  Asynchronous. */
 int slamcu_sequence_essential(slamcu_sequence* seq, int first, int n_pairs, const double* K4, double prob,
                               double threshold, int max_iters);

@@ -9,11 +9,11 @@
 // rounding, their order inside one sample may differ (that only matters for exact ties at the maximum).
 //
 // Two phases, both with ONE WARP PER SAMPLE running the minimal solver (fivept_warp.cuh):
-//   essential_ransac_kernel   one block per frame pair, adaptive like the original loop in waves of 8, 16, 32 samples:
+//   essential_ransac_kernel   one block per frame pair, adaptive like the original loop in waves of 8 and 16 samples:
 //       warps take samples from a shared counter (the last warp first draws the NEXT wave's subsets from the
 //       sequential RNG), one warp per hypothesis scores all correspondences (ballot + popc inlier count), thread 0
 //       replays the sequential accept / niters rule.  Most pairs end here (niters drops to ~10 after the first good
-//       model).  A pair still running after 56 iterations draws the subsets of ALL remaining iterations and stops.
+//       model).  A pair still running after 24 iterations draws the subsets of ALL remaining iterations and stops.
 //   essential_spec_kernel     the whole grid works on the unfinished pairs: one warp solves one remaining sample and
 //       scores its own hypotheses (speculative: iterations past the final niters are simply ignored later).
 //   essential_finish_kernel   per unfinished pair: the sequential replay over the recorded inlier counts picks exactly
@@ -27,8 +27,8 @@ namespace {
 constexpr int RT = 256;       // threads per block
 constexpr int NW = RT / 32;   // warps: one sample / one hypothesis each at a time
 constexpr int WAVE0 = 8;      // first wave of the adaptive phase
-constexpr int WAVE = 32;      // its largest wave
-constexpr int P1_ITERS = 56;  // the adaptive phase hands over to the speculative one after 8 + 16 + 32 iterations
+constexpr int WAVE = 16;      // its largest wave
+constexpr int P1_ITERS = 24;  // the adaptive phase hands over to the speculative one after 8 + 16 iterations
 constexpr int MAXM = kMaxModels;
 
 struct CvRng {
