@@ -55,6 +55,32 @@ __device__ __forceinline__ void mul21_acc(const double* a, const double* b, doub
         for (int j = 0; j < 4; j++) out[T21[i][j]] += a[i] * b[j];
 }
 
+// a / b for the Newton iterations: reciprocal seed (MUFU.RCP64H, ~20 bits) refined by two Newton steps and one
+// residual correction -- ~8 instructions and half the latency of the IEEE division; the last bit may differ from it,
+// which only moves an iterate by an ulp.  b = 0 / inf / NaN propagate to a NaN quotient: the caller then bisects.
+__device__ __forceinline__ double fast_div(double a, double b) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+    double e = __fma_rn(-b, r, 1.0);
+    r = __fma_rn(r, e, r);
+    e = __fma_rn(-b, r, 1.0);
+    r = __fma_rn(r, e, r);
+    const double q = a * r;
+    return __fma_rn(r, __fma_rn(-b, q, a), q);
+}
+
+// 1 / sqrt(s) for the normalisations: rsqrt seed refined by two Newton steps (relative error ~1e-16)
+__device__ __forceinline__ double fast_rsqrt(double s) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(s));
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const double e = __fma_rn(-(s * y), y, 1.0);  // 1 - s y^2
+        y = __fma_rn(0.5 * y, e, y);
+    }
+    return y;
+}
+
 // One level of the derivative chain for both half-warps in lockstep: f = ascending coefficients of a degree-DEG
 // polynomial (per half), cp[0..m) = the roots of f' inside the interval (ascending), closed = include the end points
 // -1 and 1 themselves.  Writes the roots of f inside the interval to nx (ascending) and returns their number (uniform
@@ -92,7 +118,7 @@ __device__ __noinline__ int root_level(const double* f, const double* cp, double
     const double tol = top ? 1e-10 : 1e-8;
     double lo = sc ? xa : 0.0, hi = sc ? xb : 0.0;
     const bool up = fa < 0.0;  // f(lo) < 0 < f(hi)
-    double x = sc ? xa - fa * ((xb - xa) / (fb - fa)) : 0.0;  // regula falsi start
+    double x = sc ? xa - fa * fast_div(xb - xa, fb - fa) : 0.0;  // regula falsi start
     if (!(x > lo && x < hi)) x = 0.5 * (lo + hi);
     double dxold = hi - lo;
     bool done = !sc;
@@ -107,7 +133,7 @@ __device__ __noinline__ int root_level(const double* f, const double* cp, double
         double fx, dfx;
         horner_pd<DEG>(c, x, fx, dfx);
         if ((fx < 0.0) == up) lo = x; else hi = x;  // f(x) has the sign of f(lo): move lo
-        const double xn = x - fx / dfx;
+        const double xn = x - fast_div(fx, dfx);
         const bool newton = xn > lo && xn < hi && fabs(2.0 * fx) <= fabs(dxold * dfx);
         const double xnew = newton ? xn : 0.5 * (lo + hi);
         const double dx = fabs(xnew - x);
@@ -125,7 +151,7 @@ __device__ __noinline__ int root_level(const double* f, const double* cp, double
         for (int r = 0; r < 2; r++) {
             double fx, dfx;
             horner_pd<DEG>(c, x, fx, dfx);
-            const double xn = x - fx / dfx;
+            const double xn = x - fast_div(fx, dfx);
             if (sc && fx != 0.0 && dfx != 0.0 && xn >= lo && xn <= hi) x = xn;
         }
     }
@@ -199,7 +225,7 @@ __device__ int five_point_warp(const double2* x1, const double2* x2, const int* 
         if (!(best > 0.0)) return 0;
         const int pr = bi, pc = bl;
         const double piv = __shfl_sync(FULL, sel5(q, pr), pc);
-        const double qn = sel5(q, pr) / piv;  // normalised pivot row, this lane's column
+        const double qn = fast_div(sel5(q, pr), piv);  // normalised pivot row, this lane's column
 #pragma unroll
         for (int k = 0; k < 5; k++) {
             const double f = __shfl_sync(FULL, q[k], pc);
@@ -242,8 +268,7 @@ __device__ int five_point_warp(const double2* x1, const double2* x2, const int* 
                 const double d = half_sum(bk[k] * bk[j]);
                 bk[k] = bk[k] - d * bk[j];
             }
-            const double nn = sqrt(half_sum(bk[k] * bk[k]));
-            bk[k] = bk[k] / nn;
+            bk[k] = bk[k] * fast_rsqrt(half_sum(bk[k] * bk[k]));
         }
     FP_MARK(1);
     // ================= B: the ten cubic constraints ====================================================================
@@ -331,7 +356,7 @@ __device__ int five_point_warp(const double2* x1, const double2* x2, const int* 
                 if (r == piv) { col[c] = col[r]; col[r] = t; }
         }
         const double d = __shfl_sync(FULL, col[c], c);
-        col[c] = col[c] / d;
+        col[c] = fast_div(col[c], d);
 #pragma unroll
         for (int r = 0; r < 10; r++) {
             if (r == c) continue;
@@ -408,7 +433,7 @@ __device__ int five_point_warp(const double2* x1, const double2* x2, const int* 
     const int half = lane >> 4, hl = lane & 15;
     double* a = pa + half * 11;
     if (hl <= n) {
-        const double v = det[lead + hl] / det[lead];  // coefficient of x^(n - hl)
+        const double v = fast_div(det[lead + hl], det[lead]);  // coefficient of x^(n - hl)
         a[half == 0 ? n - hl : hl] = v;
     }
     __syncwarp();
@@ -485,16 +510,16 @@ __device__ int five_point_warp(const double2* x1, const double2* x2, const int* 
             if (nn > vn) { vn = nn; v0 = cx; v1 = cy; v2 = cz; }
         }
         if (!(fabs(v2) < 1e-10 * sqrt(vn))) {
-            const double x = v0 / v2, y = v1 / v2;
+            const double x = fast_div(v0, v2), y = fast_div(v1, v2);
             double nn = 0.0;
 #pragma unroll
             for (int t = 0; t < 9; t++) {
                 e[t] = ((x * B4[t] + y * B4[9 + t]) + z * B4[18 + t]) + B4[27 + t];
                 nn += e[t] * e[t];
             }
-            nn = sqrt(nn);
+            nn = fast_rsqrt(nn);
 #pragma unroll
-            for (int t = 0; t < 9; t++) e[t] = e[t] / nn;
+            for (int t = 0; t < 9; t++) e[t] = e[t] * nn;
             good = true;
         }
     }
