@@ -97,11 +97,13 @@ __device__ int warp_partition(uint32_t* keys, int first, int last, uint32_t* Lpo
     return cut;
 }
 
-__global__ void __launch_bounds__(256) sort_kernel(SeqView s, int first_frame, int smem_keys) {
+// Frames with n_lo < n_raw <= n_hi are sorted by this launch (two launches cover all frames: see launch_sort_nms).
+__global__ void __launch_bounds__(256) sort_kernel(SeqView s, int first_frame, int smem_keys, int n_lo, int n_hi) {
     extern __shared__ uint32_t sk[];
     __shared__ int qn[2];
     const int f = first_frame + blockIdx.x;
     const int n = s.n_raw[f];
+    if (n <= n_lo || n > n_hi) return;
     uint32_t* gkeys = s.keys + (size_t)f * s.cap_raw;
     uint32_t* scratch = s.sort_scratch + (size_t)f * s.scratch_words;
     uint32_t* Lpos = scratch;
@@ -505,16 +507,26 @@ void init_sortnms_attributes(int smem_optin) {
 }
 
 int launch_sort_nms(const SeqView& s, int first, int n, const DetParams& p, int smem_optin, cudaStream_t st) {
-    // keys in shared memory when the frame's raw-corner count fits; else the same code runs on HBM
-    int smem_keys = min(s.cap_raw, (smem_optin - 1024) / 4);
-    size_t sort_smem = (size_t)smem_keys * 4;
-    SLAM_KERNEL("sort", st, sort_kernel<<<n, 256, sort_smem, st>>>(s, first, smem_keys));
+    // keys in shared memory when the frame's raw-corner count fits; else the same code runs on HBM.  The sort is one
+    // latency-bound block per frame, so the shared-memory request decides how many frames an SM sorts at once: a first
+    // launch takes the frames that fit a third of the SM's shared memory (3 blocks / SM), a second one the rest
+    const int smem_keys = min(s.cap_raw, (smem_optin - 1024) / 4);
+    const int small_keys = min(smem_keys, (smem_optin / 3 - 2048) / 4);
+    int launches = 0;
+    if (small_keys > 0 && small_keys < smem_keys) {
+        SLAM_KERNEL("sort", st, sort_kernel<<<n, 256, (size_t)small_keys * 4, st>>>(s, first, small_keys, 0, small_keys));
+        SLAM_KERNEL("sort_large", st, sort_kernel<<<n, 256, (size_t)smem_keys * 4, st>>>(s, first, smem_keys, small_keys, INT_MAX));
+        launches = 2;
+    } else {
+        SLAM_KERNEL("sort", st, sort_kernel<<<n, 256, (size_t)smem_keys * 4, st>>>(s, first, smem_keys, 0, INT_MAX));
+        launches = 1;
+    }
     const size_t bm_bytes = (size_t)s.rows * s.mwords * 4;
     const int use_smem = bm_bytes <= (size_t)(smem_optin - 1024);
     const int par_smem = smem_optin - 4096;  // leaves room for the kernel's static shared memory
     SLAM_KERNEL("nms", st, nms_parallel_kernel<<<n, kNmsThreads, par_smem, st>>>(s, first, p.window, par_smem));
     SLAM_KERNEL("nms_fallback", st, nms_kernel<<<n, 32, use_smem ? bm_bytes : 0, st>>>(s, first, p.window, use_smem, 1));
-    return 3;
+    return launches + 2;
 }
 
 }  // namespace slamcu
