@@ -6,15 +6,17 @@ set -u
 cd "${GRAFT_REPO_ROOT:-.}"
 O=gpurun_out
 NCU="ncu --clock-control none"
-python bench.py > $O/bench_final_orb.json 2> $O/bench_final_orb.err
-python bench.py --mode reference > $O/bench_final_refmode.json 2> $O/bench_final_refmode.err
-python bench.py --impl reference --steps 3 --warmup 1 > $O/bench_final_orb_refarm.json 2>> $O/bench_final_orb.err
-python bench.py --impl reference --mode reference --steps 3 --warmup 1 > $O/bench_final_refmode_refarm.json 2>> $O/bench_final_refmode.err
-for MODE in orb reference; do
+MODES="${MODES:-orb reference}"   # MODES=reference bash tools/profile_round.sh refreshes one mode only
+for MODE in $MODES; do
+  SFX=$([ $MODE = orb ] && echo orb || echo refmode)
+  python bench.py --mode $MODE > $O/bench_final_$SFX.json 2> $O/bench_final_$SFX.err
+  python bench.py --impl reference --mode $MODE --steps 3 --warmup 1 > $O/bench_final_${SFX}_refarm.json 2>> $O/bench_final_$SFX.err
+done
+for MODE in $MODES; do
   CMD="python bench.py --mode $MODE --frames 256 --steps 1 --warmup 3 --no-cpu-baseline"
   $NCU --metrics gpu__time_duration.sum -c 2000 --csv --log-file $O/launches_$MODE.csv $CMD > $O/ncu_launches_$MODE.log 2>&1
   FIRST=$([ $MODE = orb ] && echo pyr_down_kernel || echo fast_mask_kernel)
-  PER=$([ $MODE = orb ] && echo 31 || echo 10)
+  PER=$([ $MODE = orb ] && echo 31 || echo 11)
   # first launch of the timed resident step = the (3 warm-up steps + 1)-th step that starts with $FIRST
   SKIP=$(python - "$O/launches_$MODE.csv" $FIRST $MODE <<'PY'
 import csv, sys
@@ -30,7 +32,5 @@ PY
   $NCU --set full --import-source on --launch-skip $SKIP --launch-count $PER -o /tmp/full_$MODE -f $CMD > $O/ncu_full_$MODE.log 2>&1
   ncu -i /tmp/full_$MODE.ncu-rep --page raw --csv > $O/raw_full_$MODE.csv 2>> $O/profile_round.log
 done
-$NCU --set full --import-source on -k regex:essential --launch-skip 4 --launch-count 4 -o /tmp/full_ransac -f python tools/ransac_probe.py 512 > $O/ncu_full_ransac.log 2>&1
-ncu -i /tmp/full_ransac.ncu-rep --page raw --csv > $O/raw_full_ransac.csv 2>> $O/profile_round.log
-python tools/ransac_probe.py 512 > $O/ransac_probe_final.log 2>&1
+# (the two-view kernels: tools/profile_ransac.sh)
 tail -3 $O/profile_round.log
