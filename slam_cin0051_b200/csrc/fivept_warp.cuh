@@ -11,13 +11,11 @@
 //   E  real roots: half-warp 0 takes p on [-1, 1], half-warp 1 the reversed polynomial on (-1, 1); per level of the
 //      derivative chain lane = bracket (bracketed Newton, fivept.cuh), ballot compaction of the roots;
 //   F  back-substitution: lane = root, ballot compaction of the models.
-// Same mathematics and tolerances as fivept.cuh; the basis-vector order and a few summation orders differ, so the two
-// agree to rounding (tests/test_gpu_essential.py compares both with the oracle solver).
+// Same mathematics and tolerances as fivept.cuh (and the same null-space basis order: the conditioning of the 10x10
+// elimination depends on it); a few summation orders differ and divisions / square roots are reciprocal seeds refined by
+// Newton steps, so the two agree to rounding (tests/test_gpu_essential.py compares both with the oracle solver).
 #pragma once
 #include "fivept.cuh"
-#ifdef FIVEPT_DEBUG
-#include <cstdio>
-#endif
 
 namespace slamcu {
 
@@ -122,14 +120,7 @@ __device__ __noinline__ int root_level(const double* f, const double* cp, double
     if (!(x > lo && x < hi)) x = 0.5 * (lo + hi);
     double dxold = hi - lo;
     bool done = !sc;
-#ifdef FIVEPT_DEBUG
-    const long long tl0 = clock64();
-    int nit = 0;
-#endif
     for (int it = 0; it < 128; it++) {
-#ifdef FIVEPT_DEBUG
-        nit++;
-#endif
         double fx, dfx;
         horner_pd<DEG>(c, x, fx, dfx);
         if ((fx < 0.0) == up) lo = x; else hi = x;  // f(x) has the sign of f(lo): move lo
@@ -143,9 +134,6 @@ __device__ __noinline__ int root_level(const double* f, const double* cp, double
         done = done || stop;
         if (!__any_sync(FULL, !done)) break;
     }
-#ifdef FIVEPT_DEBUG
-    if (lane == 0) printf("deg %d its %d loop cycles %lld\n", DEG, nit, clock64() - tl0);
-#endif
     if (top) {  // two free Newton steps for the last bits, kept inside the final bracket
 #pragma unroll
         for (int r = 0; r < 2; r++) {
@@ -179,13 +167,6 @@ __device__ __forceinline__ double binom(int n, int k) {  // C(n, k), n <= 10
 __device__ int five_point_warp(const double2* x1, const double2* x2, const int* idx, double* S, double* models) {
     using namespace fpw;
     const int lane = threadIdx.x & 31;
-#ifdef FIVEPT_DEBUG
-    long long clk[8];
-    clk[0] = clock64();
-#define FP_MARK(i) clk[i] = clock64()
-#else
-#define FP_MARK(i)
-#endif
     double* B4 = S;            // [4][9]   null-space basis, kept to the end
     double* R = S + 36;        // 388 doubles reused by the stages
     // ================= A: null space of the 5x9 system, lane c < 9 holds column c =====================================
@@ -270,7 +251,6 @@ __device__ int five_point_warp(const double2* x1, const double2* x2, const int* 
             }
             bk[k] = bk[k] * fast_rsqrt(half_sum(bk[k] * bk[k]));
         }
-    FP_MARK(1);
     // ================= B: the ten cubic constraints ====================================================================
     double* Ep = R;              // [9][4]
     double* L = R + 36;          // [9][10]
@@ -330,7 +310,6 @@ __device__ int five_point_warp(const double2* x1, const double2* x2, const int* 
         Af[t] = (Dp[t] + Dp[20 + t]) + Dp[40 + t];
     }
     __syncwarp();
-    FP_MARK(2);
     // ================= C: Gauss-Jordan on the first ten columns, lane j < 20 holds column j ===========================
     double col[10];
     {
@@ -364,7 +343,6 @@ __device__ int five_point_warp(const double2* x1, const double2* x2, const int* 
             col[r] = col[r] - f * col[c];
         }
     }
-    FP_MARK(3);
     // ================= D: B(z) and det B(z) ============================================================================
     double* Ar = R;              // [6][10] rows 4..9, columns 10..19 of the reduced matrix
     double* bxyz = R + 60;       // [3][13] bx(4) by(4) b1(5)
@@ -424,7 +402,6 @@ __device__ int five_point_warp(const double2* x1, const double2* x2, const int* 
         det[lane] = v;
     }
     __syncwarp();
-    FP_MARK(4);
     // ================= E: real roots (half-warp 0: p on [-1, 1]; half-warp 1: reversed p on (-1, 1)) =================
     int lead = 0;
     while (lead < 11 && det[lead] == 0.0) lead++;
@@ -476,16 +453,6 @@ __device__ int five_point_warp(const double2* x1, const double2* x2, const int* 
     }
     __syncwarp();
     const int nz = min(m0 + m, n);
-#ifdef FIVEPT_DEBUG
-    if (lane == 0 && 0) {
-        printf("det:");
-        for (int t = 0; t < 11; t++) printf(" %.17g", det[t]);
-        printf("\nn %d m0 %d m1 %d nz %d roots:", n, m0, m1, nz);
-        for (int t = 0; t < nz; t++) printf(" %.17g", roots[t]);
-        printf("\n");
-    }
-#endif
-    FP_MARK(5);
     // ================= F: back-substitution, lane = root =================================================================
     bool good = false;
     double e[9];
@@ -530,11 +497,6 @@ __device__ int five_point_warp(const double2* x1, const double2* x2, const int* 
         for (int t = 0; t < 9; t++) models[pos * 9 + t] = e[t];
     }
     __syncwarp();
-#ifdef FIVEPT_DEBUG
-    FP_MARK(6);
-    if (lane == 0) printf("clk A %lld B %lld C %lld D %lld E %lld F %lld total %lld\n", clk[1] - clk[0], clk[2] - clk[1], clk[3] - clk[2],
-                          clk[4] - clk[3], clk[5] - clk[4], clk[6] - clk[5], clk[6] - clk[0]);
-#endif
     return __popc(gb);
 }
 
