@@ -179,7 +179,8 @@ int slamcu_knn2_hamming(slamcu_matcher* m, const uint8_t* d1, int n1, const uint
 /* ---- device-resident sequences: the batched / asynchronous path -------------------------------
  * A sequence holds up to max_frames frames of one size in HBM together with every intermediate of
  * the frontend (corner masks, raw corner lists, keypoints, descriptors, consecutive-frame matches).
- * All calls enqueue on the context's stream and return immediately unless stated otherwise. */
+ * All calls enqueue on the context's stream and return immediately unless stated otherwise.
+ * rows, cols and max_frames are at most 65535 (longer recordings are processed as several sequences). */
 int slamcu_sequence_create(slamcu_context* ctx, int rows, int cols, int max_frames, int max_raw_corners,
                            int max_keypoints, int desc_bytes, slamcu_sequence** out);
 void slamcu_sequence_destroy(slamcu_sequence* seq);

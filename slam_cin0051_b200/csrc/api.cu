@@ -346,7 +346,8 @@ int slamcu_sequence_create(slamcu_context* ctx, int rows, int cols, int max_fram
                            int desc_bytes, slamcu_sequence** out) {
     if (!ctx || !out) return SLAMCU_INVALID_ARGUMENT;
     *out = nullptr;
-    if (rows <= 0 || cols <= 0 || rows > 65535 || cols > 65535 || max_frames <= 0 || desc_bytes <= 0 || desc_bytes > 256)
+    // frames / frame pairs index grid dimensions y and z of the batched kernels: at most 65535 per sequence
+    if (rows <= 0 || cols <= 0 || rows > 65535 || cols > 65535 || max_frames <= 0 || max_frames > 65535 || desc_bytes <= 0 || desc_bytes > 256)
         return fail(ctx, SLAMCU_INVALID_ARGUMENT, "bad sequence geometry %dx%d x%d desc %d", rows, cols, max_frames,
                     desc_bytes);
     CU(ctx, cudaSetDevice(ctx->device));
