@@ -58,7 +58,11 @@ __device__ __forceinline__ void mul21_acc(const double* a, const double* b, doub
 // which only moves an iterate by an ulp.  b = 0 / inf / NaN propagate to a NaN quotient: the caller then bisects.
 __device__ __forceinline__ double fast_div(double a, double b) {
     double r;
+#if defined(SLAM_SIMT_EMULATION)
+    r = 1.0 / b;  // CPU emulation in the tests: any seed converges to the same refined value to an ulp
+#else
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+#endif
     double e = __fma_rn(-b, r, 1.0);
     r = __fma_rn(r, e, r);
     e = __fma_rn(-b, r, 1.0);
@@ -70,7 +74,11 @@ __device__ __forceinline__ double fast_div(double a, double b) {
 // 1 / sqrt(s) for the normalisations: rsqrt seed refined by two Newton steps (relative error ~1e-16)
 __device__ __forceinline__ double fast_rsqrt(double s) {
     double y;
+#if defined(SLAM_SIMT_EMULATION)
+    y = 1.0 / sqrt(s);
+#else
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(s));
+#endif
 #pragma unroll
     for (int k = 0; k < 2; k++) {
         const double e = __fma_rn(-(s * y), y, 1.0);  // 1 - s y^2
@@ -164,7 +172,7 @@ __device__ __forceinline__ double binom(int n, int k) {  // C(n, k), n <= 10
 // x1, x2: the problem's normalised correspondences, idx: the sample's 5 indices into them.  S: this warp's scratch (kFiveptScratchDoubles
 // doubles of shared memory).  models: up to kMaxModels row-major 3x3 matrices, |E|_F = 1 (global or shared).
 // Must be called by all 32 lanes of a warp; returns the number of models (uniform).
-__device__ int five_point_warp(const double2* x1, const double2* x2, const int* idx, double* S, double* models) {
+__device__ inline int five_point_warp(const double2* x1, const double2* x2, const int* idx, double* S, double* models) {
     using namespace fpw;
     const int lane = threadIdx.x & 31;
     double* B4 = S;            // [4][9]   null-space basis, kept to the end
