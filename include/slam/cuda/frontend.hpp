@@ -3,6 +3,8 @@
 //   slam::cuda::FeatureDetector  <->  slam::FeatureDetector  (include/slam/frontend/feature_detector.hpp:47-192)
 //   slam::cuda::FeatureMatcher   <->  slam::FeatureMatcher   (include/slam/frontend/feature_matcher.hpp:38-87)
 //   slam::cuda::EssentialSolver  <->  the cv::findEssentialMat call of PoseEstimator::estimate (pose_estimator.cpp:42)
+//   slam::cuda::Camera           <->  slam::Camera (common.hpp:67-190): calibration YAML, undistortImage
+//   slam::cuda::bgrToGray        <->  cv::cvtColor(BGR2GRAY) of Preprocessor::yield (preprocessor.cpp:136)
 //
 // Same constructors (a YAML path), same method names and argument order, same exception types and messages.  The
 // methods are templates over the container types so that the header works both inside the reference tree, with
@@ -259,6 +261,75 @@ private:
     Context& m_ctx;
     slamcu_matcher* m_matcher = nullptr;
 };
+
+// ---- slam::Camera (common.hpp:67-190) and the grayscale step of Preprocessor::yield (preprocessor.cpp:136) -------------
+class Camera {
+public:
+    // same argument meaning and error messages as the reference constructor (common.hpp:76-122)
+    explicit Camera(const std::filesystem::path& configPath, int cameraIndex = 0, Context& ctx = Context::instance())
+        : m_ctx(ctx), m_cameraIndex(cameraIndex) {
+        YamlLite fs(configPath.string());
+        if (!fs.isOpened()) throw std::runtime_error("Could not open calibration file: " + configPath.string());
+        const std::string kKey = "K" + std::to_string(cameraIndex), dKey = "D" + std::to_string(cameraIndex);
+        const std::vector<double> K = fs.getDoubles(kKey), D = fs.getDoubles(dKey), size = fs.getDoubles("ImageSize");
+        if (K.size() < 9 || D.empty()) throw std::runtime_error("Could not find keys " + kKey + " or " + dKey + " in file.");
+        for (int i = 0; i < 9; i++) m_K[i] = K[static_cast<size_t>(i)];
+        m_D = D;
+        m_width = size.size() > 0 ? static_cast<int>(size[0]) : 0;
+        m_height = size.size() > 1 ? static_cast<int>(size[1]) : 0;
+    }
+    const double* getIntrinsicMatrix() const { return m_K; }                 // row-major 3x3
+    const std::vector<double>& getDistortionCoefficients() const { return m_D; }
+    int width() const { return m_width; }
+    int height() const { return m_height; }
+    void intrinsics4(double K4[4]) const { K4[0] = m_K[0]; K4[1] = m_K[4]; K4[2] = m_K[2]; K4[3] = m_K[5]; }
+
+    // Camera::undistortImage (common.hpp:127-173): raw = rows x cols 8-bit grayscale (row-major, .data() / .rows() /
+    // .cols()); out(i, j) receives the reference's value / 255.0 image (any matrix type with resize(rows, cols) and
+    // operator()(i, j): Eigen::MatrixXd in the reference tree).  Same exceptions as the reference (:130-135).
+    template <class Gray, class Out>
+    void undistortImage(const Gray& raw, Out& out) const {
+        std::vector<double> f64;
+        run(raw, nullptr, &f64);
+        const int rows = static_cast<int>(raw.rows()), cols = static_cast<int>(raw.cols());
+        out.resize(rows, cols);
+        for (int i = 0; i < rows; i++)
+            for (int j = 0; j < cols; j++) out(i, j) = f64[static_cast<size_t>(i) * cols + j];
+    }
+    // the same gather emitted as the 8-bit image the detector consumes (the /255.0 double image is a dead end in the
+    // reference: nothing downstream reads it)
+    template <class Gray>
+    void undistortImageU8(const Gray& raw, Gray& out) const {
+        out.resize(raw.rows(), raw.cols());
+        run(raw, out.data(), nullptr);
+    }
+
+private:
+    template <class Gray>
+    void run(const Gray& raw, uint8_t* u8, std::vector<double>* f64) const {
+        const int rows = static_cast<int>(raw.rows()), cols = static_cast<int>(raw.cols());
+        if (rows == 0 || cols == 0) throw std::runtime_error("Input image is empty.");
+        if (cols != m_width || rows != m_height) throw std::runtime_error("Input image size does not match camera image size.");
+        double K4[4];
+        intrinsics4(K4);
+        double D4[4] = {0, 0, 0, 0};  // k1, k2, p1, p2; k3 is loaded but unused by the reference (:113, :151-154)
+        for (size_t i = 0; i < 4 && i < m_D.size(); i++) D4[i] = m_D[i];
+        if (f64) f64->assign(static_cast<size_t>(rows) * cols, 0.0);
+        m_ctx.check(slamcu_undistort(m_ctx.get(), raw.data(), rows, cols, cols, K4, D4, u8, f64 ? f64->data() : nullptr));
+    }
+    Context& m_ctx;
+    int m_cameraIndex = 0, m_width = 0, m_height = 0;
+    double m_K[9]{};
+    std::vector<double> m_D;
+};
+
+// cv::cvtColor(image, image, cv::COLOR_BGR2GRAY) of Preprocessor::yield (preprocessor.cpp:136): bgr = rows x cols x 3
+// interleaved bytes; gray receives rows x cols bytes (bit-exact with OpenCV's fixed-point formula)
+template <class Gray>
+void bgrToGray(const uint8_t* bgr, int rows, int cols, Gray& gray, Context& ctx = Context::instance()) {
+    gray.resize(rows, cols);
+    ctx.check(slamcu_bgr_to_gray(ctx.get(), bgr, rows, cols, cols * 3, gray.data(), cols));
+}
 
 // ---- the cv::findEssentialMat call of PoseEstimator::estimate -------------------------------------------------------
 struct EssentialResult {

@@ -1,11 +1,13 @@
-// yaml_lite.hpp -- reader for the flat `key: value` OpenCV-FileStorage YAML files the reference's constructors parse
-// (feature_detector.hpp:54-94, feature_matcher.cpp:19-59).  Used by the CUDA adapters so that they do not need
-// OpenCV just to read six scalars; where OpenCV is available cv::FileStorage gives the same values for these files.
+// yaml_lite.hpp -- reader for the OpenCV-FileStorage YAML files the reference's constructors parse: flat `key: value`
+// scalars (feature_detector.hpp:54-94, feature_matcher.cpp:19-59), flow sequences (`ImageSize: [w, h]`) and
+// `!!opencv-matrix` nodes (camera.yml: K<i>, D<i>; common.hpp:76-122).  Used by the CUDA adapters so that they do not
+// need OpenCV just to read a dozen numbers; where OpenCV is available cv::FileStorage gives the same values.
 #pragma once
 #include <cstdlib>
 #include <fstream>
 #include <map>
 #include <string>
+#include <vector>
 
 namespace slam::cuda {
 
@@ -14,7 +16,7 @@ public:
     explicit YamlLite(const std::string& path) {
         std::ifstream in(path);
         m_open = in.good();
-        std::string line;
+        std::string line, last;
         while (std::getline(in, line)) {
             std::string s;
             char quote = 0;
@@ -24,13 +26,18 @@ public:
                 else if (c == '#') break;
                 s.push_back(c);
             }
-            if (s.empty() || s[0] == '%' || s.rfind("---", 0) == 0 || s[0] == ' ' || s[0] == '\t') continue;
+            if (!s.empty() && (s[0] == ' ' || s[0] == '\t')) {  // continuation of the current node (opencv-matrix body)
+                if (!last.empty()) m_values[last] += " " + trim(s);
+                continue;
+            }
+            if (s.empty() || s[0] == '%' || s.rfind("---", 0) == 0) continue;
             const size_t colon = s.find(':');
             if (colon == std::string::npos) continue;
             std::string key = trim(s.substr(0, colon)), val = trim(s.substr(colon + 1));
             if (val.size() >= 2 && (val.front() == '"' || val.front() == '\'') && val.back() == val.front())
                 val = val.substr(1, val.size() - 2);
             m_values[key] = val;
+            last = key;
         }
     }
     bool isOpened() const { return m_open; }
@@ -46,6 +53,27 @@ public:
     float getFloat(const std::string& key) const {
         auto it = m_values.find(key);
         return it == m_values.end() ? 0.0F : static_cast<float>(std::strtod(it->second.c_str(), nullptr));
+    }
+    // the numbers of a flow sequence `[a, b, ...]`, or of the `data: [...]` array of an !!opencv-matrix node
+    std::vector<double> getDoubles(const std::string& key) const {
+        std::vector<double> out;
+        auto it = m_values.find(key);
+        if (it == m_values.end()) return out;
+        const std::string& v = it->second;
+        size_t from = v.find("data:");
+        from = v.find('[', from == std::string::npos ? 0 : from);
+        const size_t to = v.find(']', from == std::string::npos ? 0 : from);
+        if (from == std::string::npos || to == std::string::npos) return out;
+        const char* p = v.c_str() + from + 1;
+        const char* end = v.c_str() + to;
+        while (p < end) {
+            char* q = nullptr;
+            const double d = std::strtod(p, &q);
+            if (q == p) { p++; continue; }
+            out.push_back(d);
+            p = q;
+        }
+        return out;
     }
     std::string getString(const std::string& key) const {
         auto it = m_values.find(key);

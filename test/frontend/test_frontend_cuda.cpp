@@ -4,6 +4,8 @@
 // the oracle.  Images are binary PGM (the reference reads PNG through OpenCV, which this image does not have in C++).
 //
 //   test_frontend_cuda image0.pgm image1.pgm detector.yml matcher.yml [fx fy cx cy]
+//   test_frontend_cuda --camera camera.yml [index] image.pgm      (test/preprocessing/test_preprocessor.cpp's image path:
+//                                                                  BGR2GRAY + Camera::undistortImage, digests of both)
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
@@ -33,7 +35,55 @@ static unsigned long long fnv(const void* p, size_t n, unsigned long long h = 14
     return h;
 }
 
+static int camera_main(int argc, char** argv) {
+    try {
+        const int index = argc >= 5 ? std::atoi(argv[3]) : 0;
+        const GrayMatrix img = read_pgm(argv[argc - 1]);
+        Camera cam(argv[2], index);
+        std::printf("camera %dx%d K", cam.width(), cam.height());
+        for (int i = 0; i < 9; i++) std::printf(" %.17g", cam.getIntrinsicMatrix()[i]);
+        std::printf(" D");
+        for (double d : cam.getDistortionCoefficients()) std::printf(" %.17g", d);
+        std::printf("\n");
+        RowMajorMatrix<double> und;
+        cam.undistortImage(img, und);
+        GrayMatrix und8;
+        cam.undistortImageU8(img, und8);
+        std::printf("undistort f64 %016llx u8 %016llx\n", fnv(und.data(), static_cast<size_t>(und.rows() * und.cols()) * sizeof(double)),
+                    fnv(und8.data(), static_cast<size_t>(und8.rows() * und8.cols())));
+        // a deterministic colour image from the gray one: B = v, G = 255 - v, R = v / 2
+        std::vector<uint8_t> bgr(static_cast<size_t>(img.rows() * img.cols()) * 3);
+        for (long i = 0; i < img.rows() * img.cols(); i++) {
+            const uint8_t v = img.data()[i];
+            bgr[3 * i] = v; bgr[3 * i + 1] = static_cast<uint8_t>(255 - v); bgr[3 * i + 2] = static_cast<uint8_t>(v >> 1);
+        }
+        GrayMatrix gray;
+        bgrToGray(bgr.data(), static_cast<int>(img.rows()), static_cast<int>(img.cols()), gray);
+        std::printf("gray %016llx\n", fnv(gray.data(), static_cast<size_t>(gray.rows() * gray.cols())));
+        try {
+            GrayMatrix small(10, 10);
+            RowMajorMatrix<double> o;
+            cam.undistortImage(small, o);
+            std::fprintf(stderr, "expected std::runtime_error\n");
+            return -1;
+        } catch (const std::runtime_error& e) {
+            std::printf("mismatch: %s\n", e.what());
+        }
+        try {
+            Camera missing(argv[2], 7);
+            return -1;
+        } catch (const std::runtime_error& e) {
+            std::printf("missing: %s\n", e.what());
+        }
+    } catch (const std::exception& e) {
+        std::fprintf(stderr, "Exception: %s\n", e.what());
+        return -1;
+    }
+    return 0;
+}
+
 int main(int argc, char** argv) {
+    if (argc >= 4 && std::string(argv[1]) == "--camera") return camera_main(argc, argv);
     if (argc < 5) {
         std::fprintf(stderr, "usage: %s image0.pgm image1.pgm detector.yml matcher.yml [fx fy cx cy]\n", argv[0]);
         return -1;

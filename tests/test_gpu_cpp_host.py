@@ -89,3 +89,32 @@ def test_slam_bench_cli():
     r = json.loads(out.stdout.strip().splitlines()[-1])
     assert r["frames_per_s_resident"] > 0 and r["frames_per_s_e2e"] > 0 and r["overflowed_frames"] == 0
     assert r["keypoints_per_frame"] > 500 and r["gpu_launches"] > 0
+
+
+def test_cpp_camera_adapter(tmp_path, oracle):
+    """slam::cuda::Camera (calibration YAML with !!opencv-matrix nodes, undistortImage) and bgrToGray through the C++
+    adapters: digests equal the C++ restatement of Camera::undistortImage and cv2's BGR2GRAY; the reference's error
+    messages for a size mismatch and a missing camera index."""
+    cv2 = pytest.importorskip("cv2")
+    exe = os.path.join(BUILD, "test_frontend_cuda")
+    img = load_gray("images/0000000000.png")  # 1392 x 512, the size camera.yml declares
+    write_pgm(tmp_path / "k.pgm", img)
+    out = subprocess.run([exe, "--camera", os.path.join(DATA, "camera.yml"), "0", str(tmp_path / "k.pgm")],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    lines = out.stdout.strip().splitlines()
+    from slam_cin0051_b200.config import read_yaml
+    cfg = read_yaml(os.path.join(DATA, "camera.yml"))
+    K = np.asarray(cfg["K0"], np.float64).reshape(3, 3)
+    D = np.asarray(cfg["D0"], np.float64).reshape(-1)
+    head = lines[0].split()
+    assert head[:2] == ["camera", "1392x512"]
+    assert np.array_equal(np.array(head[3:12], np.float64), K.ravel()) and np.array_equal(np.array(head[13:], np.float64), D)
+    K4, D4 = (K[0, 0], K[1, 1], K[0, 2], K[1, 2]), tuple(D[:4])
+    want = oracle.undistort(img, K4, D4)
+    want8 = np.rint(want * 255.0).astype(np.uint8)
+    assert lines[1].split() == ["undistort", "f64", fnv(want.tobytes()), "u8", fnv(want8.tobytes())]
+    bgr = np.stack([img, 255 - img, img >> 1], -1)
+    assert lines[2].split() == ["gray", fnv(cv2.cvtColor(bgr, cv2.COLOR_BGR2GRAY).tobytes())]
+    assert lines[3] == "mismatch: Input image size does not match camera image size."
+    assert lines[4] == "missing: Could not find keys K7 or D7 in file."
