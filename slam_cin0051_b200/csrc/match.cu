@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(QT) match_kernel(MatchJob job, int with_kp, in
             uint32_t qq[8];
 #pragma unroll
             for (int w = 0; w < 8; w++) qq[w] = qd[W > 0 ? (w < W ? w : 0) : 0];
-#pragma unroll 8
+#pragma unroll 4
             for (int j = 0; j < cnt; j++) {
                 const uint4 a = *reinterpret_cast<const uint4*>(tile + j * 8);
                 const uint4 b = *reinterpret_cast<const uint4*>(tile + j * 8 + 4);
