@@ -81,3 +81,29 @@ def test_ransac_with_the_warp_solver_equals_cv2_golden(libs, name):
     E, mask, good = eo.find_essential(g["p1"], g["p2"], k4(g["K"]), solver=lambda a, b: solve(hw, "hw_five_point_warp", a, b)[0])
     assert good == int(g["mask"].sum()) and np.array_equal(mask, g["mask"])
     assert e_diff(E, g["E"]) < 1e-9
+
+
+def test_warp_solver_on_degenerate_samples(libs):
+    """Inputs the RANSAC kernels do meet (scene cuts, pure translation over a plane, repeated points): the device routine
+    must terminate and return at most ten finite unit-norm matrices that satisfy the five epipolar constraints (how many
+    real roots a degenerate polynomial has is decided by rounding, so the count is not compared with the thread solver)."""
+    _, hw = libs
+    rng = np.random.default_rng(7)
+    base = rng.uniform(-0.5, 0.5, (5, 2))
+    cases = {
+        "identical points": (np.repeat(base[:1], 5, 0), np.repeat(base[:1], 5, 0)),
+        "zero motion": (base, base.copy()),
+        "pure translation of a plane": (base, base + np.array([0.01, 0.0])),
+        "two coincident correspondences": (np.vstack([base[:4], base[:1]]), np.vstack([base[:4] + 0.02, base[:1] + 0.02])),
+        "collinear": (np.stack([np.linspace(-0.4, 0.4, 5), np.zeros(5)], 1), np.stack([np.linspace(-0.38, 0.41, 5), np.full(5, 0.01)], 1)),
+        "huge coordinates": (base * 1e6, base * 1e6 + 3.0),
+        "tiny coordinates": (base * 1e-9, base * 1e-9 + 1e-12),
+        "integer pixels, unnormalised": (np.rint(base * 600 + 320), np.rint(base * 600 + 322)),
+    }
+    for name, (a, b) in cases.items():
+        got = solve(hw, "hw_five_point_warp", a, b)[0]
+        assert len(got) <= 10, name
+        scale = max(1.0, float(np.abs(a).max())) * max(1.0, float(np.abs(b).max()))
+        for M in got:
+            assert np.isfinite(M).all() and abs(np.sqrt((M * M).sum()) - 1.0) < 1e-9, name
+            assert max(abs(np.array([*b[j], 1.0]) @ M @ np.array([*a[j], 1.0])) for j in range(5)) < 1e-9 * scale, name
