@@ -175,6 +175,10 @@ int slamcu_match(slamcu_matcher* m, const uint8_t* d1, int n1, int width1, const
  * This is both the sweep benchmark kernel (BASELINE.json config 5) and cv::BFMatcher::knnMatch(k=2). */
 int slamcu_knn2_hamming(slamcu_matcher* m, const uint8_t* d1, int n1, const uint8_t* d2, int n2, int width,
                         slamcu_knn2* out);
+/* Tuning / test knob of the single-problem calls above: the train set is searched in `n_slices` slices (an extra grid
+ * dimension; the per-slice top-2 lists are merged by (distance, index), which is exact).  0 = automatic (fill the
+ * device), 1 = one slice, at most 32.  Results do not depend on it. */
+int slamcu_matcher_set_train_slices(slamcu_matcher* m, int n_slices);
 
 /* ---- device-resident sequences: the batched / asynchronous path -------------------------------
  * A sequence holds up to max_frames frames of one size in HBM together with every intermediate of

@@ -69,6 +69,7 @@ SYMBOLS = {
     "slamcu_matcher_destroy": (None, [_vp]),
     "slamcu_match": (_i, [_vp, _u8p, _i, _i, _u8p, _i, _i, _vp, _i, _vp, _i, _vp, _i, _ip]),
     "slamcu_knn2_hamming": (_i, [_vp, _u8p, _i, _u8p, _i, _i, _vp]),
+    "slamcu_matcher_set_train_slices": (_i, [_vp, _i]),
     "slamcu_sequence_create": (_i, [_vp, _i, _i, _i, _i, _i, _i, C.POINTER(_vp)]),
     "slamcu_sequence_destroy": (None, [_vp]),
     "slamcu_sequence_upload": (_i, [_vp, _i, _i, _u8p, _i]),

@@ -13,9 +13,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libslamcu.so")
 SOURCES = ["api.cu", "fast_ref.cu", "sortnms.cu", "describe_ref.cu", "match.cu", "prep.cu", "ransac.cu", "microbench.cu", "orb.cu", "essential.cu"]
-NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-fmad=false",
-              "-Xcompiler", "-fPIC", "--use_fast_math=false"]
-NVCC_FLAGS = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"]
+# Exactness-critical: -fmad=false and NO --use_fast_math (every bit-exactness guarantee depends on them; CMakeLists.txt
+# passes the same pair, tests/test_cabi_and_host.py checks both recipes).
+EXACT_FLAGS = ["-fmad=false"]
+NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", *EXACT_FLAGS, "-Xcompiler", "-fPIC"]
 
 
 def _newest(paths):

@@ -2,6 +2,7 @@
 // across the boundary, no CPU fallback: a call either enqueues CUDA work or returns an error status.
 #include <cstdarg>
 #include <cstdio>
+#include <climits>
 #include <cstring>
 #include <cmath>
 #include <new>
@@ -137,6 +138,55 @@ int dev_alloc(slamcu_context* ctx, T** p, size_t count, std::vector<void*>& owne
 
 int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
+// Camera::undistortImage's per-pixel source index (common.hpp:143-162) with the host libm the reference itself calls
+// (Eigen's r.pow(4) is std::pow(r, 4.0)); -1 = outside the image
+int undistort_index_host(int i, int j, int rows, int cols, const CamParams& c) {
+    const double x = ((double)j - c.cx) / c.fx;
+    const double y = ((double)i - c.cy) / c.fy;
+    const double r = std::sqrt(x * x + y * y);
+    const double r2 = r * r;
+    const double r4 = std::pow(r, 4.0);
+    const double xd = x * (1 + c.k1 * r2 + c.k2 * r4) + 2 * c.p1 * x * y + c.p2 * (r2 + 2 * (x * x));
+    const double yd = y * (1 + c.k1 * r2 + c.k2 * r4) + 2 * c.p2 * x * y + c.p1 * (r2 + 2 * (y * y));
+    const double ud = c.fx * xd + c.cx;
+    const double vd = c.fy * yd + c.cy;
+    const int u = static_cast<int>(std::round(ud)), v = static_cast<int>(std::round(vd));
+    return (u >= 0 && v >= 0 && u < cols && v < rows) ? v * cols + u : -1;
+}
+
+// Device map + host fix-up of the pixels that sit on a rounding boundary (prep.cu: undistort_map_kernel).  `fix` is a
+// device scratch of 1 + kUndistFixCap ints.  Synchronises the stream (constructor-time work: once per camera).
+constexpr int kUndistFixCap = 1 << 16;
+int build_undistort_map(slamcu_context* ctx, int rows, int cols, const CamParams& cam, int* d_map, int* d_fix) {
+    ctx->launches += launch_undistort_map(rows, cols, cam, d_map, d_fix, kUndistFixCap, ctx->stream);
+    int n_fix = 0;
+    CU(ctx, cudaMemcpyAsync(&n_fix, d_fix, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    if (n_fix == 0) return SLAMCU_OK;
+    if (n_fix > kUndistFixCap) {  // degenerate calibration (e.g. NaNs): the whole map on the host
+        std::vector<int> all((size_t)rows * cols);
+        for (int i = 0; i < rows; i++)
+            for (int j = 0; j < cols; j++) all[(size_t)i * cols + j] = undistort_index_host(i, j, rows, cols, cam);
+        CU(ctx, cudaMemcpyAsync(d_map, all.data(), all.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));
+        return SLAMCU_OK;
+    }
+    std::vector<int> idx((size_t)n_fix);
+    CU(ctx, cudaMemcpyAsync(idx.data(), d_fix + 1, (size_t)n_fix * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int k = 0; k < n_fix; k++) {
+        const int v = undistort_index_host(idx[k] / cols, idx[k] % cols, rows, cols, cam);
+        CU(ctx, cudaMemcpyAsync(d_map + idx[k], &v, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        CU(ctx, cudaStreamSynchronize(ctx->stream));  // v lives on this stack frame
+    }
+    return SLAMCU_OK;
+}
+
+// every failure leaves its own message: slamcu_last_error() never reports an earlier, unrelated call
+int bad_args(slamcu_context* ctx, const char* fn) {
+    return fail(ctx, SLAMCU_INVALID_ARGUMENT, "%s: null or mismatched handle / pointer argument", fn);
+}
+
 }  // namespace
 
 struct ProfGuard {
@@ -150,6 +200,8 @@ struct slamcu_sequence {
     int max_frames = 0;
     unsigned long long* sort_keys = nullptr;  // [F][cap_kp]
     int* h_counts = nullptr;                  // pinned [F][4]
+    int* h_status = nullptr;                  // pinned [F]: status words of the latest slamcu_sequence_process call
+    int h_status_n = 0;                       // ... and how many frames it covered
     uint8_t* stage = nullptr;                 // [F][rows][cols] dense landing zone of linear H2D copies (lazy)
     uint8_t* prep_stage = nullptr;            // landing zone of slamcu_sequence_prepare (gray or BGR host frames; lazy)
     size_t prep_stage_bytes = 0;
@@ -198,6 +250,7 @@ struct slamcu_matcher {
     uint32_t* ors = nullptr;
     int* counts = nullptr;  // nq, nt, n_match, status
     int cap1 = 0, cap2 = 0, cap_words = 0;
+    int forced_slices = 0;  // slamcu_matcher_set_train_slices
 };
 
 extern "C" {
@@ -268,14 +321,14 @@ void slamcu_destroy(slamcu_context* ctx) {
 const char* slamcu_last_error(const slamcu_context* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 
 int slamcu_set_stream(slamcu_context* ctx, void* cuda_stream) {
-    if (!ctx) return SLAMCU_INVALID_ARGUMENT;
+    if (!ctx) return bad_args(ctx, __func__);
     ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
     return SLAMCU_OK;
 }
 void* slamcu_get_stream(slamcu_context* ctx) { return ctx ? ctx->stream : nullptr; }
 
 int slamcu_synchronize(slamcu_context* ctx) {
-    if (!ctx) return SLAMCU_INVALID_ARGUMENT;
+    if (!ctx) return bad_args(ctx, __func__);
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     if (ctx->s_in) CU(ctx, cudaStreamSynchronize(ctx->s_in));
     if (ctx->s_out) CU(ctx, cudaStreamSynchronize(ctx->s_out));
@@ -293,7 +346,7 @@ void slamcu_free_pinned(void* p) {
 }
 
 int slamcu_popc_peak(slamcu_context* ctx, double* gpopc_per_s) {
-    if (!ctx || !gpopc_per_s) return SLAMCU_INVALID_ARGUMENT;
+    if (!ctx || !gpopc_per_s) return bad_args(ctx, __func__);
     CU(ctx, cudaSetDevice(ctx->device));
     int rc = ensure_scratch(ctx, 4096);
     if (rc != SLAMCU_OK) return rc;
@@ -320,7 +373,7 @@ int slamcu_popc_peak(slamcu_context* ctx, double* gpopc_per_s) {
 }
 
 int slamcu_profile_enable(slamcu_context* ctx, int on) {
-    if (!ctx) return SLAMCU_INVALID_ARGUMENT;
+    if (!ctx) return bad_args(ctx, __func__);
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->prof.reset();
     ctx->profiling = on != 0;
@@ -328,7 +381,7 @@ int slamcu_profile_enable(slamcu_context* ctx, int on) {
 }
 
 int slamcu_profile_read(slamcu_context* ctx, int index, char* name, int name_cap, double* total_ms, int64_t* launches) {
-    if (!ctx) return SLAMCU_INVALID_ARGUMENT;
+    if (!ctx) return bad_args(ctx, __func__);
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->prof.collect();
     if (index < 0 || index >= (int)ctx->prof.acc.size()) return SLAMCU_INVALID_ARGUMENT;  // end of list
@@ -344,7 +397,7 @@ int slamcu_profile_read(slamcu_context* ctx, int index, char* name, int name_cap
 /* ---------------------------------------------------------------------------------------------- */
 int slamcu_sequence_create(slamcu_context* ctx, int rows, int cols, int max_frames, int max_raw, int max_kp,
                            int desc_bytes, slamcu_sequence** out) {
-    if (!ctx || !out) return SLAMCU_INVALID_ARGUMENT;
+    if (!ctx || !out) return bad_args(ctx, __func__);
     *out = nullptr;
     // frames / frame pairs index grid dimensions y and z of the batched kernels: at most 65535 per sequence
     if (rows <= 0 || cols <= 0 || rows > 65535 || cols > 65535 || max_frames <= 0 || max_frames > 65535 || desc_bytes <= 0 || desc_bytes > 256)
@@ -424,6 +477,7 @@ void slamcu_sequence_destroy(slamcu_sequence* s) {
     for (void* p : s->ess_owned) cudaFree(p);
     if (s->ess_work) cudaFree(s->ess_work);
     if (s->h_counts) cudaFreeHost(s->h_counts);
+    if (s->h_status) cudaFreeHost(s->h_status);
     delete s;
 }
 
@@ -459,7 +513,7 @@ static void seq_repitch(slamcu_sequence* s, int first, int n, cudaStream_t st) {
 }
 
 int slamcu_sequence_upload(slamcu_sequence* s, int first, int n, const uint8_t* host, int stride) {
-    if (!s || !host) return SLAMCU_INVALID_ARGUMENT;
+    if (!s || !host) return bad_args((s ? s->ctx : nullptr), __func__);
     slamcu_context* ctx = s->ctx;
     if (first < 0 || n < 0 || first + n > s->max_frames || stride < s->v.cols)
         return fail(ctx, SLAMCU_INVALID_ARGUMENT, "upload range [%d,%d) / stride %d invalid", first, first + n, stride);
@@ -478,7 +532,7 @@ int slamcu_sequence_upload(slamcu_sequence* s, int first, int n, const uint8_t* 
 
 int slamcu_sequence_prepare(slamcu_sequence* s, int first, int n, const uint8_t* host, int channels, int stride, const double* K4,
                             const double* D4) {
-    if (!s || !host) return SLAMCU_INVALID_ARGUMENT;
+    if (!s || !host) return bad_args((s ? s->ctx : nullptr), __func__);
     slamcu_context* ctx = s->ctx;
     const SeqView& v = s->v;
     if (first < 0 || n < 0 || first + n > s->max_frames || (channels != 1 && channels != 3) || stride < v.cols * channels)
@@ -499,9 +553,12 @@ int slamcu_sequence_prepare(slamcu_sequence* s, int first, int n, const uint8_t*
     if (K4) {
         const double key[8] = {K4[0], K4[1], K4[2], K4[3], D4[0], D4[1], D4[2], D4[3]};
         if (!s->has_undist || memcmp(key, s->undist_key, sizeof key) != 0) {
-            if (!s->undist_map) CU(ctx, cudaMalloc(reinterpret_cast<void**>(&s->undist_map), (size_t)v.rows * v.cols * sizeof(int)));
+            if ((long long)v.rows * v.cols > INT_MAX) return fail(ctx, SLAMCU_UNSUPPORTED, "undistortion map: rows * cols exceeds INT_MAX");
+            if (!s->undist_map)
+                CU(ctx, cudaMalloc(reinterpret_cast<void**>(&s->undist_map), ((size_t)v.rows * v.cols + 1 + kUndistFixCap) * sizeof(int)));
             CamParams cam{K4[0], K4[1], K4[2], K4[3], D4[0], D4[1], D4[2], D4[3]};
-            ctx->launches += launch_undistort_map(v.rows, v.cols, cam, s->undist_map, ctx->stream);
+            int rcm = build_undistort_map(ctx, v.rows, v.cols, cam, s->undist_map, s->undist_map + (size_t)v.rows * v.cols);
+            if (rcm != SLAMCU_OK) return rcm;
             memcpy(s->undist_key, key, sizeof key);
             s->has_undist = true;
         }
@@ -513,7 +570,7 @@ int slamcu_sequence_prepare(slamcu_sequence* s, int first, int n, const uint8_t*
 }
 
 int slamcu_sequence_image(slamcu_sequence* s, int f, uint8_t* out, int out_stride) {
-    if (!s || !out) return SLAMCU_INVALID_ARGUMENT;
+    if (!s || !out) return bad_args((s ? s->ctx : nullptr), __func__);
     slamcu_context* ctx = s->ctx;
     if (f < 0 || f >= s->max_frames || out_stride < s->v.cols) return fail(ctx, SLAMCU_INVALID_ARGUMENT, "bad frame index / stride");
     CU(ctx, cudaSetDevice(ctx->device));
@@ -524,7 +581,7 @@ int slamcu_sequence_image(slamcu_sequence* s, int f, uint8_t* out, int out_strid
 }
 
 int slamcu_sequence_frames_device(slamcu_sequence* s, void** dptr, int* pitch, int64_t* frame_bytes) {
-    if (!s) return SLAMCU_INVALID_ARGUMENT;
+    if (!s) return bad_args((s ? s->ctx : nullptr), __func__);
     if (dptr) *dptr = s->v.img;
     if (pitch) *pitch = s->v.pitch;
     if (frame_bytes) *frame_bytes = (int64_t)s->v.frame_bytes;
@@ -716,7 +773,7 @@ static int seq_extract_orb(slamcu_sequence* s, slamcu_detector* det, int first, 
 }
 
 int slamcu_sequence_octaves(slamcu_sequence* s, int f, int32_t* octaves, int capacity) {
-    if (!s || !octaves) return SLAMCU_INVALID_ARGUMENT;
+    if (!s || !octaves) return bad_args((s ? s->ctx : nullptr), __func__);
     slamcu_context* ctx = s->ctx;
     if (!s->has_orb) return fail(ctx, SLAMCU_UNSUPPORTED, "sequence was not extracted in ORB mode");
     if (f < 0 || f >= s->max_frames) return fail(ctx, SLAMCU_INVALID_ARGUMENT, "bad frame index");
@@ -733,7 +790,7 @@ int slamcu_sequence_octaves(slamcu_sequence* s, int f, int32_t* octaves, int cap
 }
 
 int slamcu_sequence_extract(slamcu_sequence* s, slamcu_detector* det, int first, int n) {
-    if (!s || !det || s->ctx != det->ctx) return SLAMCU_INVALID_ARGUMENT;
+    if (!s || !det || s->ctx != det->ctx) return bad_args((s ? s->ctx : nullptr), __func__);
     slamcu_context* ctx = s->ctx;
     if (first < 0 || n < 0 || first + n > s->max_frames) return fail(ctx, SLAMCU_INVALID_ARGUMENT, "bad frame range");
     if (det->mode == SLAMCU_MODE_ORB) return n == 0 ? SLAMCU_OK : seq_extract_orb(s, det, first, n);
@@ -747,7 +804,7 @@ int slamcu_sequence_extract(slamcu_sequence* s, slamcu_detector* det, int first,
 }
 
 int slamcu_sequence_match(slamcu_sequence* s, slamcu_matcher* m, int first, int n_pairs, int with_kp) {
-    if (!s || !m || s->ctx != m->ctx) return SLAMCU_INVALID_ARGUMENT;
+    if (!s || !m || s->ctx != m->ctx) return bad_args((s ? s->ctx : nullptr), __func__);
     slamcu_context* ctx = s->ctx;
     if (first < 0 || n_pairs < 0 || first + n_pairs + 1 > s->max_frames)
         return fail(ctx, SLAMCU_INVALID_ARGUMENT, "bad pair range");
@@ -784,7 +841,7 @@ int slamcu_sequence_match(slamcu_sequence* s, slamcu_matcher* m, int first, int 
 }
 
 int slamcu_sequence_counts(slamcu_sequence* s, int first, int n, int32_t* counts4) {
-    if (!s || !counts4) return SLAMCU_INVALID_ARGUMENT;
+    if (!s || !counts4) return bad_args((s ? s->ctx : nullptr), __func__);
     slamcu_context* ctx = s->ctx;
     if (first < 0 || n < 0 || first + n > s->max_frames) return fail(ctx, SLAMCU_INVALID_ARGUMENT, "bad frame range");
     if (n == 0) return SLAMCU_OK;
@@ -806,7 +863,7 @@ int slamcu_sequence_counts(slamcu_sequence* s, int first, int n, int32_t* counts
 
 int slamcu_sequence_frame(slamcu_sequence* s, int f, slamcu_keypoint* kps, uint8_t* desc, int desc_stride, int capacity,
                           int* n_out) {
-    if (!s || !n_out) return SLAMCU_INVALID_ARGUMENT;
+    if (!s || !n_out) return bad_args((s ? s->ctx : nullptr), __func__);
     slamcu_context* ctx = s->ctx;
     if (f < 0 || f >= s->max_frames) return fail(ctx, SLAMCU_INVALID_ARGUMENT, "bad frame index");
     int32_t c[4];
@@ -832,7 +889,7 @@ int slamcu_sequence_frame(slamcu_sequence* s, int f, slamcu_keypoint* kps, uint8
 }
 
 int slamcu_sequence_matches(slamcu_sequence* s, int f, slamcu_dmatch* matches, int capacity, int* n_out) {
-    if (!s || !n_out) return SLAMCU_INVALID_ARGUMENT;
+    if (!s || !n_out) return bad_args((s ? s->ctx : nullptr), __func__);
     slamcu_context* ctx = s->ctx;
     if (f < 0 || f >= s->max_frames) return fail(ctx, SLAMCU_INVALID_ARGUMENT, "bad frame index");
     int32_t c[4];
@@ -865,7 +922,7 @@ static int seq_download_desc(slamcu_sequence* s, int first, int n, uint8_t* desc
 
 int slamcu_sequence_download(slamcu_sequence* s, int first, int n, slamcu_keypoint* kps, uint8_t* desc, slamcu_dmatch* matches,
                              int32_t* counts4) {
-    if (!s) return SLAMCU_INVALID_ARGUMENT;
+    if (!s) return bad_args((s ? s->ctx : nullptr), __func__);
     slamcu_context* ctx = s->ctx;
     if (first < 0 || n < 0 || first + n > s->max_frames) return fail(ctx, SLAMCU_INVALID_ARGUMENT, "bad frame range");
     if (n == 0) return SLAMCU_OK;
@@ -891,10 +948,19 @@ int slamcu_sequence_download(slamcu_sequence* s, int first, int n, slamcu_keypoi
 }
 
 int slamcu_sequence_wait(slamcu_sequence* s) {
-    if (!s) return SLAMCU_INVALID_ARGUMENT;
+    if (!s) return bad_args((s ? s->ctx : nullptr), __func__);
     slamcu_context* ctx = s->ctx;
     CU(ctx, cudaEventSynchronize(s->ev_compute_done));
     CU(ctx, cudaEventSynchronize(s->ev_out_done));
+    // a frame that overflowed one of its device lists holds truncated results: say so instead of returning them as OK
+    for (int f = 0; f < s->h_status_n; f++)
+        if (s->h_status[f] != 0) {
+            const int st = s->h_status[f];
+            s->h_status_n = 0;
+            return fail(ctx, SLAMCU_CAPACITY, "frame %d overflowed a device list (status %d: 1 raw corners / candidates, 2 keypoints, 4 matches): "
+                        "raise max_raw_corners / max_keypoints", f, st);
+        }
+    s->h_status_n = 0;
     return SLAMCU_OK;
 }
 
@@ -916,7 +982,7 @@ static int ctx_pipeline_resources(slamcu_context* ctx, size_t n_events) {
 int slamcu_sequence_process(slamcu_sequence* s, slamcu_detector* det, slamcu_matcher* m, const uint8_t* host_frames,
                             int stride, int n, int chunk, int with_keypoints, slamcu_keypoint* kps, uint8_t* desc,
                             slamcu_dmatch* matches, int32_t* counts4) {
-    if (!s || !det || !m || !host_frames || s->ctx != det->ctx || s->ctx != m->ctx) return SLAMCU_INVALID_ARGUMENT;
+    if (!s || !det || !m || !host_frames || s->ctx != det->ctx || s->ctx != m->ctx) return bad_args((s ? s->ctx : nullptr), __func__);
     slamcu_context* ctx = s->ctx;
     if (n < 0 || n > s->max_frames || stride < s->v.cols) return fail(ctx, SLAMCU_INVALID_ARGUMENT, "bad frame count / stride");
     if (m->distance_type != SLAMCU_DISTANCE_HAMMING)
@@ -975,6 +1041,10 @@ int slamcu_sequence_process(slamcu_sequence* s, slamcu_detector* det, slamcu_mat
         CU(ctx, cudaMemcpy2DAsync(counts4 + 2, 16, v.n_raw, 4, 4, n, cudaMemcpyDeviceToHost, ctx->s_out));
         CU(ctx, cudaMemcpy2DAsync(counts4 + 3, 16, v.status, 4, 4, n, cudaMemcpyDeviceToHost, ctx->s_out));
     }
+    if (!s->h_status && cudaMallocHost(reinterpret_cast<void**>(&s->h_status), (size_t)s->max_frames * sizeof(int)) != cudaSuccess)
+        return fail(ctx, SLAMCU_CUDA_ERROR, "cudaMallocHost failed");
+    CU(ctx, cudaMemcpyAsync(s->h_status, v.status, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, ctx->s_out));
+    s->h_status_n = n;
     CU(ctx, cudaEventRecord(s->ev_compute_done, cs));
     CU(ctx, cudaEventRecord(s->ev_out_done, ctx->s_out));  // slamcu_sequence_wait() / slamcu_synchronize() cover it
     return SLAMCU_OK;
@@ -1025,7 +1095,7 @@ int slamcu_default_blur_weights(double* weights25) {
 }
 
 int slamcu_detector_create(slamcu_context* ctx, const slamcu_detector_config* cfg, slamcu_detector** out) {
-    if (!ctx || !cfg || !out) return SLAMCU_INVALID_ARGUMENT;
+    if (!ctx || !cfg || !out) return bad_args(ctx, __func__);
     *out = nullptr;
     // same range checks (and messages) as the reference constructor, feature_detector.hpp:60-93
     if (cfg->intensity_threshold < 0 || cfg->intensity_threshold > 255)
@@ -1134,7 +1204,7 @@ static int check_image(slamcu_context* ctx, const uint8_t* image, int rows, int 
 
 static int detect_common(slamcu_detector* d, const uint8_t* image, int rows, int cols, int stride, slamcu_keypoint* kps,
                          uint8_t* desc, int desc_stride, int capacity, int* n_out, int what /*0 detect,1 both,2 raw*/) {
-    if (!d || !n_out) return SLAMCU_INVALID_ARGUMENT;
+    if (!d || !n_out) return bad_args((d ? d->ctx : nullptr), __func__);
     slamcu_context* ctx = d->ctx;
     int rc = check_image(ctx, image, rows, cols, stride);
     if (rc != SLAMCU_OK) return rc;
@@ -1166,7 +1236,7 @@ int slamcu_detect(slamcu_detector* d, const uint8_t* image, int rows, int cols, 
 
 int slamcu_fast_corners(slamcu_detector* d, const uint8_t* image, int rows, int cols, int stride, slamcu_keypoint* kps,
                         int capacity, int* n_out) {
-    if (!d) return SLAMCU_INVALID_ARGUMENT;
+    if (!d) return bad_args((d ? d->ctx : nullptr), __func__);
     // raw probe: the keypoint list must be able to hold every raw corner
     slamcu_context* ctx = d->ctx;
     int rc = check_image(ctx, image, rows, cols, stride);
@@ -1179,13 +1249,13 @@ int slamcu_fast_corners(slamcu_detector* d, const uint8_t* image, int rows, int 
 
 int slamcu_detect_and_compute(slamcu_detector* d, const uint8_t* image, int rows, int cols, int stride,
                               slamcu_keypoint* kps, uint8_t* desc, int desc_stride, int capacity, int* n_out) {
-    if (!desc) return SLAMCU_INVALID_ARGUMENT;
+    if (!desc) return bad_args(d ? d->ctx : nullptr, __func__);
     return detect_common(d, image, rows, cols, stride, kps, desc, desc_stride, capacity, n_out, 1);
 }
 
 int slamcu_compute(slamcu_detector* d, const uint8_t* image, int rows, int cols, int stride, slamcu_keypoint* kps, int n,
                    uint8_t* desc, int desc_stride) {
-    if (!d) return SLAMCU_INVALID_ARGUMENT;
+    if (!d) return bad_args((d ? d->ctx : nullptr), __func__);
     slamcu_context* ctx = d->ctx;
     if (n < 0) return fail(ctx, SLAMCU_INVALID_ARGUMENT, "negative keypoint count");
     if (n == 0) return SLAMCU_OK;  // reference: descriptors = DescriptorMatrix(0, 0) (feature_detector.cpp:22-25)
@@ -1210,12 +1280,12 @@ int slamcu_compute(slamcu_detector* d, const uint8_t* image, int rows, int cols,
 }
 
 int slamcu_detector_last_octaves(slamcu_detector* d, int32_t* octaves, int capacity) {
-    if (!d || !d->one) return SLAMCU_INVALID_ARGUMENT;
+    if (!d || !d->one) return bad_args((d ? d->ctx : nullptr), __func__);
     return slamcu_sequence_octaves(d->one, 0, octaves, capacity);
 }
 
 int slamcu_orb_stage(slamcu_detector* d, int stage, int level, uint32_t* xy, float* value, int capacity, int* n_out) {
-    if (!d || !n_out) return SLAMCU_INVALID_ARGUMENT;
+    if (!d || !n_out) return bad_args((d ? d->ctx : nullptr), __func__);
     slamcu_context* ctx = d->ctx;
     if (d->mode != SLAMCU_MODE_ORB || !d->one || !d->one->has_orb)
         return fail(ctx, SLAMCU_UNSUPPORTED, "no ORB-mode single-frame call to probe");
@@ -1248,7 +1318,7 @@ int slamcu_orb_stage(slamcu_detector* d, int stage, int level, uint32_t* xy, flo
 }
 
 int slamcu_orb_level_image(slamcu_detector* d, int level, int blurred, uint8_t* out, int out_stride, int* rows, int* cols) {
-    if (!d) return SLAMCU_INVALID_ARGUMENT;
+    if (!d) return bad_args((d ? d->ctx : nullptr), __func__);
     slamcu_context* ctx = d->ctx;
     if (d->mode != SLAMCU_MODE_ORB || !d->one || !d->one->has_orb)
         return fail(ctx, SLAMCU_UNSUPPORTED, "no ORB-mode single-frame call to probe");
@@ -1269,7 +1339,7 @@ int slamcu_orb_level_image(slamcu_detector* d, int level, int blurred, uint8_t* 
 
 int slamcu_gaussian_blur(slamcu_detector* d, const uint8_t* image, int rows, int cols, int stride, uint8_t* out,
                          int out_stride) {
-    if (!d || !out) return SLAMCU_INVALID_ARGUMENT;
+    if (!d || !out) return bad_args((d ? d->ctx : nullptr), __func__);
     slamcu_context* ctx = d->ctx;
     int rc = check_image(ctx, image, rows, cols, stride);
     if (rc != SLAMCU_OK) return rc;
@@ -1292,7 +1362,7 @@ int slamcu_gaussian_blur(slamcu_detector* d, const uint8_t* image, int rows, int
 /* matcher                                                                                         */
 /* ---------------------------------------------------------------------------------------------- */
 int slamcu_matcher_create(slamcu_context* ctx, const slamcu_matcher_config* cfg, slamcu_matcher** out) {
-    if (!ctx || !cfg || !out) return SLAMCU_INVALID_ARGUMENT;
+    if (!ctx || !cfg || !out) return bad_args(ctx, __func__);
     *out = nullptr;
     // feature_matcher.cpp:25-57
     if (cfg->distance_type != SLAMCU_DISTANCE_HAMMING && cfg->distance_type != SLAMCU_DISTANCE_L2)
@@ -1314,6 +1384,13 @@ int slamcu_matcher_create(slamcu_context* ctx, const slamcu_matcher_config* cfg,
     m->p.use_ratio = cfg->use_ratio_test;
     m->p.ratio = cfg->ratio_test_threshold;
     *out = m;
+    return SLAMCU_OK;
+}
+
+int slamcu_matcher_set_train_slices(slamcu_matcher* m, int n_slices) {
+    if (!m) return SLAMCU_INVALID_ARGUMENT;
+    if (n_slices < 0 || n_slices > kMaxMatchSlices) return fail(m->ctx, SLAMCU_INVALID_ARGUMENT, "n_slices must be in [0, %d]", kMaxMatchSlices);
+    m->forced_slices = n_slices;
     return SLAMCU_OK;
 }
 
@@ -1413,6 +1490,7 @@ static int match_common(slamcu_matcher* m, const uint8_t* d1, int n1, int width1
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
     const int q_blocks = (n1 + 127) / 128;
     int n_seg = std::min(std::min((4 * sms + q_blocks - 1) / q_blocks, (n2 + 127) / 128), kMaxMatchSlices);
+    if (m->forced_slices > 0) n_seg = std::min(std::min(m->forced_slices, (n2 + 127) / 128), kMaxMatchSlices);
     n_seg = std::max(n_seg, 1);
     const int seg_len = ((n2 + n_seg - 1) / n_seg + 127) / 128 * 128;
     n_seg = (n2 + seg_len - 1) / seg_len;
@@ -1423,7 +1501,7 @@ static int match_common(slamcu_matcher* m, const uint8_t* d1, int n1, int width1
 int slamcu_match(slamcu_matcher* m, const uint8_t* d1, int n1, int width1, const uint8_t* d2, int n2, int width2,
                  const slamcu_keypoint* kp1, int nkp1, const slamcu_keypoint* kp2, int nkp2, slamcu_dmatch* matches,
                  int capacity, int* n_out) {
-    if (!m || !n_out) return SLAMCU_INVALID_ARGUMENT;
+    if (!m || !n_out) return bad_args((m ? m->ctx : nullptr), __func__);
     slamcu_context* ctx = m->ctx;
     *n_out = 0;
     int rc = match_common(m, d1, n1, width1, d2, n2, width2, kp1, nkp1, kp2, nkp2, true);
@@ -1444,7 +1522,7 @@ int slamcu_match(slamcu_matcher* m, const uint8_t* d1, int n1, int width1, const
 
 int slamcu_knn2_hamming(slamcu_matcher* m, const uint8_t* d1, int n1, const uint8_t* d2, int n2, int width,
                         slamcu_knn2* out) {
-    if (!m || !out) return SLAMCU_INVALID_ARGUMENT;
+    if (!m || !out) return bad_args((m ? m->ctx : nullptr), __func__);
     slamcu_context* ctx = m->ctx;
     int rc = match_common(m, d1, n1, width, d2, n2, width, nullptr, 0, nullptr, 0, false);
     if (rc != SLAMCU_OK) return rc;
@@ -1465,7 +1543,7 @@ int slamcu_knn2_hamming(slamcu_matcher* m, const uint8_t* d1, int n1, const uint
 /* ---------------------------------------------------------------------------------------------- */
 int slamcu_bgr_to_gray(slamcu_context* ctx, const uint8_t* bgr, int rows, int cols, int stride, uint8_t* gray,
                        int gray_stride) {
-    if (!ctx) return SLAMCU_INVALID_ARGUMENT;
+    if (!ctx) return bad_args(ctx, __func__);
     if (!bgr || !gray || rows <= 0 || cols <= 0 || stride < 3 * cols || gray_stride < cols)
         return fail(ctx, SLAMCU_INVALID_ARGUMENT, "bad bgr image");
     CU(ctx, cudaSetDevice(ctx->device));
@@ -1485,13 +1563,15 @@ int slamcu_bgr_to_gray(slamcu_context* ctx, const uint8_t* bgr, int rows, int co
 
 int slamcu_undistort(slamcu_context* ctx, const uint8_t* gray, int rows, int cols, int stride, const double* K4,
                      const double* D4, uint8_t* out_u8, double* out_f64) {
-    if (!ctx) return SLAMCU_INVALID_ARGUMENT;
+    if (!ctx) return bad_args(ctx, __func__);
     if (!gray || rows <= 0 || cols <= 0) return fail(ctx, SLAMCU_EMPTY_INPUT, "Input image is empty.");  // common.hpp:130-132
     if (stride < cols || !K4 || !D4 || (!out_u8 && !out_f64)) return fail(ctx, SLAMCU_INVALID_ARGUMENT, "bad arguments");
     CU(ctx, cudaSetDevice(ctx->device));
     const size_t px = (size_t)rows * cols;
+    if ((long long)rows * cols > INT_MAX) return fail(ctx, SLAMCU_UNSUPPORTED, "undistortion map: rows * cols exceeds INT_MAX");
     const size_t off_map = (px + 255) / 256 * 256, off_u8 = off_map + px * 4, off_f64 = (off_u8 + px + 255) / 256 * 256;
-    int rc = ensure_scratch(ctx, off_f64 + px * 8);
+    const size_t off_fix = off_f64 + px * 8;
+    int rc = ensure_scratch(ctx, off_fix + (1 + (size_t)kUndistFixCap) * sizeof(int));
     if (rc != SLAMCU_OK) return rc;
     uint8_t* base = static_cast<uint8_t*>(ctx->scratch);
     uint8_t* d_in = base;
@@ -1500,7 +1580,8 @@ int slamcu_undistort(slamcu_context* ctx, const uint8_t* gray, int rows, int col
     double* d_f64 = reinterpret_cast<double*>(base + off_f64);
     CU(ctx, cudaMemcpy2DAsync(d_in, cols, gray, stride, cols, rows, cudaMemcpyHostToDevice, ctx->stream));
     CamParams cam{K4[0], K4[1], K4[2], K4[3], D4[0], D4[1], D4[2], D4[3]};
-    ctx->launches += launch_undistort_map(rows, cols, cam, d_map, ctx->stream);
+    rc = build_undistort_map(ctx, rows, cols, cam, d_map, reinterpret_cast<int*>(base + off_fix));
+    if (rc != SLAMCU_OK) return rc;
     ctx->launches += launch_remap(d_in, rows, cols, cols, d_map, out_u8 ? d_u8 : nullptr, out_f64 ? d_f64 : nullptr,
                                   ctx->stream);
     rc = check_launch(ctx, "undistort");
@@ -1516,7 +1597,7 @@ int slamcu_undistort(slamcu_context* ctx, const uint8_t* gray, int rows, int col
 /* ---------------------------------------------------------------------------------------------- */
 int slamcu_ransac_score(slamcu_context* ctx, const double* models9, int n_models, const double* x1, const double* x2,
                         int n, double thr2, int32_t* counts, uint8_t* masks) {
-    if (!ctx) return SLAMCU_INVALID_ARGUMENT;
+    if (!ctx) return bad_args(ctx, __func__);
     if (!models9 || !x1 || !x2 || !counts || n_models <= 0 || n <= 0) return fail(ctx, SLAMCU_INVALID_ARGUMENT, "bad arguments");
     CU(ctx, cudaSetDevice(ctx->device));
     const size_t b_models = (size_t)n_models * 9 * 8, b_pts = (size_t)n * 2 * 8, b_cnt = ((size_t)n_models * 4 + 255) / 256 * 256;
@@ -1550,7 +1631,7 @@ static void essential_params(EssentialJob& j, const double* K4, double prob, dou
 
 int slamcu_find_essential(slamcu_context* ctx, const float* p1, const float* p2, int n, const double* K4, double prob,
                           double threshold, int max_iters, double* E9, uint8_t* mask, int* n_inliers) {
-    if (!ctx) return SLAMCU_INVALID_ARGUMENT;
+    if (!ctx) return bad_args(ctx, __func__);
     if (!p1 || !p2 || !K4 || !E9 || n < 0) return fail(ctx, SLAMCU_INVALID_ARGUMENT, "bad arguments");
     if (n < 6) return fail(ctx, SLAMCU_EMPTY_INPUT, "findEssentialMat needs more than 5 correspondences (got %d)", n);
     if (max_iters > kEssentialMaxIters) return fail(ctx, SLAMCU_INVALID_ARGUMENT, "maxIters above %d is not supported", kEssentialMaxIters);
@@ -1594,7 +1675,7 @@ int slamcu_find_essential(slamcu_context* ctx, const float* p1, const float* p2,
 
 int slamcu_estimate_pose(slamcu_context* ctx, const float* p1, const float* p2, int n, const double* K4, double* E9, uint8_t* mask,
                          int* n_inliers, double* R9, double* t3, int32_t* front4) {
-    if (!ctx) return SLAMCU_INVALID_ARGUMENT;
+    if (!ctx) return bad_args(ctx, __func__);
     if (!p1 || !p2 || !K4 || !R9 || !t3 || n < 0) return fail(ctx, SLAMCU_INVALID_ARGUMENT, "bad arguments");
     if (n < 8) return fail(ctx, SLAMCU_EMPTY_INPUT, "Cannot estimate pose, not enough matches (%d). Required at least 8.", n);
     double E[9];
@@ -1635,7 +1716,7 @@ int slamcu_estimate_pose(slamcu_context* ctx, const float* p1, const float* p2, 
 }
 
 int slamcu_fivept_solve(slamcu_context* ctx, const double* x1, const double* x2, int n_samples, double* models, int32_t* counts) {
-    if (!ctx) return SLAMCU_INVALID_ARGUMENT;
+    if (!ctx) return bad_args(ctx, __func__);
     if (!x1 || !x2 || !models || !counts || n_samples <= 0) return fail(ctx, SLAMCU_INVALID_ARGUMENT, "bad arguments");
     CU(ctx, cudaSetDevice(ctx->device));
     const size_t b_pts = (size_t)n_samples * 10 * 8, b_mod = (size_t)n_samples * 90 * 8, b_cnt = (size_t)n_samples * 4;
@@ -1660,7 +1741,7 @@ int slamcu_fivept_solve(slamcu_context* ctx, const double* x1, const double* x2,
 
 int slamcu_sequence_essential(slamcu_sequence* s, int first, int n_pairs, const double* K4, double prob, double threshold,
                               int max_iters) {
-    if (!s || !K4) return SLAMCU_INVALID_ARGUMENT;
+    if (!s || !K4) return bad_args((s ? s->ctx : nullptr), __func__);
     slamcu_context* ctx = s->ctx;
     if (first < 0 || n_pairs < 0 || first + n_pairs + 1 > s->max_frames) return fail(ctx, SLAMCU_INVALID_ARGUMENT, "bad pair range");
     if (n_pairs == 0) return SLAMCU_OK;
@@ -1712,7 +1793,7 @@ int slamcu_sequence_essential(slamcu_sequence* s, int first, int n_pairs, const 
 
 int slamcu_sequence_essential_read(slamcu_sequence* s, int pair, double* E9, int* n_inliers, int* n_iters, uint8_t* mask,
                                    int capacity, int* n_points) {
-    if (!s) return SLAMCU_INVALID_ARGUMENT;
+    if (!s) return bad_args((s ? s->ctx : nullptr), __func__);
     slamcu_context* ctx = s->ctx;
     if (!s->has_ess) return fail(ctx, SLAMCU_UNSUPPORTED, "slamcu_sequence_essential has not run on this sequence");
     if (pair < 0 || pair + 1 >= s->max_frames) return fail(ctx, SLAMCU_INVALID_ARGUMENT, "bad pair index");

@@ -84,7 +84,8 @@ int launch_prepare(const uint8_t* src, int channels, int src_stride, size_t src_
 int launch_repitch(const uint8_t* src, int stride, uint8_t* dst, int pitch, int cols, long long rows_total, cudaStream_t st);
 int launch_bgr2gray(const uint8_t* bgr, int rows, int cols, int stride, uint8_t* gray, int gstride, cudaStream_t st);
 struct CamParams { double fx, fy, cx, cy, k1, k2, p1, p2; };
-int launch_undistort_map(int rows, int cols, const CamParams& cam, int* map, cudaStream_t st);
+// fix: [1 + fix_cap] ints, fix[0] = number of pixels the host must recompute (those within 1e-6 of a rounding boundary)
+int launch_undistort_map(int rows, int cols, const CamParams& cam, int* map, int* fix, int fix_cap, cudaStream_t st);
 int launch_remap(const uint8_t* gray, int rows, int cols, int stride, const int* map, uint8_t* out_u8, double* out_f64,
                  cudaStream_t st);
 int launch_ransac_score(const double* models9, int n_models, const double* x1, const double* x2, int n, double thr2,

@@ -7,6 +7,8 @@
 //                          -> int32 source index (-1 = outside).  Constant per camera, built once.
 //   remap_kernel         : the per-frame part (:159-170): gather; emits the u8 image the detector
 //                          consumes and/or the reference's value/255.0 double image.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace slamcu {
@@ -20,7 +22,11 @@ __global__ void bgr2gray_kernel(const uint8_t* __restrict__ bgr, int rows, int c
     gray[(size_t)y * gstride + x] = (uint8_t)((3735u * p[0] + 19235u * p[1] + 9798u * p[2] + 16384u) >> 15);
 }
 
-__global__ void undistort_map_kernel(int rows, int cols, CamParams c, int* __restrict__ map) {
+// Everything but pow() is IEEE-exact on the device (no FMA, correctly rounded sqrt and division); CUDA's pow() may differ
+// from the host libm's by an ulp or two, which moves ud / vd by < 1e-9 px.  Pixels whose ud or vd lies within 1e-6 of a
+// rounding boundary (k + 0.5) are therefore appended to `fix` and recomputed by the host with the reference's own libm
+// calls (undistort_index_host in api.cu); every other pixel rounds to the same source index either way.
+__global__ void undistort_map_kernel(int rows, int cols, CamParams c, int* __restrict__ map, int* __restrict__ fix, int fix_cap) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
     if (j >= cols || i >= rows) return;
     const double x = ((double)j - c.cx) / c.fx;
@@ -34,6 +40,11 @@ __global__ void undistort_map_kernel(int rows, int cols, CamParams c, int* __res
     const double vd = c.fy * yd + c.cy;
     const int u = (int)round(ud), v = (int)round(vd);
     map[(size_t)i * cols + j] = (u >= 0 && v >= 0 && u < cols && v < rows) ? v * cols + u : -1;
+    const bool near = fabs(fabs(ud - floor(ud)) - 0.5) < 1e-6 || fabs(fabs(vd - floor(vd)) - 0.5) < 1e-6 || !(fabs(ud) < 1e9) || !(fabs(vd) < 1e9);
+    if (near) {
+        const int pos = atomicAdd(fix, 1);
+        if (pos < fix_cap) fix[1 + pos] = i * cols + j;
+    }
 }
 
 __global__ void remap_kernel(const uint8_t* __restrict__ gray, int rows, int cols, int stride,
@@ -52,16 +63,17 @@ __global__ void remap_kernel(const uint8_t* __restrict__ gray, int rows, int col
 // at the link rate, tools/xfer_probe.py.)
 __global__ void __launch_bounds__(256) repitch_kernel(const uint8_t* __restrict__ src, int stride, uint8_t* __restrict__ dst,
                                                       int pitch, int cols, long long rows_total) {
-    const long long row = (long long)blockIdx.y * 8 + (threadIdx.x >> 5);
-    if (row >= rows_total) return;
-    const uint8_t* s = src + row * stride;
-    uint8_t* d = dst + row * pitch;
-    for (int x = (blockIdx.x * 32 + (threadIdx.x & 31)) * 4; x < pitch; x += gridDim.x * 128) {
-        uint32_t w = 0;
+    // grid-stride over the rows: grid.y is capped at 65535 blocks of 8 rows, sequences may hold more rows than that
+    for (long long row = (long long)blockIdx.y * 8 + (threadIdx.x >> 5); row < rows_total; row += (long long)gridDim.y * 8) {
+        const uint8_t* s = src + row * stride;
+        uint8_t* d = dst + row * pitch;
+        for (int x = (blockIdx.x * 32 + (threadIdx.x & 31)) * 4; x < pitch; x += gridDim.x * 128) {
+            uint32_t w = 0;
 #pragma unroll
-        for (int k = 0; k < 4; k++)
-            if (x + k < cols) w |= (uint32_t)s[x + k] << (8 * k);
-        *reinterpret_cast<uint32_t*>(d + x) = w;
+            for (int k = 0; k < 4; k++)
+                if (x + k < cols) w |= (uint32_t)s[x + k] << (8 * k);
+            *reinterpret_cast<uint32_t*>(d + x) = w;
+        }
     }
 }
 
@@ -101,7 +113,7 @@ int launch_prepare(const uint8_t* src, int channels, int src_stride, size_t src_
 }
 
 int launch_repitch(const uint8_t* src, int stride, uint8_t* dst, int pitch, int cols, long long rows_total, cudaStream_t st) {
-    dim3 grid(min((pitch / 4 + 31) / 32, 4), (unsigned)((rows_total + 7) / 8));
+    dim3 grid(min((pitch / 4 + 31) / 32, 4), (unsigned)std::min<long long>((rows_total + 7) / 8, 65535));
     SLAM_KERNEL("repitch", st, repitch_kernel<<<grid, 256, 0, st>>>(src, stride, dst, pitch, cols, rows_total));
     return 1;
 }
@@ -111,9 +123,10 @@ int launch_bgr2gray(const uint8_t* bgr, int rows, int cols, int stride, uint8_t*
     bgr2gray_kernel<<<grid, 256, 0, st>>>(bgr, rows, cols, stride, gray, gstride);
     return 1;
 }
-int launch_undistort_map(int rows, int cols, const CamParams& cam, int* map, cudaStream_t st) {
+int launch_undistort_map(int rows, int cols, const CamParams& cam, int* map, int* fix, int fix_cap, cudaStream_t st) {
     dim3 grid((cols + 255) / 256, rows);
-    undistort_map_kernel<<<grid, 256, 0, st>>>(rows, cols, cam, map);
+    cudaMemsetAsync(fix, 0, sizeof(int), st);
+    undistort_map_kernel<<<grid, 256, 0, st>>>(rows, cols, cam, map, fix, fix_cap);
     return 1;
 }
 int launch_remap(const uint8_t* gray, int rows, int cols, int stride, const int* map, uint8_t* out_u8, double* out_f64,

@@ -281,3 +281,7 @@ class FeatureMatcher:
         self.ctx.check(self.ctx.lib.slamcu_knn2_hamming(self.handle, d1.ctypes.data, d1.shape[0], d2.ctypes.data,
                                                         d2.shape[0], d1.shape[1], out.ctypes.data))
         return out
+
+    def set_train_slices(self, n_slices: int = 0):
+        """Tuning / test knob (slamcu_matcher_set_train_slices): 0 = automatic; results do not depend on it."""
+        self.ctx.check(self.ctx.lib.slamcu_matcher_set_train_slices(self.handle, int(n_slices)))

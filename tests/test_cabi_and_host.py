@@ -107,3 +107,11 @@ def test_cmake_and_python_builds_list_the_same_sources():
     assert listed == set(build.SOURCES)
     assert set(f for f in os.listdir(build.CSRC) if f.endswith(".cu")) == set(build.SOURCES)
     assert "100a" in text and "-fmad=false" in text
+
+
+def test_both_build_recipes_pass_the_exactness_flags():
+    """Every bit-exactness guarantee rests on -fmad=false and on the absence of fast-math, in BOTH build recipes."""
+    from slam_cin0051_b200 import build as b
+    assert "-fmad=false" in b.NVCC_FLAGS and not any("fast_math" in f or "fast-math" in f for f in b.NVCC_FLAGS)
+    cm = open(os.path.join(ROOT, "CMakeLists.txt")).read()
+    assert "-fmad=false" in cm and "fast_math" not in cm and "fast-math" not in cm

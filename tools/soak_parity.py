@@ -1,7 +1,13 @@
 """Randomised parity soak on a GPU box: random sizes, contents and parameters through the C ABI in both modes, compared
 bit for bit with live cv2 (ORB mode, kNN) and with the C++ restatement of the reference (reference mode); RANSAC against
-the oracle loop driven by the g++ build of the device solver.  usage: python tools/soak_parity.py [seconds] [seed]
-Prints one JSON line: cases run per family and every mismatch (seed + parameters, enough to reproduce)."""
+the oracle loop driven by the g++ build of the device solver and against cv2.findEssentialMat itself.
+usage: python tools/soak_parity.py [seconds] [seed]
+Prints one JSON line: cases run per family and every mismatch (seed + parameters, enough to reproduce).
+tests/test_gpu_soak.py runs a bounded, fixed-seed slice of the same families inside `pytest -m gpu`.
+
+Two-view tolerance: device == oracle loop (driven by the g++ build of the device's own solver) exactly; against cv2 as
+stated in tests/ransac_compare.py (per problem: Jaccard >= 0.8, the mask is the exact Sampson test of the device's own E, and E
+under a condition-aware bound wherever the masks are identical)."""
 import ctypes as C
 import json
 import os
@@ -23,15 +29,22 @@ from slam_cin0051_b200.synth import make_sequence  # noqa: E402
 from tools_golden import knn2 as cv_knn2  # noqa: E402
 from tools_golden import orb_canonical  # noqa: E402
 
-budget = float(sys.argv[1]) if len(sys.argv) > 1 else 120.0
-seed0 = int(sys.argv[2]) if len(sys.argv) > 2 else 0
-ctx = S.Context(0)
-ref_oracle.build()
-so = os.path.join(ROOT, "tests", "native", "libhost_exact.so")
-if not os.path.exists(so):
-    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", so, os.path.join(ROOT, "tests", "native", "host_exact.cpp")])
-hx = C.CDLL(so)
-kitti = cv2.imread(os.path.join(ROOT, "test", "data", "images", "0000000000.png"), 0)
+ctx = None
+hx = None
+kitti = None
+
+
+def setup(context=None):
+    global ctx, hx, kitti
+    if ctx is not None:
+        return
+    ctx = context or S.Context(0)
+    ref_oracle.build()
+    so = os.path.join(ROOT, "tests", "native", "libhost_exact.so")
+    if not os.path.exists(so):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", so, os.path.join(ROOT, "tests", "native", "host_exact.cpp")])
+    hx = C.CDLL(so)
+    kitti = cv2.imread(os.path.join(ROOT, "test", "data", "images", "0000000000.png"), 0)
 
 
 def image(rng, rows, cols):
@@ -138,10 +151,13 @@ def ransac_case(rng):
     max_iters = int(rng.choice([20, 56, 100, 1000]))
     E, mask, good = S.find_essential(p1, p2, K4, max_iters=max_iters, context=ctx)
     wE, wmask, wgood = eo.find_essential(p1, p2, K4, max_iters=max_iters, solver=solver)
-    ok = good == wgood and np.array_equal(mask, wmask)
-    if ok and E is not None:
-        ok = min(np.abs(E - wE).max(), np.abs(E + wE).max()) < 1e-5  # conditioning of the winning sample; masks are the exact part
-    return bool(ok), dict(n=n, inlier_ratio=round(inl, 2), max_iters=max_iters, good=int(good), want=int(wgood))
+    ok = good == wgood and np.array_equal(mask, wmask)  # device == the oracle loop driven by the g++ build of its solver: exact
+    info = dict(n=n, inlier_ratio=round(inl, 2), max_iters=max_iters, good=int(good), want=int(wgood))
+    if ok:
+        from ransac_compare import compare
+        ok, cinfo = compare(p1, p2, K4, E, mask, max_iters=max_iters)  # ... and cv2 itself, per-problem tolerance
+        info.update(cinfo)
+    return bool(ok), info
 
 
 def sequence_case(rng):
@@ -210,21 +226,30 @@ def prep_case(rng):
     return bool(ok), dict(rows=rows, cols=cols, K4=K4, D4=D4)
 
 
-families = {"orb_vs_cv2": orb_case, "reference_vs_cpp_restatement": ref_case, "knn2_vs_cv2": knn_case, "ransac_vs_oracle_loop": ransac_case,
+families = {"orb_vs_cv2": orb_case, "reference_vs_cpp_restatement": ref_case, "knn2_vs_cv2": knn_case, "ransac_vs_oracle_loop_and_cv2": ransac_case,
             "sequence_vs_single_calls": sequence_case, "prep_vs_cv2_and_restatement": prep_case}
-runs = {k: 0 for k in families}
-fails = []
-t_end = time.time() + budget
-i = 0
-while time.time() < t_end:
-    name = list(families)[i % len(families)]
-    seed = seed0 * 1000003 + i
-    try:
-        ok, info = families[name](np.random.default_rng(seed))
-    except Exception as e:  # a crash is a finding too
-        ok, info = False, {"exception": repr(e)[:200]}
-    runs[name] += 1
-    if not ok:
-        fails.append({"family": name, "seed": seed, **info})
-    i += 1
-print(json.dumps({"tool": "soak_parity", "seconds": budget, "seed0": seed0, "cases": runs, "mismatches": len(fails), "details": fails[:20]}))
+
+
+def run(budget=120.0, seed0=0, max_cases=None, context=None):
+    """Round-robin over the families until `budget` seconds or `max_cases` cases; returns the JSON-able record."""
+    setup(context)
+    runs = {k: 0 for k in families}
+    fails = []
+    t_end = time.time() + budget
+    i = 0
+    while time.time() < t_end and (max_cases is None or i < max_cases):
+        name = list(families)[i % len(families)]
+        seed = seed0 * 1000003 + i
+        try:
+            ok, info = families[name](np.random.default_rng(seed))
+        except Exception as e:  # a crash is a finding too
+            ok, info = False, {"exception": repr(e)[:200]}
+        runs[name] += 1
+        if not ok:
+            fails.append({"family": name, "seed": seed, **info})
+        i += 1
+    return {"tool": "soak_parity", "seconds": budget, "seed0": seed0, "cases": runs, "mismatches": len(fails), "details": fails[:20]}
+
+
+if __name__ == "__main__":
+    print(json.dumps(run(float(sys.argv[1]) if len(sys.argv) > 1 else 120.0, int(sys.argv[2]) if len(sys.argv) > 2 else 0)))
