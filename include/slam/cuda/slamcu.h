@@ -230,7 +230,23 @@ int slamcu_sequence_process(slamcu_sequence* seq, slamcu_detector* det, slamcu_m
                             int stride, int n, int chunk, int with_keypoints, slamcu_keypoint* keypoints,
                             uint8_t* descriptors, slamcu_dmatch* matches, int32_t* counts4);
 
+/* The same loop with DENSE outputs: a device compaction kernel writes only the defined rows, frame after frame, straight
+ * into page-locked device-mapped host buffers (slamcu_alloc_pinned / cudaHostAlloc), so no padding crosses the link and the
+ * call stays asynchronous (nothing waits for the host to learn the counts):
+ *   keypoints / descriptors of frame f at row kp_off[f] = counts4[0][0] + ... + counts4[f-1][0]
+ *   matches of pair (f, f+1)           at row m_off[f]  = counts4[0][1] + ... + counts4[f-1][1]
+ * kp_capacity / match_capacity: rows the buffers hold; slamcu_sequence_wait returns SLAMCU_CAPACITY when they were exceeded. */
+int slamcu_sequence_process_dense(slamcu_sequence* seq, slamcu_detector* det, slamcu_matcher* m, const uint8_t* host_frames,
+                                  int stride, int n, int chunk, int with_keypoints, slamcu_keypoint* keypoints,
+                                  uint8_t* descriptors, slamcu_dmatch* matches, int32_t* counts4, int64_t kp_capacity,
+                                  int64_t match_capacity);
+/* Waits for the sequence's latest slamcu_sequence_process[_dense] call.  SLAMCU_CAPACITY if a frame overflowed one of its
+ * device lists (its results are truncated) or the dense outputs overflowed their capacities. */
 int slamcu_sequence_wait(slamcu_sequence* seq);
+/* Per-frame counts {n_keypoints, n_matches, n_raw_corners, status} of frames [first, first+n) packed into a DEVICE array
+ * int32[n][4] on the context's stream: the payload of the multi-GPU path's only collective (one all-gather of
+ * per-frame counts over NCCL), with no host round trip.  Asynchronous. */
+int slamcu_sequence_counts_device(slamcu_sequence* seq, int first, int n, int32_t* device_counts4);
 
 /* ---- image preparation (src/preprocessing) ---------------------------------------------------- */
 /* cv::cvtColor(BGR2GRAY) (preprocessor.cpp:136): gray = (3735 B + 19235 G + 9798 R + 16384) >> 15. */

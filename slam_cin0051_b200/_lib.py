@@ -82,6 +82,8 @@ SYMBOLS = {
     "slamcu_sequence_frame": (_i, [_vp, _i, _vp, _u8p, _i, _i, _ip]),
     "slamcu_sequence_matches": (_i, [_vp, _i, _vp, _i, _ip]),
     "slamcu_sequence_process": (_i, [_vp, _vp, _vp, _u8p, _i, _i, _i, _i, _vp, _u8p, _vp, _vp]),
+    "slamcu_sequence_process_dense": (_i, [_vp, _vp, _vp, _u8p, _i, _i, _i, _i, _vp, _u8p, _vp, _vp, C.c_int64, C.c_int64]),
+    "slamcu_sequence_counts_device": (_i, [_vp, _i, _i, _vp]),
     "slamcu_sequence_wait": (_i, [_vp]),
     "slamcu_sequence_download": (_i, [_vp, _i, _i, _vp, _u8p, _vp, _vp]),
     "slamcu_bgr_to_gray": (_i, [_vp, _u8p, _i, _i, _i, _u8p, _i]),

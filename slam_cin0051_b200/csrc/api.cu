@@ -200,7 +200,8 @@ struct slamcu_sequence {
     int max_frames = 0;
     unsigned long long* sort_keys = nullptr;  // [F][cap_kp]
     int* h_counts = nullptr;                  // pinned [F][4]
-    int* h_status = nullptr;                  // pinned [F]: status words of the latest slamcu_sequence_process call
+    int* h_status = nullptr;                  // pinned [F + 1]: status words of the latest slamcu_sequence_process call (+ dense overflow bits)
+    int* d_dense = nullptr;                   // [2][F + 1] running offsets of the dense outputs (keypoints, matches) + 1 overflow word
     int h_status_n = 0;                       // ... and how many frames it covered
     uint8_t* stage = nullptr;                 // [F][rows][cols] dense landing zone of linear H2D copies (lazy)
     uint8_t* prep_stage = nullptr;            // landing zone of slamcu_sequence_prepare (gray or BGR host frames; lazy)
@@ -478,6 +479,7 @@ void slamcu_sequence_destroy(slamcu_sequence* s) {
     if (s->ess_work) cudaFree(s->ess_work);
     if (s->h_counts) cudaFreeHost(s->h_counts);
     if (s->h_status) cudaFreeHost(s->h_status);
+    if (s->d_dense) cudaFree(s->d_dense);
     delete s;
 }
 
@@ -960,7 +962,12 @@ int slamcu_sequence_wait(slamcu_sequence* s) {
             return fail(ctx, SLAMCU_CAPACITY, "frame %d overflowed a device list (status %d: 1 raw corners / candidates, 2 keypoints, 4 matches): "
                         "raise max_raw_corners / max_keypoints", f, st);
         }
+    const int dense_over = s->h_status ? s->h_status[s->max_frames] : 0;
+    if (s->h_status) s->h_status[s->max_frames] = 0;
     s->h_status_n = 0;
+    if (dense_over)
+        return fail(ctx, SLAMCU_CAPACITY, "dense output overflow (%s): raise kp_capacity / match_capacity",
+                    dense_over == 1 ? "keypoints" : dense_over == 2 ? "matches" : "keypoints and matches");
     return SLAMCU_OK;
 }
 
@@ -979,9 +986,9 @@ static int ctx_pipeline_resources(slamcu_context* ctx, size_t n_events) {
 // -> FeatureMatcher), for n frames held in host memory: upload, detectAndCompute, match(f, f+1), download --
 // software-pipelined by chunks of `chunk` frames over three streams (H2D copy engine, compute, D2H copy engine) so
 // the PCIe transfers hide behind the kernels.
-int slamcu_sequence_process(slamcu_sequence* s, slamcu_detector* det, slamcu_matcher* m, const uint8_t* host_frames,
-                            int stride, int n, int chunk, int with_keypoints, slamcu_keypoint* kps, uint8_t* desc,
-                            slamcu_dmatch* matches, int32_t* counts4) {
+static int seq_process(slamcu_sequence* s, slamcu_detector* det, slamcu_matcher* m, const uint8_t* host_frames,
+                       int stride, int n, int chunk, int with_keypoints, slamcu_keypoint* kps, uint8_t* desc,
+                       slamcu_dmatch* matches, int32_t* counts4, bool dense, long long kp_capacity, long long match_capacity) {
     if (!s || !det || !m || !host_frames || s->ctx != det->ctx || s->ctx != m->ctx) return bad_args((s ? s->ctx : nullptr), __func__);
     slamcu_context* ctx = s->ctx;
     if (n < 0 || n > s->max_frames || stride < s->v.cols) return fail(ctx, SLAMCU_INVALID_ARGUMENT, "bad frame count / stride");
@@ -997,11 +1004,38 @@ int slamcu_sequence_process(slamcu_sequence* s, slamcu_detector* det, slamcu_mat
     if (rc != SLAMCU_OK) return rc;
     const SeqView& v = s->v;
     cudaStream_t cs = ctx->stream;
+    if (!s->h_status) {
+        if (cudaMallocHost(reinterpret_cast<void**>(&s->h_status), ((size_t)s->max_frames + 1) * sizeof(int)) != cudaSuccess)
+            return fail(ctx, SLAMCU_CUDA_ERROR, "cudaMallocHost failed");
+        s->h_status[s->max_frames] = 0;
+    }
+    // dense outputs: device-visible addresses of the caller's page-locked buffers, running offsets on the device
+    void *dk = nullptr, *dd = nullptr, *dm = nullptr;
+    int *kp_off = nullptr, *m_off = nullptr, *d_over = nullptr;
+    if (dense) {
+        if (kp_capacity < 0 || match_capacity < 0 || kp_capacity > INT_MAX || match_capacity > INT_MAX)
+            return fail(ctx, SLAMCU_INVALID_ARGUMENT, "dense capacities out of range");
+        if ((kps && cudaHostGetDevicePointer(&dk, kps, 0) != cudaSuccess) || (desc && cudaHostGetDevicePointer(&dd, desc, 0) != cudaSuccess) ||
+            (matches && cudaHostGetDevicePointer(&dm, matches, 0) != cudaSuccess)) {
+            cudaGetLastError();
+            return fail(ctx, SLAMCU_INVALID_ARGUMENT, "dense outputs must be page-locked, device-mapped host memory (slamcu_alloc_pinned)");
+        }
+        const size_t F1 = (size_t)s->max_frames + 1;
+        if (!s->d_dense) CU(ctx, cudaMalloc(reinterpret_cast<void**>(&s->d_dense), (2 * F1 + 1) * sizeof(int)));
+        kp_off = s->d_dense;
+        m_off = s->d_dense + F1;
+        d_over = s->d_dense + 2 * F1;
+    }
     // hazards are per sequence: the new frames may overwrite this sequence's stores only after ITS previous kernels,
     // and its kernels may overwrite the result arrays only after ITS previous downloads.  A call on another sequence
     // (double buffering) therefore overlaps its copies with this one's kernels.
     CU(ctx, cudaStreamWaitEvent(ctx->s_in, s->ev_compute_done, 0));
     CU(ctx, cudaStreamWaitEvent(cs, s->ev_out_done, 0));
+    if (dense) {  // the previous call's compaction (on s_out) is covered by ev_out_done, which s_out itself orders
+        CU(ctx, cudaMemsetAsync(kp_off, 0, sizeof(int), ctx->s_out));
+        CU(ctx, cudaMemsetAsync(m_off, 0, sizeof(int), ctx->s_out));
+        CU(ctx, cudaMemsetAsync(d_over, 0, sizeof(int), ctx->s_out));
+    }
     int f0 = 0;
     for (int c = 0; c < n_chunks; c++) {
         const int cnt = sizes[c];
@@ -1023,6 +1057,14 @@ int slamcu_sequence_process(slamcu_sequence* s, slamcu_detector* det, slamcu_mat
         }
         CU(ctx, cudaEventRecord(ctx->events[2 * c + 1], cs));
         CU(ctx, cudaStreamWaitEvent(ctx->s_out, ctx->events[2 * c + 1], 0));
+        if (dense) {
+            ProfGuard pg(ctx);
+            ctx->launches += launch_dense_scan(v.n_kp, f0, cnt, kp_off, ctx->s_out);
+            ctx->launches += launch_dense_scan(v.n_match, p0, np, m_off, ctx->s_out);
+            ctx->launches += launch_dense_copy(v, f0, cnt, p0, np, kp_off, m_off, dk, dd, dm, (int)kp_capacity, (int)match_capacity, d_over, ctx->s_out);
+            f0 += cnt;
+            continue;
+        }
         if (kps)
             CU(ctx, cudaMemcpyAsync(kps + (size_t)f0 * v.cap_kp, v.kps + (size_t)f0 * v.cap_kp,
                                     (size_t)cnt * v.cap_kp * sizeof(slamcu_keypoint), cudaMemcpyDeviceToHost, ctx->s_out));
@@ -1041,13 +1083,33 @@ int slamcu_sequence_process(slamcu_sequence* s, slamcu_detector* det, slamcu_mat
         CU(ctx, cudaMemcpy2DAsync(counts4 + 2, 16, v.n_raw, 4, 4, n, cudaMemcpyDeviceToHost, ctx->s_out));
         CU(ctx, cudaMemcpy2DAsync(counts4 + 3, 16, v.status, 4, 4, n, cudaMemcpyDeviceToHost, ctx->s_out));
     }
-    if (!s->h_status && cudaMallocHost(reinterpret_cast<void**>(&s->h_status), (size_t)s->max_frames * sizeof(int)) != cudaSuccess)
-        return fail(ctx, SLAMCU_CUDA_ERROR, "cudaMallocHost failed");
+    if (dense) CU(ctx, cudaMemcpyAsync(s->h_status + s->max_frames, d_over, sizeof(int), cudaMemcpyDeviceToHost, ctx->s_out));
     CU(ctx, cudaMemcpyAsync(s->h_status, v.status, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, ctx->s_out));
     s->h_status_n = n;
     CU(ctx, cudaEventRecord(s->ev_compute_done, cs));
     CU(ctx, cudaEventRecord(s->ev_out_done, ctx->s_out));  // slamcu_sequence_wait() / slamcu_synchronize() cover it
     return SLAMCU_OK;
+}
+
+int slamcu_sequence_process(slamcu_sequence* s, slamcu_detector* det, slamcu_matcher* m, const uint8_t* host_frames,
+                            int stride, int n, int chunk, int with_keypoints, slamcu_keypoint* kps, uint8_t* desc,
+                            slamcu_dmatch* matches, int32_t* counts4) {
+    return seq_process(s, det, m, host_frames, stride, n, chunk, with_keypoints, kps, desc, matches, counts4, false, 0, 0);
+}
+
+int slamcu_sequence_process_dense(slamcu_sequence* s, slamcu_detector* det, slamcu_matcher* m, const uint8_t* host_frames,
+                                  int stride, int n, int chunk, int with_keypoints, slamcu_keypoint* kps, uint8_t* desc,
+                                  slamcu_dmatch* matches, int32_t* counts4, int64_t kp_capacity, int64_t match_capacity) {
+    return seq_process(s, det, m, host_frames, stride, n, chunk, with_keypoints, kps, desc, matches, counts4, true, kp_capacity, match_capacity);
+}
+
+int slamcu_sequence_counts_device(slamcu_sequence* s, int first, int n, int32_t* device_counts4) {
+    if (!s || !device_counts4) return bad_args((s ? s->ctx : nullptr), __func__);
+    slamcu_context* ctx = s->ctx;
+    if (first < 0 || n < 0 || first + n > s->max_frames) return fail(ctx, SLAMCU_INVALID_ARGUMENT, "bad frame range");
+    ProfGuard pg(ctx);
+    ctx->launches += launch_pack_counts(s->v, first, n, device_counts4, ctx->stream);
+    return check_launch(ctx, "pack_counts");
 }
 
 /* ---------------------------------------------------------------------------------------------- */

@@ -91,6 +91,12 @@ int launch_remap(const uint8_t* gray, int rows, int cols, int stride, const int*
 int launch_ransac_score(const double* models9, int n_models, const double* x1, const double* x2, int n, double thr2,
                         int* counts, uint8_t* masks, cudaStream_t st);
 
+// result compaction (pack.cu)
+int launch_dense_scan(const int* counts, int first, int n, int* off, cudaStream_t st);
+int launch_dense_copy(const SeqView& s, int first, int n_frames, int pair_first, int n_pairs, const int* kp_off, const int* m_off, void* h_kps,
+                      void* h_desc, void* h_matches, int kp_cap, int m_cap, int* overflow, cudaStream_t st);
+int launch_pack_counts(const SeqView& s, int first, int n, int* out4, cudaStream_t st);
+
 // two-view geometry (essential.cu): one RANSAC problem per frame pair
 struct EssentialJob {
     double2* x1; double2* x2;        // [pairs][pt_stride] correspondences normalised by K

@@ -127,6 +127,21 @@ class FrameSequence:
             1 if with_keypoints else 0, C.c_void_p(kps_ptr or 0), C.c_void_p(desc_ptr or 0), C.c_void_p(matches_ptr or 0),
             C.c_void_p(counts_ptr or 0)))
 
+    def process_dense_ptrs(self, detector: FeatureDetector, matcher: FeatureMatcher, host_ptr: int, n: int, chunk: int = 64,
+                           with_keypoints: bool = True, kps_ptr=None, desc_ptr=None, matches_ptr=None, counts_ptr=None,
+                           kp_capacity: int = 0, match_capacity: int = 0):
+        """process_ptrs with dense outputs (slamcu_sequence_process_dense): rows of frame f start at the running sums of the
+        counts; the buffers must be page-locked (torch pin_memory / slamcu_alloc_pinned)."""
+        self.ctx.check(self.ctx.lib.slamcu_sequence_process_dense(
+            self.handle, detector.handle, matcher.handle, C.c_void_p(host_ptr), self.cols, n, chunk,
+            1 if with_keypoints else 0, C.c_void_p(kps_ptr or 0), C.c_void_p(desc_ptr or 0), C.c_void_p(matches_ptr or 0),
+            C.c_void_p(counts_ptr or 0), kp_capacity, match_capacity))
+
+    def counts_device(self, device_ptr: int, first: int = 0, n: int | None = None):
+        """Packs the per-frame counts into a device int32[n][4] array (e.g. a torch tensor) on the context's stream."""
+        n = self.max_frames - first if n is None else n
+        self.ctx.check(self.ctx.lib.slamcu_sequence_counts_device(self.handle, first, n, C.c_void_p(device_ptr)))
+
     def essential(self, K4, first: int = 0, n_pairs: int | None = None, prob: float = 0.999, threshold: float = 1.0,
                   max_iters: int = 1000):
         """cv::findEssentialMat(RANSAC) on the matches of every pair (f, f+1) of the range; asynchronous."""

@@ -16,7 +16,9 @@ What is exact and what is not ("two-view geometry"):
   over a set of problems: masks IDENTICAL to cv2's on at least the stated fraction (>= 0.9 for genuine 3-D two-view geometry,
   >= 0.7 on the pure-image-translation synthetic sequences, which are a degenerate configuration for E); where the masks are
   identical, E agrees with cv2's up to sign within max(1e-9, 100 d), d = |E_numpy - E_cv2| being what the independent numpy
-  restatement achieves on that problem (d / 2.2e-16 estimates the condition number of the winning sample).
+  restatement achieves on that problem (d / 2.2e-16 estimates the condition number of the winning sample).  E is NOT compared
+  on the pure-image-translation sequences (check_E=False): the data do not determine it there -- a family of essential matrices
+  explains the same flow, and identical inlier masks come with E's that are 1e-2 apart in cv2, numpy and on the device alike.
 """
 import numpy as np
 
@@ -34,7 +36,7 @@ def cv2_essential(p1, p2, K4, max_iters=1000):
     return E, mask
 
 
-def compare(p1, p2, K4, dev_E, dev_mask, max_iters=1000, threshold=1.0):
+def compare(p1, p2, K4, dev_E, dev_mask, max_iters=1000, threshold=1.0, check_E=True):
     """Returns (ok, info): ok = the per-problem tolerance holds; info carries mask_equal / jaccard / dE for the set-level checks."""
     from oracle import essential_oracle as eo
     p1 = np.ascontiguousarray(p1, np.float32)
@@ -53,7 +55,7 @@ def compare(p1, p2, K4, dev_E, dev_mask, max_iters=1000, threshold=1.0):
     if info["mask_equal"] and cgood > 0 and cE is not None:
         d = e_dist(dev_E, cE)
         info["dE"] = d
-        if d >= 1e-9:
+        if d >= 1e-9 and check_E:
             nE, nmask, _ = eo.find_essential(p1, p2, K4, max_iters=max_iters)
             tol = max(1e-9, 100.0 * e_dist(nE, cE)) if nE is not None else 1.0
             info["tol"] = tol

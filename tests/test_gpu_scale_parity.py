@@ -131,7 +131,7 @@ def test_config3_full_size_ransac_vs_cv2(gpu_ctx):
         p2 = np.stack([kb["x"][m["trainIdx"]], kb["y"][m["trainIdx"]]], 1).astype(np.float32)
         E1, mask1, good1 = s.find_essential(p1, p2, K4, context=gpu_ctx)  # batched path == single-call path, bit for bit
         assert np.array_equal(mask, mask1) and good == good1 and (good == 0 or np.array_equal(E, E1))
-        ok, info = compare(p1, p2, K4, E, mask)
+        ok, info = compare(p1, p2, K4, E, mask, check_E=False)  # degenerate geometry: E is not determined by the data
         assert ok, f"pair {f}: {info}"
         checked += 1
         equal += info["mask_equal"]

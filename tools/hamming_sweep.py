@@ -1,6 +1,6 @@
 """BASELINE.json config 5: all-pairs Hamming matching sweep, n x n 256-bit descriptors, k = 2 (+ ratio test through
 FeatureMatcher.match).  Reports G comparisons/s of the match kernel (CUDA events around the kernel, via the library's
-profiler) and of the whole host call (H2D + kernel + D2H).  Run on a GPU box:  python tools/hamming_sweep.py
+profiler) and of the whole host call (H2D + kernel + D2H).  Run on a GPU box:  python tools/hamming_sweep.py  (--quick: one JSON line on stdout, used by bench.py's `hamming_sweep` leg)
 Writes gpurun_out/hamming_sweep.json (copy under profiles/ to keep)."""
 import json
 import os
@@ -17,6 +17,7 @@ POP = np.array([bin(i).count("1") for i in range(256)], np.int32)
 
 
 def main():
+    quick = "--quick" in sys.argv
     ctx = S.Context(0)
     mat = S.FeatureMatcher(dict(DistanceType="HAMMING", FilterMatches=0, GoodMatchesCount=1, UseRatioTest=1,
                                 RatioTestThreshold=0.75), ctx)
@@ -44,7 +45,13 @@ def main():
         row = {"n": n, "kernel_ms": k_ms, "kernel_gcmp_s": n * n / k_ms / 1e6, "host_call_ms": wall * 1e3,
                "host_call_gcmp_s": n * n / wall / 1e9, "frac_of_4popc_peak": n * n / k_ms / 1e6 / (gpopc / 4.0), "spot_check": ok}
         out["rows"].append(row)
-        print(row, flush=True)
+        if not quick:
+            print(row, flush=True)
+    out["metric"] = "G Hamming cmp/s, n x n 256-bit descriptors, k=2"
+    out["value_at_64k"] = out["rows"][-1]["kernel_gcmp_s"]
+    if quick:  # bench.py's extra leg: one JSON line
+        print(json.dumps(out), flush=True)
+        return
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump(out, open(os.path.join(ROOT, "gpurun_out", "hamming_sweep.json"), "w"), indent=1)
 
