@@ -300,6 +300,7 @@ int slamcu_create(int device_id, slamcu_context** out) {
     init_sortnms_attributes(ctx->smem_optin);
     init_orb_attributes(ctx->smem_optin);
     init_essential_attributes();
+    init_match_attributes();
     *out = ctx;
     return SLAMCU_OK;
 }
@@ -836,6 +837,7 @@ int slamcu_sequence_match(slamcu_sequence* s, slamcu_matcher* m, int first, int 
     j.or_stride = v.desc_words;
     j.desc_words = v.desc_words;
     j.max_q = v.cap_kp;
+    j.max_t = v.cap_kp;
     j.cap_out = v.cap_kp;
     ctx->launches += launch_match(j, n_pairs, m->p, true, with_kp ? 1 : 0, s->sort_keys + (size_t)first * v.cap_kp,
                                   ctx->stream);
@@ -1545,6 +1547,7 @@ static int match_common(slamcu_matcher* m, const uint8_t* d1, int n1, int width1
     j.status = m->counts + 3;
     j.desc_words = words;
     j.max_q = n1;
+    j.max_t = n2;
     j.cap_out = n1;
     // a single problem: slice the train set so that the grid fills the device (>= ~4 blocks per SM), 128-descriptor
     // tiles at least; the batched sequence path has thousands of blocks and does not need it

@@ -72,10 +72,12 @@ struct MatchJob {
     size_t cand_pair_stride;   // entries between pairs in cand / matches
     int or_stride;
     int desc_words, max_q, cap_out;
+    int max_t;                 // upper bound of the train counts (sizes the shared-memory tile)
 };
 // sort_keys: [n_pairs][cand_pair_stride] 64-bit scratch for the top-K / sort stage
 // n_seg > 1 splits the train set into n_seg slices of seg_len descriptors (extra grid dimension, for single small
 // problems); job.cand must then hold n_seg blocks of seg_stride entries, slice 0 doubling as the merged result
+void init_match_attributes();
 int launch_match(const MatchJob& job, int n_pairs, const MatchParams& p, bool emit_matches, int with_kp,
                  unsigned long long* sort_keys, cudaStream_t st, int n_seg = 1, int seg_len = 0, size_t seg_stride = 0);
 

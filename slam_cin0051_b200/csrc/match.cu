@@ -9,6 +9,8 @@
 //                     The image-distance penalty (:161-170) uses the same IEEE float ops, no FMA.
 //   finalize_kernel : ratio test (:175-187), emission in query order, then filterAndSortMatches
 //                     (:191-204) with libstdc++'s std::partial_sort / std::sort permutation (exact.cuh).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "exact.cuh"
 
@@ -175,6 +177,134 @@ __global__ void __launch_bounds__(QT) match_kernel(MatchJob job, int with_kp, in
     if (qok) job.cand[(size_t)blockIdx.z * seg_stride + (size_t)pair * job.cand_pair_stride + q] = make_int4(t.bidx, t.best, t.second, t.sidx);
 }
 
+// ---- the penalty-free 256-bit path (cv::BFMatcher::knnMatch(k = 2) / FeatureMatcher::match without keypoints) -------
+// One block = 128 threads x 2 queries held in registers; the train set is staged through shared memory in tiles of 512
+// descriptors (16 KB; up to 2048 through SLAMCU_MATCH_TILE), one barrier pair per 1024 comparisons of a thread (the
+// 128-descriptor tiles of match_kernel paid one per 128: 15 % of its stall samples).
+// Per train descriptor two broadcast LDS.128 serve both queries; per comparison: 8 XOR + 8 LOP3 (carry-save tree) on the ALU
+// pipe, 4 POPC on the XU pipe, the weighted sum and the (distance << 20 | index) key as integer multiply-adds (FMA pipe),
+// and the running top-2 as min / max on packed keys.  Instruction budget per comparison ~28 (was 32).
+constexpr int MQ = 2, MTHR = 128, MQB = MQ * MTHR;
+constexpr int kMaxTile256 = 2048;   // largest tile the kernel may be given (64 KB)
+constexpr int kDefTile256 = 512;    // default: 16 KB per block -> nine 4-warp blocks per SM (measured: 2048 -> 780, 1024 -> 841, 512 -> 848, 256 -> 847 Gcmp/s)
+
+__device__ __forceinline__ uint32_t mad_u32(uint32_t a, uint32_t b, uint32_t c) {  // IMAD: runs on the FMA pipe, not the ALU pipe
+    uint32_t r;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+
+// full adder on bit planes with explicit LOP3 truth tables (sum = a ^ b ^ c: 0x96, carry = majority: 0xE8): one instruction
+// each.  Written as inline PTX so that the comparison costs exactly 8 XOR + 8 LOP3: left to itself ptxas re-associates the
+// query / train XORs into the adders' inputs and ends up with 22 LOP3 per comparison when two queries share the train words.
+__device__ __forceinline__ uint32_t lop3_sum(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+__device__ __forceinline__ uint32_t lop3_maj(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+
+__device__ __forceinline__ uint32_t hamming256_key(const uint32_t (&q)[8], const uint4& a, const uint4& b, uint32_t idx, uint32_t w1, uint32_t w2,
+                                                   uint32_t w4) {
+    const uint32_t x0 = q[0] ^ a.x, x1 = q[1] ^ a.y, x2 = q[2] ^ a.z, x3 = q[3] ^ a.w;
+    const uint32_t x4 = q[4] ^ b.x, x5 = q[5] ^ b.y, x6 = q[6] ^ b.z, x7 = q[7] ^ b.w;
+    const uint32_t s1 = lop3_sum(x0, x1, x2), c1 = lop3_maj(x0, x1, x2);
+    const uint32_t s2 = lop3_sum(x3, x4, x5), c2 = lop3_maj(x3, x4, x5);
+    const uint32_t ones = lop3_sum(s1, s2, x6), c3 = lop3_maj(s1, s2, x6);
+    const uint32_t twos = lop3_sum(c1, c2, c3), fours = lop3_maj(c1, c2, c3);
+    // key = (popc(ones) + popc(x7) + 2 popc(twos) + 4 popc(fours)) << 20 | idx, as four multiply-adds; the weights come in
+    // registers (w1 = 1 << 20 is a kernel argument) so that ptxas keeps IMADs instead of turning them into ALU-pipe LEAs
+    uint32_t k = mad_u32((uint32_t)__popc(ones), w1, idx);
+    k = mad_u32((uint32_t)__popc(x7), w1, k);
+    k = mad_u32((uint32_t)__popc(twos), w2, k);
+    return mad_u32((uint32_t)__popc(fours), w4, k);
+}
+
+__global__ void __launch_bounds__(MTHR) match256_kernel(MatchJob job, int n_seg, int seg_len, size_t seg_stride, int tile_cap, uint32_t w1) {
+    extern __shared__ __align__(16) uint32_t smem[];
+    uint4* tile = reinterpret_cast<uint4*>(smem);  // [tile_cap][2]
+    const int pair = blockIdx.y;
+    const int nq = job.nq[(size_t)pair * job.count_stride];
+    const int nt = job.nt[(size_t)pair * job.count_stride];
+    const int q0 = blockIdx.x * MQB;
+    if (q0 >= nq || nt <= 0) return;
+    const uint32_t* dq = job.dq + (size_t)pair * job.desc_pair_stride;
+    const uint4* dt = reinterpret_cast<const uint4*>(job.dt + (size_t)pair * job.desc_pair_stride);
+    // words that can be non-zero in either set: the reference's own 46-bit descriptors populate two words
+    int wmax = 8;
+    if (job.orq && job.ort) {
+        const uint32_t* oq = job.orq + (size_t)pair * job.or_stride;
+        const uint32_t* ot = job.ort + (size_t)pair * job.or_stride;
+        while (wmax > 1 && (oq[wmax - 1] | ot[wmax - 1]) == 0u) wmax--;
+    }
+    uint32_t qd[MQ][8];
+    bool qok[MQ];
+#pragma unroll
+    for (int m = 0; m < MQ; m++) {
+        const int q = q0 + m * MTHR + threadIdx.x;
+        qok[m] = q < nq;
+        const uint4* src = reinterpret_cast<const uint4*>(dq + (size_t)(qok[m] ? q : q0) * 8);
+        const uint4 lo = __ldg(src), hi = __ldg(src + 1);
+        qd[m][0] = lo.x; qd[m][1] = lo.y; qd[m][2] = lo.z; qd[m][3] = lo.w;
+        qd[m][4] = hi.x; qd[m][5] = hi.y; qd[m][6] = hi.z; qd[m][7] = hi.w;
+    }
+    uint32_t kbest[MQ], ksecond[MQ];
+#pragma unroll
+    for (int m = 0; m < MQ; m++) kbest[m] = ksecond[m] = 0xffffffffu;
+    const uint32_t w2 = w1 * 2u, w4 = w1 * 4u;
+
+    const int t_begin = n_seg > 1 ? (int)blockIdx.z * seg_len : 0;
+    const int t_end = n_seg > 1 ? min(nt, t_begin + seg_len) : nt;
+    for (int t0 = t_begin; t0 < t_end; t0 += tile_cap) {
+        const int cnt = min(tile_cap, t_end - t0);
+        if (t0 != t_begin) __syncthreads();  // everyone is done with the previous tile
+        {
+            const uint4* src = dt + (size_t)t0 * 2;
+            const int nv = cnt * 2;
+            int v = threadIdx.x;
+            for (; v + 7 * MTHR < nv; v += 8 * MTHR) {  // eight 128-bit loads in flight per thread
+                uint4 r[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) r[k] = __ldg(src + v + k * MTHR);
+#pragma unroll
+                for (int k = 0; k < 8; k++) tile[v + k * MTHR] = r[k];
+            }
+            for (; v < nv; v += MTHR) tile[v] = __ldg(src + v);
+        }
+        __syncthreads();
+        if (wmax > 2) {
+#pragma unroll 4
+            for (int j = 0; j < cnt; j++) {
+                const uint4 a = tile[2 * j], b = tile[2 * j + 1];
+#pragma unroll
+                for (int m = 0; m < MQ; m++) top2_update_key(kbest[m], ksecond[m], hamming256_key(qd[m], a, b, (uint32_t)(t0 + j), w1, w2, w4));
+            }
+        } else {
+#pragma unroll 4
+            for (int j = 0; j < cnt; j++) {
+                const uint4 a = tile[2 * j];
+#pragma unroll
+                for (int m = 0; m < MQ; m++) {
+                    const uint32_t d = (uint32_t)(__popc(qd[m][0] ^ a.x) + __popc(qd[m][1] ^ a.y));
+                    top2_update_key(kbest[m], ksecond[m], mad_u32(d, w1, (uint32_t)(t0 + j)));
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < MQ; m++) {
+        if (!qok[m]) continue;
+        int4 c = make_int4(-1, INT_MAX, INT_MAX, -1);
+        if (kbest[m] != 0xffffffffu) { c.y = (int)(kbest[m] >> kKeyShift); c.x = (int)(kbest[m] & ((1u << kKeyShift) - 1)); }
+        if (ksecond[m] != 0xffffffffu) { c.z = (int)(ksecond[m] >> kKeyShift); c.w = (int)(ksecond[m] & ((1u << kKeyShift) - 1)); }
+        job.cand[(size_t)blockIdx.z * seg_stride + (size_t)pair * job.cand_pair_stride + q0 + m * MTHR + threadIdx.x] = c;
+    }
+}
+
 __global__ void __launch_bounds__(256) merge_segments_kernel(MatchJob job, int n_seg, size_t seg_stride) {
     const int pair = blockIdx.y;
     const int nq = job.nq[(size_t)pair * job.count_stride];
@@ -290,16 +420,28 @@ __global__ void __launch_bounds__(256) finalize_kernel(MatchJob job, MatchParams
 
 }  // namespace
 
+void init_match_attributes() { cudaFuncSetAttribute(match256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxTile256 * 32); }
+
 int launch_match(const MatchJob& job, int n_pairs, const MatchParams& p, bool emit_matches, int with_kp,
                  unsigned long long* sort_keys, cudaStream_t st, int n_seg, int seg_len, size_t seg_stride) {
     if (n_pairs <= 0) return 0;
     if (n_seg < 1) n_seg = 1;
-    dim3 grid((job.max_q + QT - 1) / QT, n_pairs, n_seg);
-    const size_t smem = (size_t)TT * job.desc_words * 4 + TT * sizeof(float2);
-    if (job.desc_words == 8)
-        SLAM_KERNEL("match", st, match_kernel<8><<<grid, QT, smem, st>>>(job, with_kp, n_seg, seg_len, seg_stride));
-    else
-        SLAM_KERNEL("match", st, match_kernel<0><<<grid, QT, smem, st>>>(job, with_kp, n_seg, seg_len, seg_stride));
+    if (job.desc_words == 8 && !with_kp && job.max_t <= (1 << kKeyShift)) {
+        // 256-bit descriptors, no image-distance penalty: whole train slice in shared memory, two queries per thread
+        const int span = n_seg > 1 ? seg_len : job.max_t;
+        static const int tile_env = [] { const char* e = getenv("SLAMCU_MATCH_TILE"); return e ? atoi(e) : 0; }();  // tuning knob (descriptors per smem tile)
+        const int tile_max = tile_env >= 64 && tile_env <= kMaxTile256 ? tile_env / 64 * 64 : kDefTile256;
+        const int tile_cap = max(64, min(tile_max, (span + 63) / 64 * 64));
+        dim3 grid((job.max_q + MQB - 1) / MQB, n_pairs, n_seg);
+        SLAM_KERNEL("match", st, match256_kernel<<<grid, MTHR, (size_t)tile_cap * 32, st>>>(job, n_seg, seg_len, seg_stride, tile_cap, 1u << kKeyShift));
+    } else {
+        dim3 grid((job.max_q + QT - 1) / QT, n_pairs, n_seg);
+        const size_t smem = (size_t)TT * job.desc_words * 4 + TT * sizeof(float2);
+        if (job.desc_words == 8)
+            SLAM_KERNEL("match", st, match_kernel<8><<<grid, QT, smem, st>>>(job, with_kp, n_seg, seg_len, seg_stride));
+        else
+            SLAM_KERNEL("match", st, match_kernel<0><<<grid, QT, smem, st>>>(job, with_kp, n_seg, seg_len, seg_stride));
+    }
     int launches = 1;
     if (n_seg > 1) {
         SLAM_KERNEL("match_merge", st,
