@@ -741,6 +741,10 @@ static int seq_ensure_orb(slamcu_sequence* s, slamcu_detector* det) {
                 ok = encode(&s->tmaps.fast[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, base, dims, strides, box, estr,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+                const cuuint32_t bbox[3] = {(cuuint32_t)kBlurBoxW, (cuuint32_t)kBlurBoxH, 1};
+                ok = ok && encode(&s->tmaps.blur[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, base, dims, strides, bbox, estr,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
             }
             s->tmaps.valid = ok;
         }

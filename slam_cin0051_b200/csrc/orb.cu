@@ -16,6 +16,8 @@
 //   blur7_kernel        B7  7x7 sigma=2 float separable blur with OpenCV's FMA placement, cvRound
 //   orb_describe_kernel B6+B8  intensity-centroid angle (fastAtan2 polynomial, no FMA) + rBRIEF-256,
 //                           warp per keypoint, one descriptor byte per lane
+#include <cstdlib>
+
 #include "orb.cuh"
 
 namespace slamcu {
@@ -691,9 +693,16 @@ __global__ void __launch_bounds__(256) orb_assemble_kernel(SeqView s, OrbView o,
 // ---- B7 ----------------------------------------------------------------------------------------------------
 // 7x7 sigma=2 separable float blur with OpenCV's rounding: row pass s = k0*S0, s = fma(k_j, S_j, s) (j = 1..6),
 // column pass s = k3*R0, s = fma(k_{3+j}, R_{+j} + R_{-j}, s) (j = 1..3), cvRound (half to even), saturate.
-// 64x32 output tile per block; bytes are staged once in shared memory, the row pass converts them with a
-// PRMT + FADD (0x4B000000 | byte is the float 2^23 + byte), four outputs per thread in both passes.
-constexpr int GW = 64, GH = 32, GIW = GW + 8, GIH = GH + 6;
+//
+// 128 x 64 output tile per block of 4 warps.  The tile (+4 px / 3 row halo, reflected at the image border) is staged ONCE as
+// floats in shared memory (PRMT + FADD: 0x4B000000 | byte is the float 2^23 + byte).  Then every lane walks a 4-pixel-wide
+// column strip down 16 output rows with the last seven row-pass results in registers (the loop is fully unrolled, so the
+// window rotates by renaming): per input row 3 LDS.128 + 28 FMA, per output row 28 column-pass operations, 4 conversions
+// and one 32-bit store.  No second shared-memory buffer, no barrier after staging, and almost no address arithmetic -- the
+// previous two-pass version (row results through shared memory) executed 50 instructions per pixel for 20 of arithmetic.
+constexpr int BW = 128, BRS = 15, BWARPS = 4, BTH = BRS * BWARPS;  // tile width, rows per warp strip, warps, tile height (60)
+constexpr int BIW = BW + 8, BIH = BTH + 6;                          // staged floats per row (x0-4 .. x0+BW+3), staged rows (66)
+static_assert((BRS + 6) % 7 == 0, "the strip loop is unrolled by the window depth");
 __device__ __forceinline__ int reflect101(int i, int n) {
     if (i < 0) i = -i;
     if (i >= n) i = 2 * n - 2 - i;
@@ -709,94 +718,133 @@ __device__ __forceinline__ unsigned sat_u8_rn(float v) {  // cvRound (round half
     return r;
 }
 
-__global__ void __launch_bounds__(256) blur7_kernel(SeqView s, OrbView o, int first, int l) {
-    __shared__ __align__(16) float tin[GIH * GIW];        // pixels x0-4 .. x0+GW+3, rows y0-3 .. y0+GH+2, as floats
-    __shared__ __align__(16) float trow[GIH * GW];
+constexpr int BBW = kBlurBoxW, BBH = kBlurBoxH, BBX = 16;  // byte tile: pixels x0-16 .. x0+143 (160 B rows), rows y0-3 .. y0+62
+static_assert(BBW == BW + 2 * BBX && BBH == BIH, "blur tile geometry");  // (the TMA start coordinate stays a multiple of 16 bytes)
+
+constexpr int kBlurTileBytes = (BBH * BBW + 127) / 128 * 128;  // every TMA destination stays 128-byte aligned
+constexpr size_t kBlurSmemBytes = 2 * kBlurTileBytes + BIH * BIW * sizeof(float) + 16;
+static_assert((BIH * BIW * sizeof(float)) % 8 == 0, "blur shared-memory carve-up");
+// One block walks `tiles_per_block` vertically adjacent tiles of one tile column: while it converts and filters tile t, the
+// TMA engine is already writing tile t+1 into the other byte buffer (two mbarriers, one per buffer), so the global-memory
+// latency of the staging is off the critical path and the block's set-up cost is paid once per column.
+template <bool kTma>
+__global__ void __launch_bounds__(BWARPS * 32) blur7_kernel(SeqView s, OrbView o, int first, int l, int tiles_per_block,
+                                                            const __grid_constant__ CUtensorMap tmap) {
+    extern __shared__ __align__(128) uint8_t blur_smem[];  // kBlurSmemBytes: two byte tiles, the float tile, two mbarriers
+    uint8_t(*tb)[kBlurTileBytes] = reinterpret_cast<uint8_t(*)[kBlurTileBytes]>(blur_smem);
+    float* tin = reinterpret_cast<float*>(blur_smem + 2 * kBlurTileBytes);
+    uint64_t* tma_bar = reinterpret_cast<uint64_t*>(blur_smem + 2 * kBlurTileBytes + BIH * BIW * sizeof(float));
     const int f = first + blockIdx.z;
     const OrbLevel& L = o.lv[l];
     const uint8_t* img = level_ptr(s, o, f, l);
     uint8_t* out = blur_ptr(s, o, f, l);
-    const int x0 = blockIdx.x * GW, y0 = blockIdx.y * GH;
+    const int x0 = blockIdx.x * BW;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tiles_y = (L.rows + BTH - 1) / BTH;
+    const int t_begin = blockIdx.y * tiles_per_block, t_end = min(tiles_y, t_begin + tiles_per_block);
+    if (t_begin >= t_end) return;
     // getGaussianKernel(7, 2, CV_32F) (bit patterns of the cv2 result; OpenCV computes exp(-x^2/8) normalised)
     const float k0 = __uint_as_float(0x3d8fafb1u), k1 = __uint_as_float(0x3e06387eu), k2 = __uint_as_float(0x3e434a39u),
                 k3 = __uint_as_float(0x3e5d4ae0u);
-    const bool interior = x0 >= 4 && x0 + GW + 3 <= L.cols;  // no horizontal reflection inside the staged span
-    // stage: bytes -> floats once; the three word loads of a thread are issued together (latency overlap)
-    if (interior) {
-        constexpr int NW = GIH * (GIW / 4);  // 684 words
-        unsigned w[3];
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-            const int i = threadIdx.x + 256 * k;
-            const int r = i / (GIW / 4), c = i - r * (GIW / 4);
-            w[k] = 0;
-            if (i < NW)
-                w[k] = __ldg(reinterpret_cast<const uint32_t*>(img + (size_t)reflect101(y0 - 3 + r, L.rows) * L.pitch + x0 - 4) + c);
+    if (kTma) {
+        if (threadIdx.x == 0) {
+            mbar_init(&tma_bar[0], 1);
+            mbar_init(&tma_bar[1], 1);
         }
+        __syncthreads();
+        if (threadIdx.x == 0) tma_load_3d(tb[0], &tmap, x0 - BBX, t_begin * BTH - 3, f, &tma_bar[0], BBH * BBW);
+    }
+    constexpr int WPR = BIW / 4;  // 34 float4 per staged row
+    const int x = x0 + 4 * lane;
+    const int pitch = L.pitch;
+    for (int t = t_begin; t < t_end; t++) {
+        const int y0 = t * BTH, buf = (t - t_begin) & 1;
+        // ---- stage 1: the byte tile, zero outside the level (TMA: issued one tile ahead; LDG fallback: filled here)
+        if (kTma) {
+            if (threadIdx.x == 0 && t + 1 < t_end)  // buffer buf^1 was last read before the barrier that ended tile t-1
+                tma_load_3d(tb[buf ^ 1], &tmap, x0 - BBX, (t + 1) * BTH - 3, f, &tma_bar[buf ^ 1], BBH * BBW);
+            mbar_wait(&tma_bar[buf], ((t - t_begin) >> 1) & 1);
+        } else {
+            for (int i = threadIdx.x; i < BBH * (BBW / 4); i += BWARPS * 32) {
+                const int r = i / (BBW / 4), c = i - r * (BBW / 4);
+                const int gy = y0 - 3 + r, gx = x0 - BBX + 4 * c;
+                unsigned w = 0;
+                if (gy >= 0 && gy < L.rows && gx >= 0 && gx < L.pitch) {
+                    w = __ldg(reinterpret_cast<const uint32_t*>(img + (size_t)gy * L.pitch + gx));
+                    if (gx + 3 >= L.cols) w &= gx >= L.cols ? 0u : (0xffffffffu >> (8 * (gx + 4 - L.cols)));
+                }
+                reinterpret_cast<uint32_t*>(tb[buf])[i] = w;
+            }
+            __syncthreads();
+        }
+        // ---- stage 2: bytes -> floats once per pixel, BORDER_REFLECT_101 applied by reading the reflected position INSIDE
+        // the byte tile (a reflected pixel is never more than 4 px / 3 rows away from the border)
+        const int rows_needed = min(BTH, L.rows - y0) + 6;
+        for (int i = threadIdx.x; i < rows_needed * WPR; i += BWARPS * 32) {
+            const int r = i / WPR, c = i - r * WPR;
+            const int gx = x0 - 4 + 4 * c;
+            const int tr = max(reflect101(y0 - 3 + r, L.rows) - (y0 - 3), 0);
+            const uint8_t* row = tb[buf] + tr * BBW;
+            unsigned w;
+            if (gx >= 0 && gx + 3 < L.cols) {
+                w = *reinterpret_cast<const uint32_t*>(row + 4 * c + (BBX - 4));
+            } else {
+                w = 0;
 #pragma unroll
-        for (int k = 0; k < 3; k++) {
-            const int i = threadIdx.x + 256 * k;
-            if (i < NW) {
-                float4 v;
-                v.x = byte_to_float(w[k], 0x7440u);
-                v.y = byte_to_float(w[k], 0x7441u);
-                v.z = byte_to_float(w[k], 0x7442u);
-                v.w = byte_to_float(w[k], 0x7443u);
-                reinterpret_cast<float4*>(tin)[i] = v;
+                for (int k = 0; k < 4; k++) w |= (unsigned)row[min(max(reflect101(gx + k, L.cols) - (x0 - BBX), 0), BBW - 1)] << (8 * k);
+            }
+            float4 v;
+            v.x = byte_to_float(w, 0x7440u);
+            v.y = byte_to_float(w, 0x7441u);
+            v.z = byte_to_float(w, 0x7442u);
+            v.w = byte_to_float(w, 0x7443u);
+            reinterpret_cast<float4*>(tin)[i] = v;
+        }
+        __syncthreads();
+        // ---- filter: this lane's 4-pixel-wide strip of 15 output rows, seven row-pass results in registers
+        const int ys = y0 + warp * BRS;
+        if (ys < L.rows && x < pitch) {
+            const int nout = min(BRS, L.rows - ys);
+            const float4* src = reinterpret_cast<const float4*>(tin + (warp * BRS) * BIW) + lane;
+            uint8_t* dst = out + (size_t)ys * pitch + x;
+            float win[7][4];
+            for (int base = 0; base < BRS + 6; base += 7) {  // unrolled by the window depth: the slots are compile-time registers
+#pragma unroll
+                for (int jj = 0; jj < 7; jj++) {
+                    const int i = base + jj;
+                    if (i < nout + 6) {
+                        const float4 a = src[0], b = src[1], d = src[2];
+                        src += BIW / 4;
+                        const float p[10] = {a.y, a.z, a.w, b.x, b.y, b.z, b.w, d.x, d.y, d.z};  // pixels x-3 .. x+6
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            float v = k0 * p[k];
+                            v = fmaf(k1, p[k + 1], v);
+                            v = fmaf(k2, p[k + 2], v);
+                            v = fmaf(k3, p[k + 3], v);
+                            v = fmaf(k2, p[k + 4], v);
+                            v = fmaf(k1, p[k + 5], v);
+                            v = fmaf(k0, p[k + 6], v);
+                            win[jj][k] = v;
+                        }
+                        if (i >= 6) {  // staged rows i-6 .. i are in the window: emit output row i-6, centred on staged row i-3
+                            unsigned v[4];
+#pragma unroll
+                            for (int k = 0; k < 4; k++) {
+                                float acc = k3 * win[(jj + 4) % 7][k];
+                                acc = fmaf(k2, win[(jj + 5) % 7][k] + win[(jj + 3) % 7][k], acc);
+                                acc = fmaf(k1, win[(jj + 6) % 7][k] + win[(jj + 2) % 7][k], acc);
+                                acc = fmaf(k0, win[jj][k] + win[(jj + 1) % 7][k], acc);
+                                v[k] = sat_u8_rn(acc);
+                            }
+                            *reinterpret_cast<uint32_t*>(dst) = __byte_perm(__byte_perm(v[0], v[1], 0x0040), __byte_perm(v[2], v[3], 0x0040), 0x5410);
+                            dst += pitch;
+                        }
+                    }
+                }
             }
         }
-    } else {
-        for (int r = warp; r < GIH; r += 8) {
-            const uint8_t* row = img + (size_t)reflect101(y0 - 3 + r, L.rows) * L.pitch;
-            for (int c = lane; c < GIW; c += 32) tin[r * GIW + c] = (float)row[reflect101(x0 - 4 + c, L.cols)];
-        }
-    }
-    __syncthreads();
-    // row pass: 4 outputs per thread from 12 staged floats (pixels x-4 .. x+7 of the outputs at x .. x+3)
-    for (int i = threadIdx.x; i < GIH * (GW / 4); i += 256) {
-        const int r = i >> 4, c = i & 15;
-        const float4* w = reinterpret_cast<const float4*>(tin + r * GIW) + c;
-        const float4 a = w[0], b = w[1], d = w[2];
-        const float p[10] = {a.y, a.z, a.w, b.x, b.y, b.z, b.w, d.x, d.y, d.z};  // pixels x-3 .. x+6
-        float4 acc;
-        float* q = &acc.x;
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            float v = k0 * p[k];
-            v = fmaf(k1, p[k + 1], v);
-            v = fmaf(k2, p[k + 2], v);
-            v = fmaf(k3, p[k + 3], v);
-            v = fmaf(k2, p[k + 4], v);
-            v = fmaf(k1, p[k + 5], v);
-            v = fmaf(k0, p[k + 6], v);
-            q[k] = v;
-        }
-        reinterpret_cast<float4*>(trow)[i] = acc;
-    }
-    __syncthreads();
-    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-#pragma unroll
-    for (int pass = 0; pass < GH / 16; pass++) {
-        const int r = ty + 16 * pass;
-        const int gy = y0 + r;
-        if (gy >= L.rows) break;
-        const float4* q = reinterpret_cast<const float4*>(trow) + (r + 3) * (GW / 4) + tx;
-        const float4 c0 = q[0], a1 = q[GW / 4], b1 = q[-(GW / 4)], a2 = q[2 * (GW / 4)], b2 = q[-2 * (GW / 4)],
-                     a3 = q[3 * (GW / 4)], b3 = q[-3 * (GW / 4)];
-        const float* pc = &c0.x;
-        const float *pa1 = &a1.x, *pb1 = &b1.x, *pa2 = &a2.x, *pb2 = &b2.x, *pa3 = &a3.x, *pb3 = &b3.x;
-        unsigned v[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            float acc = k3 * pc[k];
-            acc = fmaf(k2, pa1[k] + pb1[k], acc);
-            acc = fmaf(k1, pa2[k] + pb2[k], acc);
-            acc = fmaf(k0, pa3[k] + pb3[k], acc);
-            v[k] = sat_u8_rn(acc);
-        }
-        const uint32_t packed = __byte_perm(__byte_perm(v[0], v[1], 0x0040), __byte_perm(v[2], v[3], 0x0040), 0x5410);
-        if (x0 + tx * 4 < L.pitch) *reinterpret_cast<uint32_t*>(out + (size_t)gy * L.pitch + x0 + tx * 4) = packed;
+        __syncthreads();  // tin (and, one tile later, this byte buffer) may be overwritten
     }
 }
 
@@ -910,6 +958,11 @@ __global__ void __launch_bounds__(128) orb_describe_kernel(SeqView s, OrbView o,
 
 void init_orb_attributes(int smem_optin) {
     cudaFuncSetAttribute(orb_retain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    // 56 KB of dynamic shared memory per 4-warp block (above the 48 KB default limit), four blocks per SM
+    cudaFuncSetAttribute(blur7_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBlurSmemBytes);
+    cudaFuncSetAttribute(blur7_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBlurSmemBytes);
+    cudaFuncSetAttribute(blur7_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(blur7_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     (void)smem_optin;
 }
 
@@ -944,8 +997,15 @@ int launch_orb_extract(const SeqView& s, const OrbView& o, int first, int n, cud
         cudaStreamWaitEvent(aux, ev_fork, 0);
     }
     for (int l = 0; l < o.nlevels; l++) {
-        dim3 grid((o.lv[l].cols + GW - 1) / GW, (o.lv[l].rows + GH - 1) / GH, n);
-        SLAM_KERNEL("blur7", bs, blur7_kernel<<<grid, 256, 0, bs>>>(s, o, first, l));
+        // a block takes a whole column of tiles when there are frames enough to fill the device, fewer for small batches
+        const int tx = (o.lv[l].cols + BW - 1) / BW, ty = (o.lv[l].rows + BTH - 1) / BTH;
+        const int tpb = max(1, min(ty, (int)((long long)tx * ty * n / 1200)));
+        dim3 grid(tx, (ty + tpb - 1) / tpb, n);
+        static const bool no_tma = getenv("SLAMCU_NO_TMA") != nullptr;  // debugging aid: stage every tile with plain loads
+        if (tmaps && tmaps->valid && !no_tma)
+            SLAM_KERNEL("blur7", bs, blur7_kernel<true><<<grid, BWARPS * 32, kBlurSmemBytes, bs>>>(s, o, first, l, tpb, tmaps->blur[l]));
+        else
+            SLAM_KERNEL("blur7", bs, blur7_kernel<false><<<grid, BWARPS * 32, kBlurSmemBytes, bs>>>(s, o, first, l, tpb, CUtensorMap{}));
         launches++;
     }
     if (forked) cudaEventRecord(ev_join, aux);

@@ -57,9 +57,11 @@ struct OrbView {
 // outside the level, box = the FAST tile with its halo.  valid == false -> the kernels stage tiles with LDG instead.
 struct OrbTmaps {
     CUtensorMap fast[kMaxLevels];
+    CUtensorMap blur[kMaxLevels];
     bool valid = false;
 };
 constexpr int kFastBoxW = 160, kFastBoxH = 56;  // FSW x FSH of fast9_mask_kernel
+constexpr int kBlurBoxW = 160, kBlurBoxH = 66;  // byte tile of blur7_kernel (128 x 60 outputs + 16 px / 3 row halo)
 
 // aux / ev_fork / ev_join: optional second stream (and two events) on which the blur kernels run concurrently
 int launch_orb_extract(const SeqView& s, const OrbView& o, int first, int n, cudaStream_t st, cudaStream_t aux = nullptr,
