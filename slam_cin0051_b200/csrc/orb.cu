@@ -185,54 +185,30 @@ __device__ __forceinline__ void fast9_load_ring(const uint8_t* t, int stride, in
     for (int k = 0; k < 16; k++) p[k] = t[dys[k] * stride + dxs[k]];
 }
 
-// Segment test.  Returns 0 (no corner), 1 (a 9-arc of brighter pixels) or 2 (a 9-arc of darker pixels); both cannot
-// hold at once (two disjoint 9-arcs do not fit in 16).  The ring masks are built by shifting in sign bits:
-// p > up  <=>  up - p < 0.
-__device__ __forceinline__ int fast9_corner_kind(int v, const int (&p)[16], int thr) {
-    const int up = v + thr, dn = v - thr;
-    unsigned mh = 0, ml = 0;
+// Segment test AND corner score in one pass over the ring: with m9 = max over the 16 arcs of (min of the arc's 9 pixels) and
+// M9 = min over the arcs of (max of the arc's 9 pixels), the pixel is a bright corner iff m9 > v + thr, a dark one iff
+// M9 < v - thr (both cannot hold: two disjoint 9-arcs do not fit in 16), and cornerScore = m9 - v - 1 resp. v - M9 - 1.
+// Returns the score, or -1 when the pixel is no corner.  2 x (16 + 16 + 8) three-input min / max operations.
+__device__ __forceinline__ int fast9_test_and_score(int v, const int (&p)[16], int thr) {
+    int lo3[16], hi3[16];
 #pragma unroll
-    for (int k = 0; k < 16; k++) {
-        mh = __funnelshift_l((unsigned)(up - p[k]), mh, 1);
-        ml = __funnelshift_l((unsigned)(p[k] - dn), ml, 1);
+    for (int i = 0; i < 16; i++) {
+        lo3[i] = __vimin3_s32(p[i], p[(i + 1) & 15], p[(i + 2) & 15]);
+        hi3[i] = __vimax3_s32(p[i], p[(i + 1) & 15], p[(i + 2) & 15]);
     }
-    mh |= mh << 16;
-    ml |= ml << 16;
-    unsigned rh = mh & (mh >> 1), rl = ml & (ml >> 1);
-    rh &= rh >> 2;
-    rl &= rl >> 2;
-    rh &= rh >> 4;
-    rl &= rl >> 4;            // runs of 8
-    rh &= mh >> 8;
-    rl &= ml >> 8;            // runs of 9
-    return rh ? 1 : (rl ? 2 : 0);
-}
-
-// cornerScore restricted to the polarity the segment test found: for a bright corner every 9-arc contains a pixel
-// that is not darker than v - thr, so the dark term is <= thr and cannot change max(thr, bright, dark); and v.v.
-__device__ __forceinline__ int fast9_ring_score_kind(int v, const int (&p)[16], int thr, int kind) {
-    int a2[16], a4[16];
-    int best;
-    if (kind == 1) {
+    int m9 = 0, M9 = 255;
 #pragma unroll
-        for (int i = 0; i < 16; i++) a2[i] = min(p[i], p[(i + 1) & 15]);
-#pragma unroll
-        for (int i = 0; i < 16; i++) a4[i] = min(a2[i], a2[(i + 2) & 15]);
-        int m = 0;
-#pragma unroll
-        for (int i = 0; i < 16; i++) m = max(m, min(min(a4[i], a4[(i + 4) & 15]), p[(i + 8) & 15]));
-        best = m - v;
-    } else {
-#pragma unroll
-        for (int i = 0; i < 16; i++) a2[i] = max(p[i], p[(i + 1) & 15]);
-#pragma unroll
-        for (int i = 0; i < 16; i++) a4[i] = max(a2[i], a2[(i + 2) & 15]);
-        int m = 255;
-#pragma unroll
-        for (int i = 0; i < 16; i++) m = min(m, max(max(a4[i], a4[(i + 4) & 15]), p[(i + 8) & 15]));
-        best = v - m;
+    for (int i = 0; i < 16; i += 2) {
+        const int a0 = __vimin3_s32(lo3[i], lo3[(i + 3) & 15], lo3[(i + 6) & 15]);
+        const int a1 = __vimin3_s32(lo3[i + 1], lo3[(i + 4) & 15], lo3[(i + 7) & 15]);
+        m9 = __vimax3_s32(m9, a0, a1);
+        const int b0 = __vimax3_s32(hi3[i], hi3[(i + 3) & 15], hi3[(i + 6) & 15]);
+        const int b1 = __vimax3_s32(hi3[i + 1], hi3[(i + 4) & 15], hi3[(i + 7) & 15]);
+        M9 = __vimin3_s32(M9, b0, b1);
     }
-    return max(thr, best) - 1;
+    const int bright = m9 - v, dark = v - M9;  // > thr <=> corner of that polarity
+    const int best = max(bright, dark);
+    return best > thr ? best - 1 : -1;
 }
 
 // bytes of |a - b| that exceed thr -> bit 7 of the byte (SWAR; thr in [0, 255])
@@ -354,7 +330,7 @@ __global__ void __launch_bounds__(256) fast9_mask_kernel(SeqView s, OrbView o, i
         }
     }
     __syncthreads();
-    // ---- phase 2: segment test (list-2 entries carry the polarity in bits 14-15)
+    // ---- phase 2 + 3: segment test and corner score in one pass over the ring (fast9_test_and_score) -> score grid, list 2
     const int c1 = n1;
     for (int e = threadIdx.x; e < c1; e += 256) {
         const int idx = list1[e];
@@ -362,25 +338,17 @@ __global__ void __launch_bounds__(256) fast9_mask_kernel(SeqView s, OrbView o, i
         const uint8_t* t = tile + (ry + 3) * FSW + (FHX - 4) + cx;
         int p[16];
         fast9_load_ring(t, FSW, p);
-        const int kind = fast9_corner_kind(t[0], p, thr);
-        if (kind) list2[atomicAdd(&n2, 1)] = (uint16_t)(idx | (kind << 14));
+        const int score = fast9_test_and_score(t[0], p, thr);
+        if (score >= 0) {
+            sc[idx] = (uint8_t)score;
+            list2[atomicAdd(&n2, 1)] = (uint16_t)idx;
+        }
     }
     __syncthreads();
-    // ---- phase 3: scores
     const int c2 = n2;
-    for (int e = threadIdx.x; e < c2; e += 256) {
-        const int ent = list2[e];
-        const int idx = ent & 0x3fff, kind = ent >> 14;
-        const int ry = idx / SCW, cx = idx - ry * SCW;
-        const uint8_t* t = tile + (ry + 3) * FSW + (FHX - 4) + cx;
-        int p[16];
-        fast9_load_ring(t, FSW, p);
-        sc[idx] = (uint8_t)fast9_ring_score_kind(t[0], p, thr, kind);
-    }
-    __syncthreads();
     // ---- phase 4: NMS + border filter
     for (int e = threadIdx.x; e < c2; e += 256) {
-        const int idx = list2[e] & 0x3fff;
+        const int idx = list2[e];
         const int ry = idx / SCW, cx = idx - ry * SCW;
         const int r = ry - 1, lx = cx - 4;
         if ((unsigned)r >= (unsigned)FTH || (unsigned)lx >= (unsigned)FTW) continue;

@@ -14,6 +14,7 @@ PY
 SKIP=$((3 * PER))
 ncu --clock-control none --set full --import-source on -k regex:$K --launch-skip $SKIP --launch-count 1 -o gpurun_out/ncu_$TAG -f $CMD > gpurun_out/ncu_$TAG.log 2>&1
 ncu -i gpurun_out/ncu_$TAG.ncu-rep --page raw --csv > /tmp/raw_$TAG.csv 2>/dev/null
+ncu -i gpurun_out/ncu_$TAG.ncu-rep --page source --csv > gpurun_out/src_$TAG.csv 2>/dev/null
 python - /tmp/raw_$TAG.csv > gpurun_out/ncu_$TAG.txt <<'PY'
 import csv, sys
 rows = [r for r in csv.reader(l for l in open(sys.argv[1]) if l.startswith('"'))]
