@@ -1557,8 +1557,9 @@ static int match_common(slamcu_matcher* m, const uint8_t* d1, int n1, int width1
     // tiles at least; the batched sequence path has thousands of blocks and does not need it
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
-    const int q_blocks = (n1 + 127) / 128;
-    int n_seg = std::min(std::min((4 * sms + q_blocks - 1) / q_blocks, (n2 + 127) / 128), kMaxMatchSlices);
+    // blocks hold 256 queries (128 for small problems, launch_match decides): aim at ~8 blocks per SM, slices of at least 128
+    const int q_blocks = (n1 + 255) / 256;
+    int n_seg = std::min(std::min((8 * sms + q_blocks - 1) / q_blocks, (n2 + 127) / 128), kMaxMatchSlices);
     if (m->forced_slices > 0) n_seg = std::min(std::min(m->forced_slices, (n2 + 127) / 128), kMaxMatchSlices);
     n_seg = std::max(n_seg, 1);
     const int seg_len = ((n2 + n_seg - 1) / n_seg + 127) / 128 * 128;

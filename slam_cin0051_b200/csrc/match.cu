@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(QT) match_kernel(MatchJob job, int with_kp, in
 // Per train descriptor two broadcast LDS.128 serve both queries; per comparison: 8 XOR + 8 LOP3 (carry-save tree) on the ALU
 // pipe, 4 POPC on the XU pipe, the weighted sum and the (distance << 20 | index) key as integer multiply-adds (FMA pipe),
 // and the running top-2 as min / max on packed keys.  Instruction budget per comparison ~28 (was 32).
-constexpr int MQ = 2, MTHR = 128, MQB = MQ * MTHR;
+constexpr int MTHR = 128;
 constexpr int kMaxTile256 = 2048;   // largest tile the kernel may be given (64 KB)
 constexpr int kDefTile256 = 512;    // default: 16 KB per block -> nine 4-warp blocks per SM (measured: 2048 -> 780, 1024 -> 841, 512 -> 848, 256 -> 847 Gcmp/s)
 
@@ -224,7 +224,9 @@ __device__ __forceinline__ uint32_t hamming256_key(const uint32_t (&q)[8], const
     return mad_u32((uint32_t)__popc(fours), w4, k);
 }
 
+template <int MQ>  // queries per thread: 2 for batches and large problems, 1 for small single problems (twice the blocks)
 __global__ void __launch_bounds__(MTHR) match256_kernel(MatchJob job, int n_seg, int seg_len, size_t seg_stride, int tile_cap, uint32_t w1) {
+    constexpr int MQB = MQ * MTHR;
     extern __shared__ __align__(16) uint32_t smem[];
     uint4* tile = reinterpret_cast<uint4*>(smem);  // [tile_cap][2]
     const int pair = blockIdx.y;
@@ -420,7 +422,10 @@ __global__ void __launch_bounds__(256) finalize_kernel(MatchJob job, MatchParams
 
 }  // namespace
 
-void init_match_attributes() { cudaFuncSetAttribute(match256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxTile256 * 32); }
+void init_match_attributes() {
+    cudaFuncSetAttribute(match256_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxTile256 * 32);
+    cudaFuncSetAttribute(match256_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxTile256 * 32);
+}
 
 int launch_match(const MatchJob& job, int n_pairs, const MatchParams& p, bool emit_matches, int with_kp,
                  unsigned long long* sort_keys, cudaStream_t st, int n_seg, int seg_len, size_t seg_stride) {
@@ -432,8 +437,14 @@ int launch_match(const MatchJob& job, int n_pairs, const MatchParams& p, bool em
         static const int tile_env = [] { const char* e = getenv("SLAMCU_MATCH_TILE"); return e ? atoi(e) : 0; }();  // tuning knob (descriptors per smem tile)
         const int tile_max = tile_env >= 64 && tile_env <= kMaxTile256 ? tile_env / 64 * 64 : kDefTile256;
         const int tile_cap = max(64, min(tile_max, (span + 63) / 64 * 64));
-        dim3 grid((job.max_q + MQB - 1) / MQB, n_pairs, n_seg);
-        SLAM_KERNEL("match", st, match256_kernel<<<grid, MTHR, (size_t)tile_cap * 32, st>>>(job, n_seg, seg_len, seg_stride, tile_cap, 1u << kKeyShift));
+        // two queries per thread when that still leaves a few blocks per SM, else one (small single problems)
+        const bool two = (long long)n_pairs * ((job.max_q + 2 * MTHR - 1) / (2 * MTHR)) * n_seg >= 4 * 148;
+        const int qpb = (two ? 2 : 1) * MTHR;
+        dim3 grid((job.max_q + qpb - 1) / qpb, n_pairs, n_seg);
+        if (two)
+            SLAM_KERNEL("match", st, match256_kernel<2><<<grid, MTHR, (size_t)tile_cap * 32, st>>>(job, n_seg, seg_len, seg_stride, tile_cap, 1u << kKeyShift));
+        else
+            SLAM_KERNEL("match", st, match256_kernel<1><<<grid, MTHR, (size_t)tile_cap * 32, st>>>(job, n_seg, seg_len, seg_stride, tile_cap, 1u << kKeyShift));
     } else {
         dim3 grid((job.max_q + QT - 1) / QT, n_pairs, n_seg);
         const size_t smem = (size_t)TT * job.desc_words * 4 + TT * sizeof(float2);
