@@ -2,6 +2,8 @@
 //
 //   slam::cuda::FeatureDetector  <->  slam::FeatureDetector  (include/slam/frontend/feature_detector.hpp:47-192)
 //   slam::cuda::FeatureMatcher   <->  slam::FeatureMatcher   (include/slam/frontend/feature_matcher.hpp:38-87)
+//   slam::cuda::PoseEstimator    <->  slam::PoseEstimator    (include/slam/frontend/pose_estimator.hpp:13-36)
+//   slam::cuda::Preprocessor     <->  slam::Preprocessor     (include/slam/preprocessing/preprocessor.hpp:22-54)
 //   slam::cuda::EssentialSolver  <->  the cv::findEssentialMat call of PoseEstimator::estimate (pose_estimator.cpp:42)
 //   slam::cuda::Camera           <->  slam::Camera (common.hpp:67-190): calibration YAML, undistortImage
 //   slam::cuda::bgrToGray        <->  cv::cvtColor(BGR2GRAY) of Preprocessor::yield (preprocessor.cpp:136)
@@ -14,11 +16,18 @@
 // There is no CPU fallback: construction throws if no CUDA device is available.
 #pragma once
 #include <algorithm>
+#include <chrono>
 #include <cstdint>
+#include <cstring>
+#include <ctime>
 #include <filesystem>
 #include <fstream>
+#include <iomanip>
+#include <sstream>
 #include <stdexcept>
 #include <string>
+#include <type_traits>
+#include <utility>
 #include <vector>
 
 #include "slamcu.h"
@@ -116,20 +125,12 @@ public:
         c.blur_weights = m_blur;
         // opt-in OpenCV-ORB-compatible mode: keys the reference's YAML does not have
         if (fs.has("NumLevels") || fs.has("MaxFeatures") || fs.has("ScaleFactor")) {
-            if (!fs.has("OrbPatternFile"))
-                throw std::runtime_error("ORB mode needs OrbPatternFile (256x4 int32 rBRIEF pattern, raw little-endian).");
-            std::filesystem::path pat(fs.getString("OrbPatternFile"));
-            if (pat.is_relative()) pat = configPath.parent_path() / pat;  // relative to the YAML file
-            std::ifstream pf(pat, std::ios::binary);
-            m_orbPattern.resize(1024);
-            pf.read(reinterpret_cast<char*>(m_orbPattern.data()), 4096);
-            if (pf.gcount() != 4096) throw std::runtime_error("Could not read OrbPatternFile.");
             c.mode = SLAMCU_MODE_ORB;
             c.n_levels = fs.has("NumLevels") ? fs.getInt("NumLevels") : 8;
             c.scale_factor = fs.has("ScaleFactor") ? fs.getFloat("ScaleFactor") : 1.2F;
             c.max_features = fs.has("MaxFeatures") ? fs.getInt("MaxFeatures") : 2000;
             c.fast_threshold = fs.has("FastThreshold") ? fs.getInt("FastThreshold") : c.intensity_threshold;
-            c.orb_pattern = m_orbPattern.data();
+            c.orb_pattern = nullptr;  // OpenCV's bit_pattern_31_, built into the library
         }
         m_descBytes = c.num_brief_pairs / 8;
         m_ctx.check(slamcu_detector_create(m_ctx.get(), &c, &m_det));
@@ -203,7 +204,7 @@ private:
     }
     Context& m_ctx;
     slamcu_detector* m_det = nullptr;
-    std::vector<int32_t> m_pattern, m_orbPattern;
+    std::vector<int32_t> m_pattern;
     double m_blur[25]{};
     int m_descBytes = 32;
 };
@@ -379,6 +380,204 @@ public:
 private:
     Context& m_ctx;
     double m_K[4]{};
+};
+
+// ---- slam::PoseEstimator (pose_estimator.hpp:13-36) ----------------------------------------------------------------------
+namespace detail {
+// fx, fy, cx, cy out of Camera::getIntrinsicMatrix(): an Eigen::Matrix3d in the reference (operator()(r, c)), a row-major
+// double[9] in slam::cuda::Camera
+template <class CameraT>
+void intrinsics_of(const CameraT& camera, double K4[4]) {
+    const auto& K = camera.getIntrinsicMatrix();
+    if constexpr (std::is_pointer_v<std::decay_t<decltype(K)>>) {
+        K4[0] = K[0]; K4[1] = K[4]; K4[2] = K[2]; K4[3] = K[5];
+    } else {
+        K4[0] = K(0, 0); K4[1] = K(1, 1); K4[2] = K(0, 2); K4[3] = K(1, 2);
+    }
+}
+// cv::Mat-shaped outputs: create(rows, cols, CV_64F) + contiguous `data` (cv::Mat in the reference tree)
+template <class MatT>
+void assign_f64(MatT& m, int rows, int cols, const double* v) {
+    m.create(rows, cols, 6 /* CV_64F */);
+    std::memcpy(m.data, v, sizeof(double) * static_cast<size_t>(rows) * cols);
+}
+}  // namespace detail
+
+class PoseEstimator {
+public:
+    // pose_estimator.hpp:15.  The reference keeps a reference to the camera; only its intrinsic matrix is ever read
+    // (pose_estimator.cpp:40-41, :72-73), so the four intrinsics are copied here.
+    template <class CameraT>
+    explicit PoseEstimator(const CameraT& camera, Context& ctx = Context::instance()) : m_ctx(ctx) {
+        detail::intrinsics_of(camera, m_K);
+    }
+    // PoseEstimator::estimate (pose_estimator.cpp:18-67).  pairs: std::vector<KeyDescriptorPair> (only .first.pt is read,
+    // :33-34); R, t: cv::Mat.  Like the reference, returns WITHOUT touching R, t below 8 matches (:22-26) and when no essential
+    // matrix was accepted (:44-47).
+    template <class Pair, class MatT>
+    void estimate(const std::vector<Pair>& pairs1, const std::vector<Pair>& pairs2, const std::vector<std::pair<int, int>>& matches, MatT& R,
+                  MatT& t) {
+        if (matches.size() < 8) return;
+        std::vector<float> p1, p2;
+        p1.reserve(matches.size() * 2);
+        p2.reserve(matches.size() * 2);
+        for (const auto& m : matches) {
+            p1.push_back(pairs1[static_cast<size_t>(m.first)].first.pt.x);
+            p1.push_back(pairs1[static_cast<size_t>(m.first)].first.pt.y);
+            p2.push_back(pairs2[static_cast<size_t>(m.second)].first.pt.x);
+            p2.push_back(pairs2[static_cast<size_t>(m.second)].first.pt.y);
+        }
+        double E[9], Rv[9], tv[3];
+        int inliers = 0, front[4];
+        const int st = slamcu_estimate_pose(m_ctx.get(), p1.data(), p2.data(), static_cast<int>(matches.size()), m_K, E, nullptr, &inliers, Rv, tv, front);
+        if (st == SLAMCU_EMPTY_INPUT) return;  // "Essential Matrix could not be computed."
+        m_ctx.check(st);
+        detail::assign_f64(R, 3, 3, Rv);
+        detail::assign_f64(t, 3, 1, tv);
+    }
+    // PoseEstimator::triangulatePoints (pose_estimator.cpp:69-104): P1 = K [I | 0], P2 = K [R | t], slam::triangulate per match,
+    // x / x[3].  P3: cv::Point3d; KP: cv::KeyPoint; DM: cv::DMatch; R, t: CV_64F cv::Mat (read through .data like R.at<double>).
+    // (The reference's own result is indeterminate -- Mat::copyTo into a differently typed column, common.hpp:217 -- this is the
+    // value that code evidently means; slamcu.h.)
+    template <class P3, class KP, class DM, class MatT>
+    std::vector<P3> triangulatePoints(const std::vector<KP>& keypoints1, const std::vector<KP>& keypoints2, const std::vector<DM>& matches,
+                                      const MatT& R, const MatT& t) {
+        const double* r = reinterpret_cast<const double*>(R.data);
+        const double* tv = reinterpret_cast<const double*>(t.data);
+        const double fx = m_K[0], fy = m_K[1], cx = m_K[2], cy = m_K[3];
+        const double P1[12] = {fx, 0, cx, 0, 0, fy, cy, 0, 0, 0, 1, 0};
+        double P2[12];
+        for (int j = 0; j < 4; j++) {
+            const double c0 = j < 3 ? r[j] : tv[0], c1 = j < 3 ? r[3 + j] : tv[1], c2 = j < 3 ? r[6 + j] : tv[2];
+            P2[j] = fx * c0 + cx * c2;
+            P2[4 + j] = fy * c1 + cy * c2;
+            P2[8 + j] = c2;
+        }
+        std::vector<float> p1, p2;
+        for (const auto& m : matches) {
+            p1.push_back(keypoints1[static_cast<size_t>(m.queryIdx)].pt.x);
+            p1.push_back(keypoints1[static_cast<size_t>(m.queryIdx)].pt.y);
+            p2.push_back(keypoints2[static_cast<size_t>(m.trainIdx)].pt.x);
+            p2.push_back(keypoints2[static_cast<size_t>(m.trainIdx)].pt.y);
+        }
+        std::vector<double> x3(matches.size() * 3);
+        m_ctx.check(slamcu_triangulate(m_ctx.get(), P1, P2, p1.data(), p2.data(), static_cast<int>(matches.size()), nullptr, x3.data()));
+        std::vector<P3> out;
+        out.reserve(matches.size());
+        for (size_t i = 0; i < matches.size(); i++) out.emplace_back(x3[3 * i], x3[3 * i + 1], x3[3 * i + 2]);
+        return out;
+    }
+
+private:
+    Context& m_ctx;
+    double m_K[4]{};
+};
+
+// ---- slam::Preprocessor (preprocessor.hpp:22-54, preprocessor.cpp) -------------------------------------------------------
+// Directory streams: the same file selection, lexical order, timestamps.txt parsing and error messages as the reference
+// (preprocessor.cpp:24-82).  Decoding a file into BGR bytes is the one step that stays a host library call (cv::imread there):
+// the adapter takes it as a callable  bool decode(const std::filesystem::path&, int& rows, int& cols, std::vector<uint8_t>& bgr).
+// yield() does cv::cvtColor(BGR2GRAY) + Camera::undistortImage on the device and returns the reference's double image;
+// yieldInto() does the same for a batch straight into a device-resident sequence (slamcu_sequence_prepare) -- the 8-bit image
+// the detector consumes, with no double image in between.  Video files need cv::VideoCapture and are not supported here.
+template <class Decoder>
+class Preprocessor {
+public:
+    using TimePoint = std::chrono::system_clock::time_point;
+    template <class CameraT>
+    Preprocessor(std::filesystem::path streamPath, const CameraT& camera, Decoder decode, int frameSkip = 0, Context& ctx = Context::instance())
+        : m_ctx(ctx), m_decode(std::move(decode)), m_frameSkip(frameSkip), m_streamPath(std::move(streamPath)) {
+        detail::intrinsics_of(camera, m_K);
+        const auto& D = camera.getDistortionCoefficients();
+        for (int i = 0; i < 4; i++) m_D[i] = static_cast<long>(D.size()) > i ? static_cast<double>(D[static_cast<size_t>(i)]) : 0.0;
+        if (std::filesystem::is_directory(m_streamPath)) prepareDirectory();
+        else if (std::filesystem::is_regular_file(m_streamPath)) throw std::runtime_error("Could not open video file: " + m_streamPath.string());
+        else throw std::runtime_error("Unsupported stream type: " + m_streamPath.string());
+    }
+    int totalFrames() const { return m_totalFrames; }
+
+    // Preprocessor::yield (preprocessor.cpp:95-141).  Out: Eigen::MatrixXd (resize(rows, cols), operator()(i, j)).  An empty
+    // (0 x 0) image and a default time point at the end of the stream, like the reference's default-constructed pair.
+    template <class Out>
+    std::pair<Out, TimePoint> yield() {
+        std::pair<Out, TimePoint> pair;
+        if (m_frameNumber >= m_totalFrames) return pair;
+        int rows = 0, cols = 0;
+        std::vector<uint8_t> bgr;
+        if (!m_decode(m_files[static_cast<size_t>(m_frameNumber)], rows, cols, bgr) || rows <= 0 || cols <= 0)
+            throw std::runtime_error("Failed to read image from file: " + m_files[static_cast<size_t>(m_frameNumber)].string());
+        std::vector<uint8_t> gray(static_cast<size_t>(rows) * cols);
+        m_ctx.check(slamcu_bgr_to_gray(m_ctx.get(), bgr.data(), rows, cols, cols * 3, gray.data(), cols));
+        std::vector<double> f64(gray.size());
+        m_ctx.check(slamcu_undistort(m_ctx.get(), gray.data(), rows, cols, cols, m_K, m_D, nullptr, f64.data()));
+        pair.first.resize(rows, cols);
+        for (int i = 0; i < rows; i++)
+            for (int j = 0; j < cols; j++) pair.first(i, j) = f64[static_cast<size_t>(i) * cols + j];
+        pair.second = stampOf(m_frameNumber);
+        m_frameNumber += 1 + m_frameSkip;
+        return pair;
+    }
+
+    // Batched yield: up to n frames are decoded, uploaded as BGR with one copy and converted + undistorted on the device into
+    // slots [first, first + count) of `seq`.  Returns count (0 at the end of the stream).
+    int yieldInto(slamcu_sequence* seq, int first, int n, std::vector<TimePoint>* stamps = nullptr) {
+        std::vector<uint8_t> batch;
+        int count = 0, rows0 = 0, cols0 = 0;
+        while (count < n && m_frameNumber < m_totalFrames) {
+            int rows = 0, cols = 0;
+            std::vector<uint8_t> bgr;
+            if (!m_decode(m_files[static_cast<size_t>(m_frameNumber)], rows, cols, bgr) || rows <= 0 || cols <= 0)
+                throw std::runtime_error("Failed to read image from file: " + m_files[static_cast<size_t>(m_frameNumber)].string());
+            if (count == 0) { rows0 = rows; cols0 = cols; }
+            if (rows != rows0 || cols != cols0) throw std::runtime_error("Input image size does not match camera image size.");
+            batch.insert(batch.end(), bgr.begin(), bgr.end());
+            if (stamps) stamps->push_back(stampOf(m_frameNumber));
+            m_frameNumber += 1 + m_frameSkip;
+            count++;
+        }
+        if (count > 0) {
+            m_ctx.check(slamcu_sequence_prepare(seq, first, count, batch.data(), 3, cols0 * 3, m_K, m_D));
+            m_ctx.check(slamcu_synchronize(m_ctx.get()));  // `batch` goes out of scope
+        }
+        return count;
+    }
+
+private:
+    void prepareDirectory() {  // preprocessor.cpp:24-82
+        for (const auto& entry : std::filesystem::directory_iterator(m_streamPath)) {
+            if ((entry.is_regular_file() && entry.path().extension() == ".jpg") || entry.path().extension() == ".png") {  // (sic, :34-35)
+                m_totalFrames++;
+                m_files.push_back(entry.path());
+            }
+        }
+        std::sort(m_files.begin(), m_files.end());
+        std::ifstream file(m_streamPath / "timestamps.txt");
+        if (!file) throw std::runtime_error("Could not open timestamps.txt in directory: " + m_streamPath.string());
+        std::string line;
+        while (std::getline(file, line)) {
+            const auto decimalPos = line.find('.');
+            if (decimalPos == std::string::npos) continue;
+            std::tm timeStruct = {};
+            std::stringstream ss(line.substr(0, decimalPos));
+            ss >> std::get_time(&timeStruct, "%Y-%m-%d %H:%M:%S");
+            if (ss.fail()) continue;
+            auto timePoint = std::chrono::system_clock::from_time_t(std::mktime(&timeStruct));
+            timePoint += std::chrono::duration_cast<std::chrono::system_clock::duration>(std::chrono::nanoseconds(std::stoll(line.substr(decimalPos + 1))));
+            m_timestamps.push_back(timePoint);
+        }
+        if (static_cast<int>(m_timestamps.size()) != m_totalFrames) throw std::runtime_error("Number of timestamps does not match number of frames.");
+    }
+    TimePoint stampOf(int frame) const {  // preprocessor.cpp:114-119: the stamp truncated to milliseconds
+        const double ms = static_cast<double>(m_timestamps[static_cast<size_t>(frame)].time_since_epoch().count()) / 1.0e6;
+        return TimePoint(std::chrono::milliseconds(static_cast<int64_t>(ms)));
+    }
+    Context& m_ctx;
+    Decoder m_decode;
+    int m_frameNumber = 0, m_totalFrames = 0, m_frameSkip = 0;
+    std::vector<TimePoint> m_timestamps;
+    std::vector<std::filesystem::path> m_files;
+    std::filesystem::path m_streamPath;
+    double m_K[4]{}, m_D[4]{};
 };
 
 }  // namespace slam::cuda

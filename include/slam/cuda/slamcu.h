@@ -78,7 +78,7 @@ typedef struct slamcu_detector_config {
     float scale_factor;    /* ScaleFactor (1.2f) */
     int32_t max_features;  /* MaxFeatures (2000) */
     int32_t fast_threshold; /* = intensity_threshold by default */
-    const int32_t* orb_pattern; /* [256][4] OpenCV bit_pattern_31_ (host supplied), or NULL */
+    const int32_t* orb_pattern; /* [256][4] rBRIEF test pairs x1,y1,x2,y2; NULL = OpenCV's bit_pattern_31_ (built in) */
 } slamcu_detector_config;
 
 /* feature_matcher.cpp:25-57 */
@@ -279,6 +279,27 @@ int slamcu_find_essential(slamcu_context* ctx, const float* p1, const float* p2,
  * (the reference logs a warning and returns without touching R, t). */
 int slamcu_estimate_pose(slamcu_context* ctx, const float* p1, const float* p2, int n, const double* K4, double* E9, uint8_t* mask,
                          int* n_inliers, double* R9, double* t3, int32_t* front4);
+/* slam::triangulate (common.hpp:201-221) as PoseEstimator::triangulatePoints calls it (pose_estimator.cpp:69-104): per
+ * correspondence, the null vector of the 4x4 DLT system of the projection matrices P1, P2 (row-major 3x4, e.g. K [I|0] and
+ * K [R|t]) and the pixel coordinates pts1 / pts2 (n x 2 float).  points4 (n x 4, may be NULL): the homogeneous solution, unit
+ * norm, last component >= 0; points3 (n x 3, may be NULL): x / x[3], what triangulatePoints returns.  (The reference writes
+ * its solution through Mat::copyTo into a column view of a differently typed matrix -- common.hpp:217 -- and returns
+ * indeterminate values; this is the result that code evidently means, checked against numpy's SVD.) */
+int slamcu_triangulate(slamcu_context* ctx, const double* P1, const double* P2, const float* pts1, const float* pts2, int n,
+                       double* points4, double* points3);
+/* The RANSAC of LoopClosure::verifyGeometricConsistency (loop_closure.cpp:177-222): for every hypothesis h, solvePnP
+ * (:238-274, the 6-point DLT with the reference's own vector -> matrix mapping reproduced literally: K is never removed and the
+ * row-major null vector is read back column-major) on the correspondences samples6[h][0..5], then the reprojection test of
+ * every correspondence (:201-215; threshold in pixels, points behind the camera skipped).  The caller draws the sample indices
+ * (the reference seeds std::mt19937 from std::random_device: the host adapter takes a seed instead).  The sign of the DLT null
+ * vector is an implementation detail of the SVD and changes the outcome, so both signs are evaluated: counts2[2 h + s] and
+ * Rt24[(2 h + s) * 12 ..] = R (row-major 3x3) then t, s = 0: the null vector's largest component positive, s = 1: negated.
+ * n >= 6; points3d n x 3, points2d n x 2 (double); K9 row-major 3x3. */
+/* The sample draw of that loop (:177-193) with the host library's std::mt19937 / std::uniform_int_distribution<int>(0, n-1),
+ * seeded by the caller: samples6[n_hypotheses][6], six distinct indices per hypothesis.  Host only. */
+int slamcu_pnp_sample_indices(uint32_t seed, int n, int n_hypotheses, int32_t* samples6);
+int slamcu_pnp_ransac(slamcu_context* ctx, const double* points3d, const double* points2d, int n, const int32_t* samples6,
+                      int n_hypotheses, const double* K9, double threshold, int32_t* counts2, double* Rt24);
 /* Stage probe: the 5-point minimal solver on n_samples independent samples.  x1/x2: [n_samples][5][2] normalised
  * coordinates; models: [n_samples][10][9] (row-major E, unit norm); counts[n_samples] = solutions per sample. */
 int slamcu_fivept_solve(slamcu_context* ctx, const double* x1, const double* x2, int n_samples, double* models,

@@ -177,6 +177,8 @@ public:
     const T& operator()(Index r, Index c) const { return d_[(size_t)(O == RowMajor ? r * c_ + c : c * r_ + r)]; }
     T& operator()(Index k) { return d_[(size_t)k]; }             // vectors
     const T& operator()(Index k) const { return d_[(size_t)k]; }
+    T& operator[](Index k) { return d_[(size_t)k]; }             // vectors, like Eigen's DenseCoeffsBase
+    const T& operator[](Index k) const { return d_[(size_t)k]; }
     T coeff(Index k) const { return d_[(size_t)k]; }
     T x() const { return d_[0]; }
     T y() const { return d_[1]; }

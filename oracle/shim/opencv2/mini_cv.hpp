@@ -29,7 +29,9 @@ using uchar = unsigned char;
 
 struct Size { int width = 0, height = 0; Size() = default; Size(int w, int h) : width(w), height(h) {} };
 struct Point2f { float x = 0, y = 0; Point2f() = default; Point2f(float X, float Y) : x(X), y(Y) {} };
+struct Point3d { double x = 0, y = 0, z = 0; Point3d() = default; Point3d(double X, double Y, double Z) : x(X), y(Y), z(Z) {} };
 struct KeyPoint { Point2f pt; float size = 0, angle = -1, response = 0; int octave = 0, class_id = -1; };
+struct DMatch { int queryIdx = -1, trainIdx = -1, imgIdx = -1; float distance = 0; };
 
 class Mat;
 struct MatExpr { std::shared_ptr<Mat> value; };

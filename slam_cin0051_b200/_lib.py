@@ -91,6 +91,9 @@ SYMBOLS = {
     "slamcu_ransac_score": (_i, [_vp, _f64p, _i, _f64p, _f64p, _i, C.c_double, _vp, _u8p]),
     "slamcu_find_essential": (_i, [_vp, _f32p, _f32p, _i, _f64p, C.c_double, C.c_double, _i, _f64p, _u8p, _ip]),
     "slamcu_estimate_pose": (_i, [_vp, _f32p, _f32p, _i, _f64p, _f64p, _u8p, _ip, _f64p, _f64p, _vp]),
+    "slamcu_triangulate": (_i, [_vp, _f64p, _f64p, _f32p, _f32p, _i, _f64p, _f64p]),
+    "slamcu_pnp_sample_indices": (_i, [C.c_uint32, _i, _i, _vp]),
+    "slamcu_pnp_ransac": (_i, [_vp, _f64p, _f64p, _i, _vp, _i, _f64p, C.c_double, _vp, _f64p]),
     "slamcu_fivept_solve": (_i, [_vp, _f64p, _f64p, _i, _f64p, _vp]),
     "slamcu_sequence_essential": (_i, [_vp, _i, _i, _f64p, C.c_double, C.c_double, _i]),
     "slamcu_sequence_essential_read": (_i, [_vp, _i, _f64p, _ip, _ip, _u8p, _i, _ip]),

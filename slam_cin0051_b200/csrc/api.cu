@@ -30,6 +30,10 @@ thread_local Profiler* g_prof = nullptr;
 }
 
 namespace {
+constexpr int8_t kOrbBitPattern31[1024] = {
+#include "orb_pattern.inc"
+};
+
 struct EventProfiler : Profiler {
     struct Rec { const char* name; cudaEvent_t a, b; };
     struct Acc { const char* name; double ms; long long count; };
@@ -1189,7 +1193,6 @@ int slamcu_detector_create(slamcu_context* ctx, const slamcu_detector_config* cf
         if (cfg->n_levels < 1 || cfg->n_levels > kMaxLevels) return fail(ctx, SLAMCU_INVALID_ARGUMENT, "NumLevels must be in [1, %d]", kMaxLevels);
         if (!(cfg->scale_factor > 1.0f)) return fail(ctx, SLAMCU_INVALID_ARGUMENT, "ScaleFactor must be > 1");
         if (cfg->max_features <= 0) return fail(ctx, SLAMCU_INVALID_ARGUMENT, "MaxFeatures must be positive");
-        if (!cfg->orb_pattern) return fail(ctx, SLAMCU_INVALID_ARGUMENT, "ORB mode needs the 256x4 rBRIEF pattern");
         if (cfg->num_brief_pairs != 256) return fail(ctx, SLAMCU_INVALID_ARGUMENT, "ORB mode descriptors are 256 bits");
     }
     CU(ctx, cudaSetDevice(ctx->device));
@@ -1210,10 +1213,10 @@ int slamcu_detector_create(slamcu_context* ctx, const slamcu_detector_config* cf
         d->scale_factor = cfg->scale_factor;
         d->max_features = cfg->max_features;
         d->fast_threshold = cfg->fast_threshold > 0 ? cfg->fast_threshold : cfg->intensity_threshold;
-        int8_t h[1024];
-        for (int i = 0; i < 1024; i++) h[i] = (int8_t)cfg->orb_pattern[i];
+        int8_t h[1024];  // NULL = OpenCV's own bit_pattern_31_, built into the library
+        for (int i = 0; i < 1024; i++) h[i] = cfg->orb_pattern ? (int8_t)cfg->orb_pattern[i] : kOrbBitPattern31[i];
         float hf[1024];
-        for (int i = 0; i < 1024; i++) hf[i] = (float)cfg->orb_pattern[i];
+        for (int i = 0; i < 1024; i++) hf[i] = (float)h[i];
         if (cudaMalloc(reinterpret_cast<void**>(&d->d_orb_pattern), 1024) != cudaSuccess ||
             cudaMemcpy(d->d_orb_pattern, h, 1024, cudaMemcpyHostToDevice) != cudaSuccess ||
             cudaMalloc(reinterpret_cast<void**>(&d->d_orb_patf), sizeof hf) != cudaSuccess ||
@@ -1782,6 +1785,92 @@ int slamcu_estimate_pose(slamcu_context* ctx, const float* p1, const float* p2, 
     CU(ctx, cudaMemcpyAsync(hf, dfront, 16, cudaMemcpyDeviceToHost, ctx->stream));
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     if (front4) memcpy(front4, hf, sizeof hf);
+    return SLAMCU_OK;
+}
+
+// The sampling loop of LoopClosure::verifyGeometricConsistency (loop_closure.cpp:177-193) with the host C++ library's own
+// std::mt19937 and std::uniform_int_distribution<int>(0, n - 1), seeded by the caller instead of std::random_device:
+// six distinct indices per iteration, redrawn on duplicates.  (solvePnP never fails for six points, so no iteration is skipped.)
+int slamcu_pnp_sample_indices(uint32_t seed, int n, int n_hypotheses, int32_t* samples6) {
+    if (!samples6 || n < 6 || n_hypotheses < 0) return SLAMCU_INVALID_ARGUMENT;
+    std::mt19937 rng(seed);
+    std::uniform_int_distribution<int> dist(0, n - 1);
+    for (int h = 0; h < n_hypotheses; h++) {
+        int got = 0;
+        while (got < 6) {
+            const int idx = dist(rng);
+            bool dup = false;
+            for (int k = 0; k < got; k++) dup |= samples6[6 * h + k] == idx;
+            if (!dup) samples6[6 * h + got++] = idx;
+        }
+    }
+    return SLAMCU_OK;
+}
+
+int slamcu_triangulate(slamcu_context* ctx, const double* P1, const double* P2, const float* pts1, const float* pts2, int n, double* points4,
+                       double* points3) {
+    if (!ctx) return SLAMCU_INVALID_ARGUMENT;
+    if (!P1 || !P2 || n < 0 || (n > 0 && (!pts1 || !pts2)) || (!points4 && !points3)) return fail(ctx, SLAMCU_INVALID_ARGUMENT, "bad arguments");
+    if (n == 0) return SLAMCU_OK;
+    CU(ctx, cudaSetDevice(ctx->device));
+    const size_t b_in = ((size_t)n * 8 + 255) / 256 * 256, b4 = (size_t)n * 32, b3 = ((size_t)n * 24 + 255) / 256 * 256;
+    int rc = ensure_scratch(ctx, 256 + 2 * b_in + b4 + b3);
+    if (rc != SLAMCU_OK) return rc;
+    uint8_t* base = static_cast<uint8_t*>(ctx->scratch);
+    double* dP = reinterpret_cast<double*>(base);
+    float* d1 = reinterpret_cast<float*>(base + 256);
+    float* d2 = reinterpret_cast<float*>(base + 256 + b_in);
+    double* d4 = reinterpret_cast<double*>(base + 256 + 2 * b_in);
+    double* d3 = reinterpret_cast<double*>(base + 256 + 2 * b_in + b4);
+    CU(ctx, cudaMemcpyAsync(dP, P1, 96, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(dP + 12, P2, 96, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(d1, pts1, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(d2, pts2, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    {
+        ProfGuard pg(ctx);
+        ctx->launches += launch_triangulate(dP, d1, d2, n, d4, d3, ctx->stream);
+    }
+    rc = check_launch(ctx, "triangulate");
+    if (rc != SLAMCU_OK) return rc;
+    if (points4) CU(ctx, cudaMemcpyAsync(points4, d4, (size_t)n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    if (points3) CU(ctx, cudaMemcpyAsync(points3, d3, (size_t)n * 24, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
+    return SLAMCU_OK;
+}
+
+int slamcu_pnp_ransac(slamcu_context* ctx, const double* points3d, const double* points2d, int n, const int32_t* samples6, int n_hypotheses,
+                      const double* K9, double threshold, int32_t* counts2, double* Rt24) {
+    if (!ctx) return SLAMCU_INVALID_ARGUMENT;
+    if (!points3d || !points2d || !samples6 || !K9 || !counts2 || n < 6 || n_hypotheses <= 0)
+        return fail(ctx, SLAMCU_INVALID_ARGUMENT, "pnp_ransac: need at least 6 correspondences and one hypothesis");
+    for (long long i = 0; i < 6LL * n_hypotheses; i++)
+        if (samples6[i] < 0 || samples6[i] >= n) return fail(ctx, SLAMCU_INVALID_ARGUMENT, "pnp_ransac: sample index %d out of range", samples6[i]);
+    CU(ctx, cudaSetDevice(ctx->device));
+    auto up = [](size_t b) { return (b + 255) / 256 * 256; };
+    const size_t b3 = up((size_t)n * 24), b2 = up((size_t)n * 16), bs = up((size_t)n_hypotheses * 24), bc = up((size_t)n_hypotheses * 8),
+                 br = (size_t)n_hypotheses * 2 * 96;
+    int rc = ensure_scratch(ctx, 256 + b3 + b2 + bs + bc + br);
+    if (rc != SLAMCU_OK) return rc;
+    uint8_t* base = static_cast<uint8_t*>(ctx->scratch);
+    double* dK = reinterpret_cast<double*>(base);
+    double* d3 = reinterpret_cast<double*>(base + 256);
+    double* d2 = reinterpret_cast<double*>(base + 256 + b3);
+    int* ds = reinterpret_cast<int*>(base + 256 + b3 + b2);
+    int* dc = reinterpret_cast<int*>(base + 256 + b3 + b2 + bs);
+    double* dr = reinterpret_cast<double*>(base + 256 + b3 + b2 + bs + bc);
+    CU(ctx, cudaMemcpyAsync(dK, K9, 72, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(d3, points3d, (size_t)n * 24, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(d2, points2d, (size_t)n * 16, cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx, cudaMemcpyAsync(ds, samples6, (size_t)n_hypotheses * 24, cudaMemcpyHostToDevice, ctx->stream));
+    {
+        ProfGuard pg(ctx);
+        ctx->launches += launch_pnp_ransac(d3, d2, n, ds, n_hypotheses, dK, threshold, dc, dr, ctx->stream);
+    }
+    rc = check_launch(ctx, "pnp_ransac");
+    if (rc != SLAMCU_OK) return rc;
+    CU(ctx, cudaMemcpyAsync(counts2, dc, (size_t)n_hypotheses * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (Rt24) CU(ctx, cudaMemcpyAsync(Rt24, dr, br, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx, cudaStreamSynchronize(ctx->stream));
     return SLAMCU_OK;
 }
 

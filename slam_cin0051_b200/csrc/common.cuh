@@ -118,6 +118,11 @@ int launch_essential_gather(const SeqView& s, int first, int n_pairs, const Esse
 int launch_essential_normalise(const float* p1, const float* p2, int n, const EssentialJob& job, const double* K4, cudaStream_t st);
 int launch_essential_ransac(const EssentialJob& job, int n_pairs, cudaStream_t st);
 int launch_recover_pose(const EssentialJob& job, int n_pairs, const double* K4, double* R, double* t, int* front, cudaStream_t st);
+// P24: the two row-major 3x4 projection matrices back to back (device); out4 / out3 may be null
+int launch_triangulate(const double* P24, const float* p1, const float* p2, int n, double* out4, double* out3, cudaStream_t st);
+// counts[2 * n_hyp], Rt[2 * n_hyp][12] (R row-major, then t): both signs of the DLT null vector per hypothesis
+int launch_pnp_ransac(const double* X3, const double* x2, int n, const int* samples6, int n_hyp, const double* K9, double thr, int* counts,
+                      double* Rt, cudaStream_t st);
 int launch_fivept_probe(const double* x1, const double* x2, int n_samples, double* models, int* counts, cudaStream_t st);
 
 // ---- optional per-kernel timing (CUDA events on the launching stream; bench.py's roofline input) ----

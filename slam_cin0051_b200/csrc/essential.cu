@@ -604,10 +604,159 @@ __global__ void __launch_bounds__(128) recover_pose_kernel(EssentialJob job, dou
     }
 }
 
+
+// ---- slam::triangulate (common.hpp:201-221) as PoseEstimator::triangulatePoints uses it (pose_estimator.cpp:69-104) ----------
+// One thread per correspondence: the 4x4 DLT system from the two projection matrices and the pixel coordinates, its null
+// vector by the same one-sided Jacobi SVD as the cheirality vote above (the reference: cv::SVD, vt.row(3)).
+// The reference then copies the CV_64F solution into a column view of a CV_32F matrix with Mat::copyTo, which re-allocates
+// the temporary header instead of writing the column (common.hpp:217) -- its output is indeterminate; this kernel returns
+// what the code evidently means: the homogeneous solution, and x / x[3] (pose_estimator.cpp:95-100).
+__global__ void __launch_bounds__(128) triangulate_kernel(const double* __restrict__ Pm, const float* __restrict__ p1, const float* __restrict__ p2,
+                                                          int n, double* __restrict__ out4, double* __restrict__ out3) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const double ax = (double)p1[2 * j], ay = (double)p1[2 * j + 1], bx = (double)p2[2 * j], by = (double)p2[2 * j + 1];
+    double A[4][4], V[4][4], w[4];
+    for (int k = 0; k < 4; k++) {
+        A[0][k] = ax * Pm[8 + k] - Pm[k];
+        A[1][k] = ay * Pm[8 + k] - Pm[4 + k];
+        A[2][k] = bx * Pm[12 + 8 + k] - Pm[12 + k];
+        A[3][k] = by * Pm[12 + 8 + k] - Pm[12 + 4 + k];
+    }
+    jacobi_svd<4>(A, V, w);
+    int m = 0;
+    for (int k = 1; k < 4; k++)
+        if (w[k] < w[m]) m = k;
+    const double sgn = V[3][m] < 0 ? -1.0 : 1.0;  // unit-norm null vector, last component non-negative
+    if (out4)
+        for (int k = 0; k < 4; k++) out4[4 * (size_t)j + k] = sgn * V[k][m];
+    if (out3)
+        for (int k = 0; k < 3; k++) out3[3 * (size_t)j + k] = V[k][m] / V[3][m];
+}
+
+// ---- LoopClosure::verifyGeometricConsistency's RANSAC (loop_closure.cpp:177-222) ---------------------------------------------
+// One block per hypothesis.  Thread 0 runs LoopClosure::solvePnP (:238-274) on the six sampled correspondences LITERALLY:
+// the 12x12 DLT system (:246-253), its null vector p, P = Eigen::Map<Matrix<double,3,4>>(p.data()) -- a COLUMN-major view
+// of a vector that was laid out row-major (:258), so R = [p0 p3 p6; p1 p4 p7; p2 p5 p8], t = (p9, p10, p11) --, then
+// rotation = U diag(1, 1, det(U V')) V' of that R and translation = t / |R|_F (:263-270); K is never removed.
+// The sign of a null vector is an implementation detail of the SVD (Eigen::JacobiSVD in the reference), and it matters
+// here (it flips R and t, and with them det and the z > 0 test), so BOTH signs are solved and scored: counts[2 h + s].
+// All threads then score every correspondence (:201-215): X' = R X + t, skipped when z <= 0, projected = K (X' / z),
+// inlier iff |x - projected| < threshold; the inlier count is a ballot / popc reduction.
+__global__ void __launch_bounds__(128) pnp_ransac_kernel(const double* __restrict__ X3, const double* __restrict__ x2, int n,
+                                                         const int* __restrict__ samples6, const double* __restrict__ K9, double thr,
+                                                         int* __restrict__ counts, double* __restrict__ Rt) {
+    __shared__ double sR[2][9], st[2][3];
+    __shared__ int cnt[2];
+    const int h = blockIdx.x;
+    if (threadIdx.x < 2) cnt[threadIdx.x] = 0;
+    if (threadIdx.x == 0) {
+        double A[12][12], V[12][12], w[12];
+        for (int i = 0; i < 6; i++) {
+            const int idx = samples6[6 * h + i];
+            const double X = X3[3 * idx], Y = X3[3 * idx + 1], Z = X3[3 * idx + 2], u = x2[2 * idx], v = x2[2 * idx + 1];
+            const double r0[12] = {X, Y, Z, 1, 0, 0, 0, 0, -u * X, -u * Y, -u * Z, -u};
+            const double r1[12] = {0, 0, 0, 0, X, Y, Z, 1, -v * X, -v * Y, -v * Z, -v};
+            for (int k = 0; k < 12; k++) { A[2 * i][k] = r0[k]; A[2 * i + 1][k] = r1[k]; }
+        }
+        jacobi_svd<12>(A, V, w);
+        int m = 0;
+        for (int k = 1; k < 12; k++)
+            if (w[k] < w[m]) m = k;
+        double p[12];
+        for (int k = 0; k < 12; k++) p[k] = V[k][m];
+        int big = 0;
+        for (int k = 1; k < 12; k++)
+            if (fabs(p[k]) > fabs(p[big])) big = k;
+        const double s0 = p[big] < 0 ? -1.0 : 1.0;  // sign 0: the component of largest magnitude is positive
+        for (int sgn = 0; sgn < 2; sgn++) {
+            const double f = sgn == 0 ? s0 : -s0;
+            double R[3][3], U[3][3], W[3][3], sw[3];
+            double fro = 0;
+            for (int r = 0; r < 3; r++)
+                for (int c = 0; c < 3; c++) {
+                    R[r][c] = f * p[3 * c + r];  // column-major Map of the row-major vector
+                    fro += R[r][c] * R[r][c];
+                }
+            fro = sqrt(fro);
+            for (int r = 0; r < 3; r++)
+                for (int c = 0; c < 3; c++) U[r][c] = R[r][c];
+            jacobi_svd<3>(U, W, sw);  // U <- U diag(sw) (columns), W = V
+            int ord[3] = {0, 1, 2};
+            for (int i = 0; i < 2; i++)
+                for (int j = i + 1; j < 3; j++)
+                    if (sw[ord[j]] > sw[ord[i]]) { const int t = ord[i]; ord[i] = ord[j]; ord[j] = t; }
+            double Uo[3][3], Vo[3][3];
+            for (int c = 0; c < 3; c++)
+                for (int k = 0; k < 3; k++) {
+                    Uo[k][c] = sw[ord[c]] > 0 ? U[k][ord[c]] / sw[ord[c]] : 0.0;
+                    Vo[k][c] = W[k][ord[c]];
+                }
+            if (!(sw[ord[2]] > 1e-300)) {  // rank-deficient block: complete U with a cross product
+                Uo[0][2] = Uo[1][0] * Uo[2][1] - Uo[2][0] * Uo[1][1];
+                Uo[1][2] = Uo[2][0] * Uo[0][1] - Uo[0][0] * Uo[2][1];
+                Uo[2][2] = Uo[0][0] * Uo[1][1] - Uo[1][0] * Uo[0][1];
+            }
+            double UVt[9];
+            for (int r = 0; r < 3; r++)
+                for (int c = 0; c < 3; c++) UVt[3 * r + c] = (Uo[r][0] * Vo[c][0] + Uo[r][1] * Vo[c][1]) + Uo[r][2] * Vo[c][2];
+            const double det = det3(UVt);
+            for (int r = 0; r < 3; r++)
+                for (int c = 0; c < 3; c++) sR[sgn][3 * r + c] = (Uo[r][0] * Vo[c][0] + Uo[r][1] * Vo[c][1]) + det * Uo[r][2] * Vo[c][2];
+            for (int k = 0; k < 3; k++) st[sgn][k] = f * p[9 + k] / fro;
+        }
+    }
+    __syncthreads();
+    const unsigned lane = lane_id();
+    for (int sgn = 0; sgn < 2; sgn++) {
+        const double* R = sR[sgn];
+        const double* t = st[sgn];
+        int good = 0;
+        for (int base = 0; base < n; base += blockDim.x) {
+            const int j = base + threadIdx.x;
+            bool in = false;
+            if (j < n) {
+                const double X = X3[3 * j], Y = X3[3 * j + 1], Z = X3[3 * j + 2];
+                const double tx = ((R[0] * X + R[1] * Y) + R[2] * Z) + t[0];
+                const double ty = ((R[3] * X + R[4] * Y) + R[5] * Z) + t[1];
+                const double tz = ((R[6] * X + R[7] * Y) + R[8] * Z) + t[2];
+                if (tz > 0) {
+                    const double nx = tx / tz, ny = ty / tz, nz = tz / tz;
+                    const double px = (K9[0] * nx + K9[1] * ny) + K9[2] * nz;
+                    const double py = (K9[3] * nx + K9[4] * ny) + K9[5] * nz;
+                    const double dx = x2[2 * j] - px, dy = x2[2 * j + 1] - py;
+                    in = sqrt(dx * dx + dy * dy) < thr;
+                }
+            }
+            good += __popc(__ballot_sync(0xffffffffu, in));
+        }
+        if (lane == 0 && good) atomicAdd(&cnt[sgn], good);
+    }
+    __syncthreads();
+    if (threadIdx.x < 2) counts[2 * h + threadIdx.x] = cnt[threadIdx.x];
+    if (threadIdx.x < 24) {
+        const int sgn = threadIdx.x / 12, k = threadIdx.x % 12;
+        Rt[(size_t)(2 * h + sgn) * 12 + k] = k < 9 ? sR[sgn][k] : st[sgn][k - 9];
+    }
+}
+
 }  // namespace
 
 int launch_recover_pose(const EssentialJob& job, int n_pairs, const double* K4, double* R, double* t, int* front, cudaStream_t st) {
     SLAM_KERNEL("recover_pose", st, recover_pose_kernel<<<n_pairs, 128, 0, st>>>(job, K4[0], K4[1], K4[2], K4[3], R, t, front));
+    return 1;
+}
+
+int launch_triangulate(const double* P24, const float* p1, const float* p2, int n, double* out4, double* out3, cudaStream_t st) {
+    if (n <= 0) return 0;
+    SLAM_KERNEL("triangulate", st, triangulate_kernel<<<(n + 127) / 128, 128, 0, st>>>(P24, p1, p2, n, out4, out3));
+    return 1;
+}
+
+int launch_pnp_ransac(const double* X3, const double* x2, int n, const int* samples6, int n_hyp, const double* K9, double thr, int* counts,
+                      double* Rt, cudaStream_t st) {
+    if (n_hyp <= 0) return 0;
+    SLAM_KERNEL("pnp_ransac", st, pnp_ransac_kernel<<<n_hyp, 128, 0, st>>>(X3, x2, n, samples6, K9, thr, counts, Rt));
     return 1;
 }
 

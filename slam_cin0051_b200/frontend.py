@@ -88,14 +88,12 @@ class FeatureDetector:
             self.max_features = get_int(cfg, "MaxFeatures") or 2000
             if self.patch_size != 31 or self.num_brief_pairs != 256:
                 raise RuntimeError("ORB mode requires PatchSize 31 and NumBRIEFPairs 256.")
-            self.orb_pattern = np.ascontiguousarray(
-                np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "orb_bit_pattern_31.npy")), np.int32)
             c.mode = 1
             c.n_levels = self.num_levels
             c.scale_factor = self.scale_factor
             c.max_features = self.max_features
             c.fast_threshold = get_int(cfg, "FastThreshold") or self.intensity_threshold
-            c.orb_pattern = self.orb_pattern.ctypes.data_as(C.POINTER(C.c_int32))
+            c.orb_pattern = None  # the library's built-in copy of OpenCV's bit_pattern_31_
         h = C.c_void_p()
         self.ctx.check(lib.slamcu_detector_create(self.ctx.handle, C.byref(c), C.byref(h)))
         self.handle = h

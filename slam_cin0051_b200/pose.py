@@ -116,3 +116,74 @@ class PoseEstimator:
         c = self.camera
         r = estimate_pose(p1, p2, (c.fx, c.fy, c.cx, c.cy), context=self.ctx)
         return None if r is None else (r["R"], r["t"])
+
+
+def triangulate(P1, P2, points1, points2, context: Context | None = None):
+    """slam::triangulate (common.hpp:201-221): per correspondence the null vector of the 4x4 DLT system of the 3x4 projection
+    matrices P1, P2 and the pixel coordinates.  Returns (points4 (n, 4) unit norm with w >= 0, points3 (n, 3) = x / w)."""
+    ctx = context or Context.default()
+    a = np.ascontiguousarray(P1, np.float64).reshape(12)
+    b = np.ascontiguousarray(P2, np.float64).reshape(12)
+    p1 = np.ascontiguousarray(points1, np.float32).reshape(-1, 2)
+    p2 = np.ascontiguousarray(points2, np.float32).reshape(-1, 2)
+    if len(p1) != len(p2):
+        raise RuntimeError("point sets must have the same size")
+    x4, x3 = np.zeros((len(p1), 4)), np.zeros((len(p1), 3))
+    ctx.check(ctx.lib.slamcu_triangulate(ctx.handle, a.ctypes.data, b.ctypes.data, p1.ctypes.data, p2.ctypes.data, len(p1), x4.ctypes.data,
+                                         x3.ctypes.data))
+    return x4, x3
+
+
+def triangulate_points(K, R, t, points1, points2, context: Context | None = None):
+    """PoseEstimator::triangulatePoints (pose_estimator.cpp:69-104) on gathered pixel correspondences: P1 = K [I | 0],
+    P2 = K [R | t]; returns the (n, 3) points."""
+    K = np.asarray(K, np.float64).reshape(3, 3)
+    T1 = np.hstack([np.eye(3), np.zeros((3, 1))])
+    T2 = np.hstack([np.asarray(R, np.float64).reshape(3, 3), np.asarray(t, np.float64).reshape(3, 1)])
+    return triangulate(K @ T1, K @ T2, points1, points2, context)[1]
+
+
+def pnp_sample_indices(seed: int, n: int, iterations: int) -> np.ndarray:
+    """The 6-subset draws of LoopClosure::verifyGeometricConsistency (loop_closure.cpp:177-193), libstdc++ mt19937 seeded by `seed`."""
+    from . import _lib
+    out = np.zeros((iterations, 6), np.int32)
+    if _lib.load().slamcu_pnp_sample_indices(seed & 0xFFFFFFFF, n, iterations, out.ctypes.data) != 0:
+        raise RuntimeError("pnp_sample_indices: need n >= 6")
+    return out
+
+
+def pnp_ransac(points3d, points2d, K, samples6, threshold: float = 2.0, context: Context | None = None):
+    """The hypothesis loop of LoopClosure::verifyGeometricConsistency (loop_closure.cpp:177-222) for the given 6-subsets.
+    Returns (counts (h, 2) int32, Rt (h, 2, 12)): inliers, R (row-major) and t for both signs of each DLT null vector."""
+    ctx = context or Context.default()
+    X = np.ascontiguousarray(points3d, np.float64).reshape(-1, 3)
+    x = np.ascontiguousarray(points2d, np.float64).reshape(-1, 2)
+    s6 = np.ascontiguousarray(samples6, np.int32).reshape(-1, 6)
+    k = np.ascontiguousarray(K, np.float64).reshape(9)
+    counts = np.zeros((len(s6), 2), np.int32)
+    Rt = np.zeros((len(s6), 2, 12))
+    ctx.check(ctx.lib.slamcu_pnp_ransac(ctx.handle, X.ctypes.data, x.ctypes.data, len(X), s6.ctypes.data, len(s6), k.ctypes.data, threshold,
+                                        counts.ctypes.data, Rt.ctypes.data))
+    return counts, Rt
+
+
+def verify_geometric_consistency(points3d, points2d, K, iterations: int = 100, threshold: float = 2.0, min_inliers: int = 5, seed: int = 0,
+                                 sign: str = "best", context: Context | None = None):
+    """LoopClosure::verifyGeometricConsistency's decision (loop_closure.cpp:177-236) on gathered correspondences: the first
+    hypothesis with the strictly largest inlier count wins (:217-221); None below `min_inliers` (:224-235).  sign: which null-vector
+    sign the SVD 'returned' ("best": the better of the two per hypothesis; 0 / 1: fixed)."""
+    s6 = pnp_sample_indices(seed, len(points3d), iterations)
+    counts, Rt = pnp_ransac(points3d, points2d, K, s6, threshold, context)
+    pick = counts.argmax(1) if sign == "best" else np.full(len(counts), int(sign))
+    c = counts[np.arange(len(counts)), pick]
+    best, max_inl = -1, 0
+    for h in range(len(c)):
+        if c[h] > max_inl:
+            best, max_inl = h, int(c[h])
+    if best < 0 or max_inl < min_inliers:
+        return None
+    rt = Rt[best, pick[best]]
+    T = np.eye(4)
+    T[:3, :3] = rt[:9].reshape(3, 3)
+    T[:3, 3] = rt[9:]
+    return {"inliers": max_inl, "relativeTransform": T, "hypothesis": best}

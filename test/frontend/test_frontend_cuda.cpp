@@ -6,6 +6,9 @@
 //   test_frontend_cuda image0.pgm image1.pgm detector.yml matcher.yml [fx fy cx cy]
 //   test_frontend_cuda --camera camera.yml [index] image.pgm      (test/preprocessing/test_preprocessor.cpp's image path:
 //                                                                  BGR2GRAY + Camera::undistortImage, digests of both)
+//   test_frontend_cuda --preprocess dir camera.yml                 (slam::Preprocessor over a directory stream: yield() per frame
+//                                                                  and the batched yieldInto(); frames are binary PPM payloads)
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
@@ -82,8 +85,81 @@ static int camera_main(int argc, char** argv) {
     return 0;
 }
 
+// the role cv::imread(path, IMREAD_COLOR) plays in Preprocessor::yield: here the files hold binary PPM (P6) payloads whose three
+// bytes per pixel are taken as B, G, R
+struct PpmDecoder {
+    bool operator()(const std::filesystem::path& path, int& rows, int& cols, std::vector<uint8_t>& bgr) const {
+        std::ifstream in(path, std::ios::binary);
+        std::string magic;
+        int maxv = 0;
+        in >> magic >> cols >> rows >> maxv;
+        in.get();
+        if (!in || magic != "P6" || maxv != 255) return false;
+        bgr.resize(static_cast<size_t>(rows) * cols * 3);
+        in.read(reinterpret_cast<char*>(bgr.data()), static_cast<std::streamsize>(bgr.size()));
+        return in.gcount() == static_cast<std::streamsize>(bgr.size());
+    }
+};
+
+static int preprocess_main(char** argv) {
+    try {
+        Camera cam(argv[3], 0);
+        Preprocessor<PpmDecoder> pre(argv[2], cam, PpmDecoder{}, 0);
+        std::printf("frames %d\n", pre.totalFrames());
+        for (;;) {  // test_preprocessing.cpp: yield until the stream ends
+            auto frame = pre.yield<RowMajorMatrix<double>>();
+            if (frame.first.rows() == 0) break;
+            const long long ms = std::chrono::duration_cast<std::chrono::milliseconds>(frame.second.time_since_epoch()).count();
+            std::printf("yield %ldx%ld %016llx ms_mod %lld\n", frame.first.rows(), frame.first.cols(),
+                        fnv(frame.first.data(), static_cast<size_t>(frame.first.rows() * frame.first.cols()) * sizeof(double)), ms % 1000);
+        }
+        // the batched path: BGR2GRAY + undistortion straight into a device-resident sequence, every second frame (frameSkip = 1)
+        Preprocessor<PpmDecoder> pre2(argv[2], cam, PpmDecoder{}, 1);
+        slamcu_sequence* seq = nullptr;
+        Context& ctx = Context::instance();
+        ctx.check(slamcu_sequence_create(ctx.get(), cam.height(), cam.width(), 8, 0, 0, 32, &seq));
+        const int got = pre2.yieldInto(seq, 0, 8);
+        std::printf("batched %d\n", got);
+        for (int f = 0; f < got; f++) {
+            GrayMatrix img(cam.height(), cam.width());
+            ctx.check(slamcu_sequence_image(seq, f, img.data(), cam.width()));
+            std::printf("slot %d %016llx\n", f, fnv(img.data(), static_cast<size_t>(img.rows() * img.cols())));
+        }
+        slamcu_sequence_destroy(seq);
+        try {
+            Preprocessor<PpmDecoder> bad(std::string(argv[2]) + "/does-not-exist", cam, PpmDecoder{});
+            return -1;
+        } catch (const std::runtime_error& e) {
+            std::printf("bad: %s\n", e.what());
+        }
+    } catch (const std::exception& e) {
+        std::fprintf(stderr, "Exception: %s\n", e.what());
+        return -1;
+    }
+    return 0;
+}
+
+// cv::Mat / cv::KeyPoint / cv::DMatch / cv::Point3d / KeyDescriptorPair look-alikes for slam::cuda::PoseEstimator (the shapes of
+// the reference's types: tests/native/adapter_signatures.cpp compiles the same calls against the reference's own headers)
+struct MockMat {
+    int rows = 0, cols = 0;
+    unsigned char* data = nullptr;
+    std::vector<unsigned char> buf;
+    void create(int r, int c, int /*type: CV_64F*/) { rows = r; cols = c; buf.assign(static_cast<size_t>(r) * c * 8, 0); data = buf.data(); }
+    bool empty() const { return data == nullptr; }
+};
+struct MockPoint2f { float x, y; };
+struct MockKeyPoint { MockPoint2f pt; };
+struct MockDMatch { int queryIdx, trainIdx; };
+struct MockPoint3d { double x, y, z; MockPoint3d(double X, double Y, double Z) : x(X), y(Y), z(Z) {} };
+struct CameraK {  // only getIntrinsicMatrix() is read
+    double K[9];
+    const double* getIntrinsicMatrix() const { return K; }
+};
+
 int main(int argc, char** argv) {
     if (argc >= 4 && std::string(argv[1]) == "--camera") return camera_main(argc, argv);
+    if (argc >= 4 && std::string(argv[1]) == "--preprocess") return preprocess_main(argv);
     if (argc < 5) {
         std::fprintf(stderr, "usage: %s image0.pgm image1.pgm detector.yml matcher.yml [fx fy cx cy]\n", argv[0]);
         return -1;
@@ -146,6 +222,36 @@ int main(int argc, char** argv) {
             std::printf("pose valid %d R", pose.valid ? 1 : 0);
             for (double v : pose.R) std::printf(" %.17g", v);
             std::printf(" t %.17g %.17g %.17g\n", pose.t[0], pose.t[1], pose.t[2]);
+            // slam::PoseEstimator's own signature: estimate(pairs1, pairs2, matches, R, t) + triangulatePoints
+            const CameraK camK{{K4[0], 0, K4[2], 0, K4[1], K4[3], 0, 0, 1}};
+            PoseEstimator estimator(camK);
+            std::vector<std::pair<MockKeyPoint, MockMat>> pairs0, pairs1;
+            std::vector<MockKeyPoint> ck0, ck1;
+            for (const Keypoint& k : kps0) { pairs0.push_back({MockKeyPoint{{k.x, k.y}}, MockMat{}}); ck0.push_back(MockKeyPoint{{k.x, k.y}}); }
+            for (const Keypoint& k : kps1) { pairs1.push_back({MockKeyPoint{{k.x, k.y}}, MockMat{}}); ck1.push_back(MockKeyPoint{{k.x, k.y}}); }
+            std::vector<std::pair<int, int>> idx;
+            std::vector<MockDMatch> dm;
+            for (const Match& m : mn) { idx.emplace_back(m.queryIdx, m.trainIdx); dm.push_back(MockDMatch{m.queryIdx, m.trainIdx}); }
+            MockMat R, t;
+            estimator.estimate(pairs0, pairs1, idx, R, t);
+            std::printf("estimator touched %d", R.empty() ? 0 : 1);
+            if (!R.empty()) {
+                const double* r = reinterpret_cast<const double*>(R.data);
+                const double* tv = reinterpret_cast<const double*>(t.data);
+                std::printf(" R");
+                for (int i = 0; i < 9; i++) std::printf(" %.17g", r[i]);
+                std::printf(" t %.17g %.17g %.17g", tv[0], tv[1], tv[2]);
+            }
+            std::printf("\n");
+            MockMat R2, t2;  // fewer than 8 matches: R, t stay untouched (pose_estimator.cpp:22-26)
+            estimator.estimate(pairs0, pairs1, std::vector<std::pair<int, int>>(idx.begin(), idx.begin() + std::min<size_t>(idx.size(), 7)), R2, t2);
+            std::printf("estimator_few touched %d\n", R2.empty() ? 0 : 1);
+            if (!R.empty()) {
+                const std::vector<MockPoint3d> pts = estimator.triangulatePoints<MockPoint3d>(ck0, ck1, dm, R, t);
+                std::printf("triangulated %zu", pts.size());
+                for (size_t i = 0; i < pts.size() && i < 3; i++) std::printf(" %.17g %.17g %.17g", pts[i].x, pts[i].y, pts[i].z);
+                std::printf("\n");
+            }
         }
     } catch (const std::exception& e) {
         std::fprintf(stderr, "Exception: %s\n", e.what());

@@ -115,3 +115,12 @@ def test_both_build_recipes_pass_the_exactness_flags():
     assert "-fmad=false" in b.NVCC_FLAGS and not any("fast_math" in f or "fast-math" in f for f in b.NVCC_FLAGS)
     cm = open(os.path.join(ROOT, "CMakeLists.txt")).read()
     assert "-fmad=false" in cm and "fast_math" not in cm and "fast-math" not in cm
+
+
+def test_builtin_orb_pattern_is_the_extracted_cv2_table():
+    """csrc/orb_pattern.inc (compiled into the library; used when slamcu_detector_config.orb_pattern is NULL) holds exactly the
+    256 x 4 table tools/extract_orb_pattern.py recovered from cv2 (slam_cin0051_b200/orb_bit_pattern_31.npy)."""
+    txt = open(os.path.join(ROOT, "slam_cin0051_b200", "csrc", "orb_pattern.inc")).read()
+    vals = [int(t) for line in txt.splitlines() if not line.lstrip().startswith("//") for t in line.replace(",", " ").split()]
+    want = np.load(os.path.join(ROOT, "slam_cin0051_b200", "orb_bit_pattern_31.npy")).astype(int).reshape(-1)
+    assert len(vals) == 1024 and vals == want.tolist()
