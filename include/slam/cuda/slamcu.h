@@ -118,6 +118,9 @@ int64_t slamcu_launch_count(const slamcu_context* ctx);
  * milliseconds and launch count of the index-th kernel name (SLAMCU_INVALID_ARGUMENT past the end). */
 /* Measured POPC issue ceiling of the device (G popc/s): the matcher's roofline denominator. */
 int slamcu_popc_peak(slamcu_context* ctx, double* gpopc_per_s);
+/* Test hook of the -DSLAMCU_DEBUG_BOUNDS build (libslamcu_dbg.so): evaluates one out-of-range index through the range-check macro
+ * the kernels use, which traps there; a no-op in the release build. */
+int slamcu_debug_trip_bound(slamcu_context* ctx);
 int slamcu_profile_enable(slamcu_context* ctx, int on);
 int slamcu_profile_read(slamcu_context* ctx, int index, char* name, int name_cap, double* total_ms, int64_t* launches);
 

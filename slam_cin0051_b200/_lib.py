@@ -11,7 +11,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libslamcu.so")
+# SLAMCU_LIB selects another build of the same library (the debug-bounds build libslamcu_dbg.so in tests/test_gpu_debug_bounds.py)
+LIB_PATH = os.environ.get("SLAMCU_LIB") or os.path.join(HERE, "libslamcu.so")
 
 OK, INVALID_ARGUMENT, EMPTY_INPUT, SIZE_MISMATCH, CAPACITY, CUDA_ERROR, UNSUPPORTED = range(7)
 
@@ -50,6 +51,7 @@ SYMBOLS = {
     "slamcu_alloc_pinned": (_i, [C.c_size_t, C.POINTER(_vp)]),
     "slamcu_free_pinned": (None, [_vp]),
     "slamcu_popc_peak": (_i, [_vp, C.POINTER(C.c_double)]),
+    "slamcu_debug_trip_bound": (_i, [_vp]),
     "slamcu_profile_enable": (_i, [_vp, _i]),
     "slamcu_profile_read": (_i, [_vp, _i, C.c_char_p, _i, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "slamcu_default_brief_pattern": (_i, [_i, _i, _vp, _i, _ip]),

@@ -57,6 +57,29 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return OUT
 
 
+def build_debug() -> str:
+    """libslamcu_dbg.so: the same sources with -DSLAMCU_DEBUG_BOUNDS (every list / tile / gather index is checked and traps);
+    used by tests/test_gpu_debug_bounds.py in place of compute-sanitizer."""
+    out = os.path.join(HERE, "libslamcu_dbg.so")
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "slam", "cuda", "slamcu.h")]
+    if os.path.exists(out) and _newest(deps) <= os.path.getmtime(out):
+        return out
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    os.makedirs(os.path.join(HERE, "build", "dbg"), exist_ok=True)
+    procs, objs = [], []
+    for src in SOURCES:
+        obj = os.path.join(HERE, "build", "dbg", src.replace(".cu", ".o"))
+        objs.append(obj)
+        procs.append((src, subprocess.Popen([nvcc, *NVCC_FLAGS, "-DSLAMCU_DEBUG_BOUNDS", "-c", os.path.join(CSRC, src), "-o", obj],
+                                            stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for src, p in procs:
+        o, _ = p.communicate()
+        if p.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src} (debug-bounds build):\n{o}")
+    subprocess.check_call([nvcc, "-shared", "-o", out, *objs, "-lcudart"])
+    return out
+
+
 def build_host_tools(verbose: bool = False) -> list:
     """Host C++ programs above the C ABI: tools/cli/slam_bench and test/frontend/test_frontend_cuda (g++, no CUDA
     headers needed; they link libslamcu.so with an rpath to the package directory)."""
@@ -82,3 +105,4 @@ def build_host_tools(verbose: bool = False) -> list:
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
     print(build_host_tools(verbose="-v" in sys.argv))
+    print(build_debug())

@@ -22,6 +22,7 @@ void init_sortnms_attributes(int smem_optin);
 int launch_desc_or(const uint32_t* desc, const int* n_dev, int desc_words, uint32_t* out, cudaStream_t st, int sets = 1,
                    size_t set_stride = 0);
 long long launch_popc_peak(unsigned* scratch, int blocks, int iters, cudaStream_t st);
+void launch_trip_bound(cudaStream_t st);
 void init_orb_attributes(int smem_optin);
 }
 
@@ -376,6 +377,12 @@ int slamcu_popc_peak(slamcu_context* ctx, double* gpopc_per_s) {
     cudaEventDestroy(b);
     *gpopc_per_s = best;
     return check_launch(ctx, "popc_peak");
+}
+
+int slamcu_debug_trip_bound(slamcu_context* ctx) {
+    if (!ctx) return SLAMCU_INVALID_ARGUMENT;
+    launch_trip_bound(ctx->stream);
+    return check_launch(ctx, "trip_bound");
 }
 
 int slamcu_profile_enable(slamcu_context* ctx, int on) {

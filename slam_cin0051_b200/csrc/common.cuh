@@ -138,6 +138,18 @@ extern thread_local Profiler* g_prof;  // set by the API entry points while prof
         if (slamcu::g_prof) slamcu::g_prof->end(st);         \
     } while (0)
 
+// -DSLAMCU_DEBUG_BOUNDS (slam_cin0051_b200.build.build_debug -> libslamcu_dbg.so): every atomically indexed list write, tile
+// offset and gather named in DESIGN.md traps when its index leaves [0, limit).  compute-sanitizer is not available on the GPU
+// pool, so tests/test_gpu_debug_bounds.py runs the edge cases (noise, tiny images, list overflow) through this build instead.
+#ifdef SLAMCU_DEBUG_BOUNDS
+#define SLAMCU_BOUND(index, limit)                                                             \
+    do {                                                                                       \
+        if (!((long long)(index) >= 0 && (long long)(index) < (long long)(limit))) __trap();  \
+    } while (0)
+#else
+#define SLAMCU_BOUND(index, limit) ((void)0)
+#endif
+
 __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31; }
 __device__ __forceinline__ unsigned lanemask_lt() {
     unsigned m;

@@ -129,7 +129,10 @@ __global__ void __launch_bounds__(256) fast_mask_kernel(SeqView s, int first, in
                 const int base = r * TW + 4 * lane;
 #pragma unroll
                 for (int k = 0; k < 4; k++)
-                    if (m & (0x80u << (8 * k))) list[pos++] = (uint16_t)(base + k);
+                    if (m & (0x80u << (8 * k))) {
+                        SLAMCU_BOUND(pos, TH * TW);
+                        list[pos++] = (uint16_t)(base + k);
+                    }
             }
         }
     }

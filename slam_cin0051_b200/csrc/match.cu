@@ -303,6 +303,8 @@ __global__ void __launch_bounds__(MTHR) match256_kernel(MatchJob job, int n_seg,
         int4 c = make_int4(-1, INT_MAX, INT_MAX, -1);
         if (kbest[m] != 0xffffffffu) { c.y = (int)(kbest[m] >> kKeyShift); c.x = (int)(kbest[m] & ((1u << kKeyShift) - 1)); }
         if (ksecond[m] != 0xffffffffu) { c.z = (int)(ksecond[m] >> kKeyShift); c.w = (int)(ksecond[m] & ((1u << kKeyShift) - 1)); }
+        SLAMCU_BOUND(q0 + m * MTHR + threadIdx.x, job.max_q);
+        SLAMCU_BOUND(c.x + 1, nt + 1);  // -1 = no candidate (an empty train slice)
         job.cand[(size_t)blockIdx.z * seg_stride + (size_t)pair * job.cand_pair_stride + q0 + m * MTHR + threadIdx.x] = c;
     }
 }
@@ -365,6 +367,7 @@ __global__ void __launch_bounds__(256) finalize_kernel(MatchJob job, MatchParams
         for (int w = 0; w < warp; w++) off += warp_tot[w];
         const int pos = off + __popc(b & lanemask_lt());
         if (good && pos < job.cap_out) {
+            SLAMCU_BOUND(pos, job.cap_out);
             if (staged) keys_g[pos] = ((unsigned long long)(uint32_t)c.y << 32) | (uint32_t)q;
             else {
                 slamcu_dmatch m;

@@ -19,7 +19,11 @@ __global__ void __launch_bounds__(256) popc_peak_kernel(unsigned* out, int iters
     }
     if ((s0 + s1 + s2 + s3) == 0xffffffffu) out[0] = s0;
 }
+__global__ void trip_bound_kernel(int index, int limit) { SLAMCU_BOUND(index, limit); }
 }  // namespace
+
+// test hook of the debug-bounds build: an out-of-range index through the very macro the kernels use (a no-op in release builds)
+void launch_trip_bound(cudaStream_t st) { trip_bound_kernel<<<1, 1, 0, st>>>(1, 1); }
 
 // returns the number of POPCs executed; caller times it
 long long launch_popc_peak(unsigned* scratch, int blocks, int iters, cudaStream_t st) {

@@ -318,7 +318,10 @@ __global__ void __launch_bounds__(256) fast9_mask_kernel(SeqView s, OrbView o, i
                 const int base = ry * SCW + 4 + 4 * lane;
 #pragma unroll
                 for (int k = 0; k < 4; k++)
-                    if (m & (0x80u << (8 * k))) list1[pos++] = (uint16_t)(base + k);
+                    if (m & (0x80u << (8 * k))) {
+                        SLAMCU_BOUND(pos, SCH * SCW);
+                        list1[pos++] = (uint16_t)(base + k);
+                    }
             }
         }
         if (threadIdx.x < 2 * SCH) {  // the two ring columns of every score-grid row
@@ -326,7 +329,11 @@ __global__ void __launch_bounds__(256) fast9_mask_kernel(SeqView s, OrbView o, i
             const int cx = (threadIdx.x & 1) ? FTW + 4 : 3;  // score-grid columns of x0+128 and x0-1
             const int gx = x0 - 4 + cx;
             if ((unsigned)(gy - 3) < (unsigned)(L.rows - 6) && gx >= lo && gx < hi)
-                list1[atomicAdd(&n1, 1)] = (uint16_t)(ry * SCW + cx);
+            {
+                const int pos = atomicAdd(&n1, 1);
+                SLAMCU_BOUND(pos, SCH * SCW);
+                list1[pos] = (uint16_t)(ry * SCW + cx);
+            }
         }
     }
     __syncthreads();
@@ -336,12 +343,17 @@ __global__ void __launch_bounds__(256) fast9_mask_kernel(SeqView s, OrbView o, i
         const int idx = list1[e];
         const int ry = idx / SCW, cx = idx - ry * SCW;
         const uint8_t* t = tile + (ry + 3) * FSW + (FHX - 4) + cx;
+        SLAMCU_BOUND((ry + 3 - 3) * FSW + (FHX - 4) + cx - 3, FSH * FSW);
+        SLAMCU_BOUND((ry + 3 + 3) * FSW + (FHX - 4) + cx + 3, FSH * FSW);
         int p[16];
         fast9_load_ring(t, FSW, p);
         const int score = fast9_test_and_score(t[0], p, thr);
         if (score >= 0) {
             sc[idx] = (uint8_t)score;
-            list2[atomicAdd(&n2, 1)] = (uint16_t)idx;
+            const int pos = atomicAdd(&n2, 1);
+            SLAMCU_BOUND(pos, SCH * SCW);
+            SLAMCU_BOUND(idx, SCH * SCW);
+            list2[pos] = (uint16_t)idx;
         }
     }
     __syncthreads();
@@ -474,7 +486,10 @@ __global__ void __launch_bounds__(256) orb_select_kernel(SeqView s, OrbView o, i
         __syncthreads();
         int off = carry;
         for (int w = 0; w < warp; w++) off += warp_tot[w];
-        if (keep) sxy[off + __popc(b & lanemask_lt())] = cxy[i];
+        if (keep) {
+            SLAMCU_BOUND(off + __popc(b & lanemask_lt()), L.capc);
+            sxy[off + __popc(b & lanemask_lt())] = cxy[i];
+        }
         __syncthreads();
         if (threadIdx.x == 0) {
             int t = 0;
@@ -601,6 +616,7 @@ __global__ void __launch_bounds__(256) orb_retain_kernel(SeqView s, OrbView o, i
         for (int w = 0; w < warp; w++) off += warp_tot[w];
         if (keep) {
             const int pos = off + __popc(b & lanemask_lt());
+            SLAMCU_BOUND(pos, L.capc);
             fxy[pos] = sxy[i];
             fr[pos] = v;
         }
@@ -646,6 +662,7 @@ __global__ void __launch_bounds__(256) orb_assemble_kernel(SeqView s, OrbView o,
             k.size = (float)kOrbPatch * L.scale;
             k.angle = 0.f;
             k.response = o.fresp[base_off + i];
+            SLAMCU_BOUND(pos, s.cap_kp);
             kps[pos] = k;
             o.octave[(size_t)f * s.cap_kp + pos] = l;
             o.lxy[(size_t)f * s.cap_kp + pos] = p;
@@ -872,6 +889,8 @@ __global__ void __launch_bounds__(128) orb_describe_kernel(SeqView s, OrbView o,
 #pragma unroll
             for (int v = 1; v <= kOrbHalfPatch; v++) {
                 if (au <= umax[v]) {
+                    SLAMCU_BOUND((y + v) * pitch + x + u, o.lv[l].rows * pitch);
+                    SLAMCU_BOUND((y - v) * pitch + x + u, o.lv[l].rows * pitch);
                     const int below = c[v * pitch], above = c[-v * pitch];
                     col += below + above;
                     vsum += v * (below - above);
@@ -911,6 +930,8 @@ __global__ void __launch_bounds__(128) orb_describe_kernel(SeqView s, OrbView o,
             const float2 p0 = pp[2 * k], p1 = pp[2 * k + 1];
             const int ix0 = __float2int_rn(p0.x * a - p0.y * b), iy0 = __float2int_rn(p0.x * b + p0.y * a);
             const int ix1 = __float2int_rn(p1.x * a - p1.y * b), iy1 = __float2int_rn(p1.x * b + p1.y * a);
+            SLAMCU_BOUND((y + iy0) * pitch + x + ix0, o.lv[l].rows * pitch);
+            SLAMCU_BOUND((y + iy1) * pitch + x + ix1, o.lv[l].rows * pitch);
             const int t0 = cb[iy0 * pitch + ix0], t1 = cb[iy1 * pitch + ix1];
             byte |= (unsigned)(t0 < t1) << k;
         }

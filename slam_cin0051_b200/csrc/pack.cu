@@ -68,6 +68,8 @@ __global__ void __launch_bounds__(256) dense_copy_kernel(SeqView s, int first, i
                 if (threadIdx.x == 0) atomicOr(overflow, 1);
                 continue;
             }
+            SLAMCU_BOUND(base, kp_cap + 1);
+            SLAMCU_BOUND(n, s.cap_kp + 1);
             if (h_kps) copy_rows<5>(reinterpret_cast<const uint32_t*>(s.kps + (size_t)f * s.cap_kp), h_kps + (size_t)base * 5, n, 0, 1);
             if (h_desc) {
                 const uint32_t* src = s.desc + (size_t)f * s.cap_kp * s.desc_words;
