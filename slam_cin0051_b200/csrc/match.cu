@@ -279,8 +279,22 @@ __global__ void __launch_bounds__(MTHR) match256_kernel(MatchJob job, int n_seg,
         }
         __syncthreads();
         if (wmax > 2) {
-#pragma unroll 4
-            for (int j = 0; j < cnt; j++) {
+            // two train descriptors per step: their keys are ordered first, then merged into the running top-2 with a 3-input
+            // minimum -- five min / max per two comparisons instead of six
+            int j = 0;
+#pragma unroll 2
+            for (; j + 1 < cnt; j += 2) {
+                const uint4 a0 = tile[2 * j], b0 = tile[2 * j + 1], a1 = tile[2 * j + 2], b1 = tile[2 * j + 3];
+#pragma unroll
+                for (int m = 0; m < MQ; m++) {
+                    const uint32_t k0 = hamming256_key(qd[m], a0, b0, (uint32_t)(t0 + j), w1, w2, w4);
+                    const uint32_t k1 = hamming256_key(qd[m], a1, b1, (uint32_t)(t0 + j + 1), w1, w2, w4);
+                    const uint32_t lo = min(k0, k1), hi = max(k0, k1);
+                    ksecond[m] = __vimin3_u32(ksecond[m], max(kbest[m], lo), hi);
+                    kbest[m] = min(kbest[m], lo);
+                }
+            }
+            if (j < cnt) {
                 const uint4 a = tile[2 * j], b = tile[2 * j + 1];
 #pragma unroll
                 for (int m = 0; m < MQ; m++) top2_update_key(kbest[m], ksecond[m], hamming256_key(qd[m], a, b, (uint32_t)(t0 + j), w1, w2, w4));
