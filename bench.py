@@ -400,8 +400,7 @@ def run_ours(args, w, rank, world, local_rank):
             dist.barrier()
 
     def step_resident():
-        seq.extract(det, 0, NF)
-        seq.match_consecutive(mat, 0, NP, with_keypoints=with_kp)
+        seq.extract_match(det, mat, 0, NF, with_keypoints=with_kp, chunk=args.lane_chunk)  # detectAndCompute + match(f, f+1)
         if k4:
             seq.essential(k4, 0, NP)
         gather_counts(seq)
@@ -542,8 +541,8 @@ def run_ours(args, w, rank, world, local_rank):
                       "raw_corners_per_frame_mean": n_raw_mean, "matches_per_pair_mean": n_match_mean,
                       "gathered_keypoints_total": int(g_host[:, 0].sum()), "gathered_matches_total": int(g_host[:, 1].sum()),
                       "l2": f"inputs larger than L2: {NF * ROWS * COLS / 1e6:.0f} MB of frames per GPU per step vs 126 MB L2",
-                      "timing": "value: CUDA events around K unprofiled steps (blur pyramid on a forked stream), max over ranks; kernels[]: a second pass of "
-                                "the same K steps with events around every launch",
+                      "timing": "value: CUDA events around K unprofiled steps (blur pyramid on a forked stream), max over ranks; kernels[]: a second pass "
+                                "of the same K steps with events around every launch; e2e: chunks alternate between two compute lanes",
                       "ms_per_step_profiled_pass": ms_prof / args.steps, "collective": "all_gather_into_tensor of int32[frames][4] per step, inside both timed regions" if world > 1 else "none at N=1 (device-side count pack only)",
                       "numa": numa},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -613,6 +612,7 @@ def main():
     ap.add_argument("--frames", type=int, default=None, help="frames per GPU per step (default: the workload's; kitti = 1000 per GPU)")
     ap.add_argument("--max-keypoints", type=int, default=None)
     ap.add_argument("--chunk", type=int, default=None, help="frames per pipeline stage of the end-to-end leg")
+    ap.add_argument("--lane-chunk", type=int, default=0, help="frames per chunk of a two-lane resident step (0: one lane, the faster choice with resident inputs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra-legs", action="store_true", help="skip the mode_reference / config3 / hamming_sweep legs (N = 1 default run)")
     args = ap.parse_args()

@@ -80,6 +80,7 @@ SYMBOLS = {
     "slamcu_sequence_frames_device": (_i, [_vp, C.POINTER(_vp), _ip, C.POINTER(C.c_int64)]),
     "slamcu_sequence_extract": (_i, [_vp, _vp, _i, _i]),
     "slamcu_sequence_match": (_i, [_vp, _vp, _i, _i, _i]),
+    "slamcu_sequence_extract_match": (_i, [_vp, _vp, _vp, _i, _i, _i, _i]),
     "slamcu_sequence_counts": (_i, [_vp, _i, _i, _vp]),
     "slamcu_sequence_frame": (_i, [_vp, _i, _vp, _u8p, _i, _i, _ip]),
     "slamcu_sequence_matches": (_i, [_vp, _i, _vp, _i, _ip]),

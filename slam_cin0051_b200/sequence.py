@@ -80,6 +80,14 @@ class FrameSequence:
         self.ctx.check(self.ctx.lib.slamcu_sequence_match(self.handle, matcher.handle, first, n_pairs,
                                                           1 if with_keypoints else 0))
 
+    def extract_match(self, detector: FeatureDetector, matcher: FeatureMatcher, first: int = 0, n: int | None = None,
+                      with_keypoints: bool = True, chunk: int = 0):
+        """extract() on frames [first, first + n) and match_consecutive() on the n - 1 pairs inside, chunked over the context's two
+        compute lanes (the matcher of one chunk overlaps the extraction of the next); same results, asynchronous."""
+        n = self.max_frames - first if n is None else n
+        self.ctx.check(self.ctx.lib.slamcu_sequence_extract_match(self.handle, detector.handle, matcher.handle, first, n,
+                                                                  1 if with_keypoints else 0, chunk))
+
     def counts(self, first: int = 0, n: int | None = None) -> np.ndarray:
         """(n, 4) int32: n_keypoints, n_matches (pair f,f+1), n_raw_corners, status.  Synchronises."""
         n = self.max_frames - first if n is None else n

@@ -79,3 +79,45 @@ def test_sequence_with_empty_frames(gpu_ctx, mode):
     assert k0.tobytes() == k0s.tobytes() and np.array_equal(d0, d0s)
     k2, d2 = seq.frame(2)
     assert len(k2) == 0
+
+
+@pytest.mark.parametrize("mode", ["orb", "reference"])
+def test_two_lane_extract_match_equals_the_serial_calls(gpu_ctx, mode):
+    """slamcu_sequence_extract_match (chunks alternating between the two compute lanes, the matcher of one chunk next to the
+    extraction of the following one) gives bit for bit what extract() followed by match_consecutive() gives."""
+    import os
+
+    import slam_cin0051_b200 as s
+    from conftest import DATA
+    from slam_cin0051_b200.synth import make_sequence
+    sfx = "_orb" if mode == "orb" else ""
+    det = s.FeatureDetector(os.path.join(DATA, f"feature_detector{sfx}.yml"), gpu_ctx)
+    mat = s.FeatureMatcher(os.path.join(DATA, f"feature_matcher{sfx}.yml"), gpu_ctx)
+    n = 37
+    frames = np.concatenate([make_sequence(240, 400, 16, 14, seed=50 + g) for g in range(3)])[:n]
+    with_kp = mode != "orb"
+
+    def snapshot(seq):
+        c = seq.counts()
+        assert (c[:, 3] == 0).all()
+        return c.tobytes(), [tuple(x.tobytes() for x in seq.frame(f)) for f in range(n)], [seq.matches(f).tobytes() for f in range(n - 1)]
+
+    a = s.FrameSequence(240, 400, n, desc_bytes=32, max_keypoints=4096, context=gpu_ctx)
+    a.upload(frames)
+    a.extract(det)
+    a.match_consecutive(mat, with_keypoints=with_kp)
+    want = snapshot(a)
+    for chunk in (0, 1, 5, 16, 36, 64):
+        b = s.FrameSequence(240, 400, n, desc_bytes=32, max_keypoints=4096, context=gpu_ctx)
+        b.upload(frames)
+        for _ in range(2):  # twice: the second call reuses events and lanes
+            b.extract_match(det, mat, 0, n, with_keypoints=with_kp, chunk=chunk)
+        assert snapshot(b) == want, chunk
+    # a sub-range
+    b = s.FrameSequence(240, 400, n, desc_bytes=32, max_keypoints=4096, context=gpu_ctx)
+    b.upload(frames)
+    b.extract_match(det, mat, 5, 20, with_keypoints=with_kp, chunk=6)
+    for f in range(5, 25):
+        assert tuple(x.tobytes() for x in b.frame(f)) == want[1][f]
+    for f in range(5, 24):
+        assert b.matches(f).tobytes() == want[2][f]
