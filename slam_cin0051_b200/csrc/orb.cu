@@ -79,11 +79,13 @@ __global__ void __launch_bounds__(256) pyr_down_gather_kernel(SeqView s, OrbView
 
 // The same arithmetic with the source staged through shared memory: one block produces a 128 x 64 tile of level l from
 // the (128 s + 2) x (64 s + 2) source window of level l-1, loaded once with aligned 128-bit loads.  A thread walks
-// 4 columns down 8 output rows and keeps the horizontally interpolated source row it shares with the next output row
+// 4 columns down PT_RPT output rows and keeps the horizontally interpolated source row it shares with the next output row
 // (consecutive output rows are 1.2 source rows apart, so most rows cost one new source row, not two).
 constexpr int PT_W = 128, PT_H = 64;        // output tile
+constexpr int PT_RPT = 16;                   // output rows per thread (the per-thread set-up -- column selectors, table loads -- is paid once)
+constexpr int PT_THREADS = 32 * (PT_H / PT_RPT);
 constexpr int PS_PITCH = 192, PS_ROWS = 84;  // source window held in shared memory (bytes per row, rows)
-__global__ void __launch_bounds__(256) pyr_down_kernel(SeqView s, OrbView o, int first, int l) {
+__global__ void __launch_bounds__(PT_THREADS) pyr_down_kernel(SeqView s, OrbView o, int first, int l) {
     __shared__ __align__(16) uint8_t tile[PS_ROWS * PS_PITCH];
     const int f = first + blockIdx.z;
     const OrbLevel& d = o.lv[l];
@@ -93,10 +95,10 @@ __global__ void __launch_bounds__(256) pyr_down_kernel(SeqView s, OrbView o, int
     const uint8_t* src = level_ptr(s, o, f, l - 1);
     uint8_t* dst = level_ptr_w(s, o, f, l);
     const int x = x0 + (threadIdx.x & 31) * 4;
-    const int yw = y0 + (threadIdx.x >> 5) * 8;  // first of this thread's 8 output rows
+    const int yw = y0 + (threadIdx.x >> 5) * PT_RPT;  // first of this thread's PT_RPT output rows
     if (x0 >= d.cols) {  // a block in the row padding: zeros, like the gather kernel writes them
         if (x < d.pitch)
-            for (int r = 0; r < 8 && yw + r < d.rows; r++) *reinterpret_cast<uint32_t*>(dst + (size_t)(yw + r) * d.pitch + x) = 0u;
+            for (int r = 0; r < PT_RPT && yw + r < d.rows; r++) *reinterpret_cast<uint32_t*>(dst + (size_t)(yw + r) * d.pitch + x) = 0u;
         return;
     }
     const int sy_lo = (int)(__ldg(d.yt + y0) >> 8);
@@ -104,56 +106,69 @@ __global__ void __launch_bounds__(256) pyr_down_kernel(SeqView s, OrbView o, int
     const int sx_lo = (int)(__ldg(d.xt + x0) >> 8) & ~15;
     const int sx_hi = min((int)(__ldg(d.xt + min(x0 + PT_W, d.cols) - 1) >> 8) + 1, p.cols - 1);
     const int nrows = sy_hi - sy_lo + 1, nvec = (sx_hi - sx_lo) / 16 + 1;  // host guarantees nrows <= PS_ROWS, nvec * 16 <= PS_PITCH
-    for (int i = threadIdx.x; i < nrows * nvec; i += 256) {
-        const int r = i / nvec, c = i - r * nvec;
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (sx_lo + c * 16 < p.pitch) v = __ldg(reinterpret_cast<const uint4*>(src + (size_t)(sy_lo + r) * p.pitch + sx_lo + c * 16));
-        *reinterpret_cast<uint4*>(tile + r * PS_PITCH + c * 16) = v;
+    {  // 16 threads per staged row (nvec <= 12 of them load a 128-bit vector), rows strided over the thread groups
+        const int c = threadIdx.x & 15;
+        if (c < nvec) {
+            const bool inside = sx_lo + c * 16 < p.pitch;
+            const uint8_t* g = src + (size_t)sy_lo * p.pitch + sx_lo + c * 16;
+            for (int r = threadIdx.x >> 4; r < nrows; r += PT_THREADS / 16) {
+                uint4 v = make_uint4(0, 0, 0, 0);
+                if (inside) v = __ldg(reinterpret_cast<const uint4*>(g + (size_t)r * p.pitch));
+                *reinterpret_cast<uint4*>(tile + r * PS_PITCH + c * 16) = v;
+            }
+        }
     }
     __syncthreads();
     if (x >= d.pitch || yw >= d.rows) return;
-    int oa[4], ob[4], ax[4];
-    int nvalid = 0;
+    // Per thread (4 output columns): the source bytes all four outputs touch lie within 8 bytes of the first one (3 * 2.0 + 1
+    // at the steepest supported step), so a source row costs 3 aligned LDS.32 from the thread's own window, 2 funnel shifts to
+    // byte-align it, and per output one PRMT (picks the pair a, b) + one IDP.2A ((256 - ax) a + ax b, exact in 16 bits).
+    unsigned wx[4], sel[4];
+    int nvalid = 0, o0 = 0;
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         const bool ok = x + k < d.cols;
         const uint32_t t = ok ? __ldg(d.xt + x + k) : 0u;
-        const int sx0 = ok ? (int)(t >> 8) : sx_lo;
-        oa[k] = sx0 - sx_lo;
-        ob[k] = min(sx0 + 1, p.cols - 1) - sx_lo;
-        ax[k] = (int)(t & 255u);
+        const int sx0 = ok ? (int)(t >> 8) : sx_lo + o0;
+        const int a_off = sx0 - sx_lo, b_off = min(sx0 + 1, p.cols - 1) - sx_lo;
+        if (k == 0) o0 = a_off;
+        const unsigned axk = t & 255u;
+        wx[k] = (256u - axk) | (axk << 16);                          // IDP.2A weights: (256 - ax, ax)
+        sel[k] = (unsigned)(a_off - o0) | ((unsigned)(b_off - o0) << 4);           // PRMT selector: byte 0 <- a, byte 1 <- b
         nvalid += ok;
     }
-    uint32_t tys[8];  // the 8 row-table entries up front: independent loads instead of one dependent load per row
+    const int wbase = o0 & ~3, sh = 8 * (o0 & 3);
+    uint32_t tys[PT_RPT];  // the row-table entries up front: independent loads instead of one dependent load per row
 #pragma unroll
-    for (int r = 0; r < 8; r++) tys[r] = __ldg(d.yt + min(yw + r, d.rows - 1));
-    const int prows1 = p.rows - 1, dpitch = d.pitch, nrow = min(8, d.rows - yw);
+    for (int r = 0; r < PT_RPT; r++) tys[r] = __ldg(d.yt + min(yw + r, d.rows - 1));
+    const int prows1 = p.rows - 1, dpitch = d.pitch, nrow = min(PT_RPT, d.rows - yw);
     uint8_t* out = dst + (size_t)yw * dpitch + x;
+    auto hrow4 = [&](int sy, unsigned (&h)[4]) {  // the horizontally interpolated source row sy at the 4 output columns
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(tile + (sy - sy_lo) * PS_PITCH + wbase);
+        const unsigned w0 = w[0], w1 = w[1], w2 = w[2];
+        const unsigned lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
+#pragma unroll
+        for (int k = 0; k < 4; k++) h[k] = __dp2a_lo(wx[k], __byte_perm(lo, hi, sel[k]), 0u);  // IDP.2A.LO reads bytes 0, 1 of the pair only
+    };
     int hrow = -1;  // source row whose horizontal interpolation is cached in hc
-    int hc[4] = {0, 0, 0, 0};
+    unsigned hc[4] = {0, 0, 0, 0};
 #pragma unroll
-    for (int r = 0; r < 8; r++) {
+    for (int r = 0; r < PT_RPT; r++) {
         if (r >= nrow) break;
-        const int sy0 = (int)(tys[r] >> 8), ay = (int)(tys[r] & 255u), sy1 = min(sy0 + 1, prows1);
-        const uint8_t* r1 = tile + (sy1 - sy_lo) * PS_PITCH;
-        if (sy0 != hrow) {
-            const uint8_t* r0 = tile + (sy0 - sy_lo) * PS_PITCH;
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const int a = r0[oa[k]], b = r0[ob[k]];
-                hc[k] = (a << 8) + ax[k] * (b - a);
-            }
-        }
-        uint32_t packed = 0;
+        const int sy0 = (int)(tys[r] >> 8), sy1 = min(sy0 + 1, prows1);
+        const unsigned ay = tys[r] & 255u;
+        if (sy0 != hrow) hrow4(sy0, hc);
+        unsigned h1[4], v[4];
+        hrow4(sy1, h1);
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            const int a = r1[oa[k]], b = r1[ob[k]];
-            const int h1 = (a << 8) + ax[k] * (b - a);
-            const uint32_t v = (uint32_t)(((hc[k] << 8) + ay * (h1 - hc[k]) + 32768) >> 16);
-            if (k < nvalid) packed |= v << (8 * k);
-            hc[k] = h1;
+            // ((h0 << 8) + ay (h1 - h0) + 32768) >> 16, < 2^24: the result is byte 2 of the sum
+            v[k] = (hc[k] << 8) + 32768u + ay * (h1[k] - hc[k]);
+            hc[k] = h1[k];
         }
         hrow = sy1;
+        unsigned packed = __byte_perm(__byte_perm(v[0], v[1], 0x4462u), __byte_perm(v[2], v[3], 0x4462u), 0x5410u);
+        if (nvalid < 4) packed &= nvalid == 0 ? 0u : (0xffffffffu >> (8 * (4 - nvalid)));
         *reinterpret_cast<uint32_t*>(out) = packed;
         out += dpitch;
     }
@@ -969,7 +984,7 @@ int launch_orb_extract(const SeqView& s, const OrbView& o, int first, int n, cud
         const bool fits = PT_W * sx + 3 + 15 + 16 <= PS_PITCH && PT_H * sy + 4 <= PS_ROWS;
         if (fits) {
             dim3 grid((o.lv[l].pitch + PT_W - 1) / PT_W, (o.lv[l].rows + PT_H - 1) / PT_H, n);
-            SLAM_KERNEL("pyr_down", st, pyr_down_kernel<<<grid, 256, 0, st>>>(s, o, first, l));
+            SLAM_KERNEL("pyr_down", st, pyr_down_kernel<<<grid, PT_THREADS, 0, st>>>(s, o, first, l));
         } else {  // steep scale factors: per-pixel gather
             dim3 grid((o.lv[l].pitch + 127) / 128, (o.lv[l].rows + 7) / 8, n);
             SLAM_KERNEL("pyr_down", st, pyr_down_gather_kernel<<<grid, 256, 0, st>>>(s, o, first, l));
