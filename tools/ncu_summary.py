@@ -45,7 +45,7 @@ def main():
         for r in body:
             m = re.search(r"(\w+?)_kernel", r[kn])
             name = m.group(1) if m else r[kn]
-            name = {"orb_describe": "orb_describe", "desc_or": "desc_or", "finalize": "match_finalize"}.get(name, name)
+            name = {"orb_describe": "orb_describe", "desc_or": "desc_or", "finalize": "match_finalize", "match256": "match"}.get(name, name)
             b = to_bytes(r[col["dram__bytes_read.sum"]], units[col["dram__bytes_read.sum"]]) + \
                 to_bytes(r[col["dram__bytes_write.sum"]], units[col["dram__bytes_write.sum"]])
             dram[name] = dram.get(name, 0.0) + b
