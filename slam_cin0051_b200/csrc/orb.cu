@@ -180,15 +180,15 @@ __global__ void __launch_bounds__(PT_THREADS) pyr_down_kernel(SeqView s, OrbView
 //   0  stage the tile (+16 px / 4 row halo) in shared memory with aligned 128-bit loads; clear the score grid
 //   1  SWAR pre-test, 4 pixels per thread on packed bytes: a 9-arc contains two ring pixels 90 degrees apart
 //      (one of N/S and one of E/W) that differ from the centre by more than t -> survivors to list 1
-//   2  segment test on list 1 (16-bit brighter / darker ring masks, run of 9 by shift-AND) -> corners to list 2
-//   3  cornerScore for list 2 -> dense score grid (1 px ring around the tile for the NMS)
+//   2  segment test + cornerScore on list 1 in one pass over the ring (fast9_test_and_score) -> dense score grid
+//      (1 px ring around the tile for the NMS), corners to list 2
 //   4  3x3 strict NMS + edgeThreshold border filter for the list-2 entries inside the tile -> bit mask
 constexpr int FTW = 128, FTH = 48, FHX = 16, FSW = FTW + 2 * FHX, FSH = FTH + 8;  // pixel tile with halo
 constexpr int SCW = FTW + 8, SCH = FTH + 2;  // score grid: x0-4 .. x0+131 (4-px groups), y0-1 .. y0+32
 
 // cornerScore of cv::FAST (9/16) = max over the 16 arcs of 9 ring pixels of min |v - p| (one sign), minus 1.
 // With d = v - p:  min over an arc of d = v - max(p),  min of -d = min(p) - v, so the score needs the sliding-window
-// (length 9, circular) min or max of the raw ring pixels: doubling steps 2, 4, 8, then +1 (fast9_ring_score_kind below).
+// (length 9, circular) min or max of the raw ring pixels: windows of 3, then of 9 (fast9_test_and_score below).
 // The subtraction from v is applied AFTER the min/max network on purpose: nvcc 12.9 folds max(a, -b) chains into
 // VIMNMX3 for sm_100a and loses the negation ("toolchain finding").
 
@@ -203,34 +203,36 @@ __device__ __forceinline__ void fast9_load_ring(const uint8_t* t, int stride, in
 // Segment test AND corner score in one pass over the ring: with m9 = max over the 16 arcs of (min of the arc's 9 pixels) and
 // M9 = min over the arcs of (max of the arc's 9 pixels), the pixel is a bright corner iff m9 > v + thr, a dark one iff
 // M9 < v - thr (both cannot hold: two disjoint 9-arcs do not fit in 16), and cornerScore = m9 - v - 1 resp. v - M9 - 1.
-// Returns the score, or -1 when the pixel is no corner.  2 x (16 + 16 + 8) three-input min / max operations.
+// Both polarities share ONE network: every ring pixel is widened to the halfword pair (p, 255 - p) by a single IMAD, so the
+// sliding minimum of the low halves is min(p) and that of the high halves is 255 - max(p); 16 + 16 + 8 VIMNMX3.U16x2.
+// Returns the score, or -1 when the pixel is no corner.
 __device__ __forceinline__ int fast9_test_and_score(int v, const int (&p)[16], int thr) {
-    int lo3[16], hi3[16];
+    unsigned q[16], lo3[16];
 #pragma unroll
-    for (int i = 0; i < 16; i++) {
-        lo3[i] = __vimin3_s32(p[i], p[(i + 1) & 15], p[(i + 2) & 15]);
-        hi3[i] = __vimax3_s32(p[i], p[(i + 1) & 15], p[(i + 2) & 15]);
-    }
-    int m9 = 0, M9 = 255;
+    for (int i = 0; i < 16; i++) q[i] = (unsigned)p[i] * 0xFFFF0001u + 0x00FF0000u;  // p | (255 - p) << 16
+#pragma unroll
+    for (int i = 0; i < 16; i++) lo3[i] = __vimin3_u16x2(q[i], q[(i + 1) & 15], q[(i + 2) & 15]);
+    unsigned m = 0;
 #pragma unroll
     for (int i = 0; i < 16; i += 2) {
-        const int a0 = __vimin3_s32(lo3[i], lo3[(i + 3) & 15], lo3[(i + 6) & 15]);
-        const int a1 = __vimin3_s32(lo3[i + 1], lo3[(i + 4) & 15], lo3[(i + 7) & 15]);
-        m9 = __vimax3_s32(m9, a0, a1);
-        const int b0 = __vimax3_s32(hi3[i], hi3[(i + 3) & 15], hi3[(i + 6) & 15]);
-        const int b1 = __vimax3_s32(hi3[i + 1], hi3[(i + 4) & 15], hi3[(i + 7) & 15]);
-        M9 = __vimin3_s32(M9, b0, b1);
+        const unsigned a0 = __vimin3_u16x2(lo3[i], lo3[(i + 3) & 15], lo3[(i + 6) & 15]);
+        const unsigned a1 = __vimin3_u16x2(lo3[i + 1], lo3[(i + 4) & 15], lo3[(i + 7) & 15]);
+        m = __vimax3_u16x2(m, a0, a1);
     }
-    const int bright = m9 - v, dark = v - M9;  // > thr <=> corner of that polarity
-    const int best = max(bright, dark);
+    const int bright = (int)(m & 0xffffu) - v;      // m9 - v
+    const int dark = (int)(m >> 16) - (255 - v);    // (255 - M9) - (255 - v) = v - M9
+    const int best = max(bright, dark);             // > thr <=> corner of that polarity
     return best > thr ? best - 1 : -1;
 }
 
-// bytes of |a - b| that exceed thr -> bit 7 of the byte (SWAR; thr in [0, 255])
+// bytes of |a - b| that exceed thr -> bit 7 of the byte (SWAR; thr in [0, 255]).  thr < 128: bit 7 of d + (127 - thr), or of d
+// itself.  The addition runs over the whole word: a byte with d >= 129 + thr carries into its neighbour, which can only turn
+// that neighbour's "d == thr" into a hit (a wrap of the neighbour needs d >= 128, which the OR catches).  The pre-test may
+// pass extra pixels, never drop one: the exact test follows.  thr >= 128 (never the default): exact form, bit 7 of both.
 __device__ __forceinline__ unsigned swar_absdiff_gt(unsigned a, unsigned b, unsigned k7, bool big) {
     const unsigned d = __vabsdiffu4(a, b);
-    const unsigned s = (d & 0x7f7f7f7fu) + k7;  // no carry between bytes: both addends are <= 127
-    return big ? (s & d) : (s | d);             // thr >= 128: needs bit 7 of d as well; else bit 7 of d suffices
+    if (!big) return (d + k7) | d;
+    return ((d & 0x7f7f7f7fu) + k7) & d;
 }
 
 // ---- TMA helpers (sm_90+ PTX): one thread arms an mbarrier with the box size and issues cp.async.bulk.tensor; the
