@@ -19,6 +19,7 @@
 #include <cstdlib>
 
 #include "orb.cuh"
+#include <type_traits>
 
 namespace slamcu {
 namespace {
@@ -229,9 +230,15 @@ __device__ __forceinline__ int fast9_test_and_score(int v, const int (&p)[16], i
 // itself.  The addition runs over the whole word: a byte with d >= 129 + thr carries into its neighbour, which can only turn
 // that neighbour's "d == thr" into a hit (a wrap of the neighbour needs d >= 128, which the OR catches).  The pre-test may
 // pass extra pixels, never drop one: the exact test follows.  thr >= 128 (never the default): exact form, bit 7 of both.
-__device__ __forceinline__ unsigned swar_absdiff_gt(unsigned a, unsigned b, unsigned k7, bool big) {
+// `one` is 1 in a register the compiler cannot see through: d * one + k7 stays an IMAD (FMA pipe) instead of an ALU-pipe add,
+// and the ALU pipe is this kernel's limiter.
+__device__ __forceinline__ unsigned swar_absdiff_gt(unsigned a, unsigned b, unsigned k7, bool big, unsigned one) {
     const unsigned d = __vabsdiffu4(a, b);
-    if (!big) return (d + k7) | d;
+    unsigned sum;
+    if (!big) {
+        asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(sum) : "r"(d), "r"(one), "r"(k7));
+        return sum | d;
+    }
     return ((d & 0x7f7f7f7fu) + k7) & d;
 }
 
@@ -308,11 +315,12 @@ __global__ void __launch_bounds__(256) fast9_mask_kernel(SeqView s, OrbView o, i
     __syncthreads();
     // ---- phase 1: a warp per score-grid row, a lane per 4-pixel group of the tile's 128 columns; the two ring
     // columns (x0-1, x0+128) skip the pre-test and go straight to list 1
-    {
-        const bool big = thr >= 128;
+    // valid score-grid columns: the FAST domain [3, cols-3) intersected with [x0-1, x0+129)
+    const int lo = max(3, x0 - 1), hi = min(L.cols - 3, x0 + FTW + 1);
+    auto pretest = [&](auto bigc) {  // the threshold class is block-uniform: two loops, not predicated twins in one
+        constexpr bool big = decltype(bigc)::value;
         const unsigned k7 = (unsigned)(big ? 255 - thr : 127 - thr) * 0x01010101u;
-        // valid score-grid columns: the FAST domain [3, cols-3) intersected with [x0-1, x0+129)
-        const int lo = max(3, x0 - 1), hi = min(L.cols - 3, x0 + FTW + 1);
+        const unsigned one = (unsigned)min(o.nlevels, 1);
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
         for (int ry = warp; ry < SCH; ry += 8) {
             const int gy = y0 - 1 + ry;
@@ -322,8 +330,8 @@ __global__ void __launch_bounds__(256) fast9_mask_kernel(SeqView s, OrbView o, i
             const unsigned wn = row[-3 * (FSW / 4)], ws = row[3 * (FSW / 4)];
             const unsigned we = __funnelshift_r(w0, wp, 24);  // pixels x+3 .. x+6
             const unsigned ww = __funnelshift_r(wm, w0, 8);   // pixels x-3 .. x
-            unsigned m = (swar_absdiff_gt(wn, w0, k7, big) | swar_absdiff_gt(ws, w0, k7, big)) &
-                         (swar_absdiff_gt(we, w0, k7, big) | swar_absdiff_gt(ww, w0, k7, big)) & 0x80808080u;
+            unsigned m = (swar_absdiff_gt(wn, w0, k7, big, one) | swar_absdiff_gt(ws, w0, k7, big, one)) &
+                         (swar_absdiff_gt(we, w0, k7, big, one) | swar_absdiff_gt(ww, w0, k7, big, one)) & 0x80808080u;
             const int gxb = x0 + 4 * lane;
             if (m != 0 && (gxb < lo || gxb + 4 > hi)) {
 #pragma unroll
@@ -341,6 +349,10 @@ __global__ void __launch_bounds__(256) fast9_mask_kernel(SeqView s, OrbView o, i
                     }
             }
         }
+    };
+    {
+        if (thr >= 128) pretest(std::true_type{});
+        else pretest(std::false_type{});
         if (threadIdx.x < 2 * SCH) {  // the two ring columns of every score-grid row
             const int ry = threadIdx.x >> 1, gy = y0 - 1 + ry;
             const int cx = (threadIdx.x & 1) ? FTW + 4 : 3;  // score-grid columns of x0+128 and x0-1
