@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libslamcu.so")
-SOURCES = ["api.cu", "fast_ref.cu", "sortnms.cu", "describe_ref.cu", "match.cu", "prep.cu", "ransac.cu", "microbench.cu", "orb.cu", "essential.cu", "pack.cu"]
+SOURCES = ["api.cu", "fast_ref.cu", "sortnms.cu", "describe_ref.cu", "match.cu", "match_tc.cu", "prep.cu", "ransac.cu", "microbench.cu", "orb.cu", "essential.cu", "pack.cu"]
 # Exactness-critical: -fmad=false and NO --use_fast_math (every bit-exactness guarantee depends on them; CMakeLists.txt
 # passes the same pair, tests/test_cabi_and_host.py checks both recipes).
 EXACT_FLAGS = ["-fmad=false"]

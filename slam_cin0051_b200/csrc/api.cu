@@ -16,6 +16,7 @@
 
 #include "common.cuh"
 #include "orb.cuh"
+#include "match_tc.cuh"
 
 using namespace slamcu;
 
@@ -236,6 +237,12 @@ struct slamcu_sequence {
     float orb_scale = 0.f;
     std::vector<void*> orb_owned;
     OrbTmaps tmaps{};  // TMA descriptors of the pyramid levels (host copies; passed to the kernels as __grid_constant__)
+    // tensor-core matcher operands (lazy): every frame's descriptors widened to one byte per bit + key constants
+    uint8_t* tc_x8 = nullptr;   // [F][tc_rows][256]
+    uint32_t* tc_ck = nullptr;  // [F][tc_rows]
+    int tc_rows = 0;            // cap_kp rounded up to 128
+    int tc_state = 0;           // 0 = not tried, 1 = ready, -1 = unavailable (integer-pipe kernels)
+    MatchTc tc{};
 };
 
 struct slamcu_detector {
@@ -264,6 +271,11 @@ struct slamcu_matcher {
     int* counts = nullptr;  // nq, nt, n_match, status
     int cap1 = 0, cap2 = 0, cap_words = 0;
     int forced_slices = 0;  // slamcu_matcher_set_train_slices
+    // tensor-core operands of the single-call path (lazy)
+    uint8_t *x1 = nullptr, *x2 = nullptr;
+    uint32_t *ck1 = nullptr, *ck2 = nullptr;
+    int tc_rows1 = 0, tc_rows2 = 0;
+    MatchTc tc{};
 };
 
 extern "C" {
@@ -313,6 +325,7 @@ int slamcu_create(int device_id, slamcu_context** out) {
     init_orb_attributes(ctx->smem_optin);
     init_essential_attributes();
     init_match_attributes();
+    init_match_tc_attributes();
     *out = ctx;
     return SLAMCU_OK;
 }
@@ -504,6 +517,8 @@ void slamcu_sequence_destroy(slamcu_sequence* s) {
     if (s->h_counts) cudaFreeHost(s->h_counts);
     if (s->h_status) cudaFreeHost(s->h_status);
     if (s->d_dense) cudaFree(s->d_dense);
+    if (s->tc_x8) cudaFree(s->tc_x8);
+    if (s->tc_ck) cudaFree(s->tc_ck);
     delete s;
 }
 
@@ -833,6 +848,52 @@ int slamcu_sequence_extract(slamcu_sequence* s, slamcu_detector* det, int first,
     return seq_compute(s, det, first, n);
 }
 
+// ---- tensor-core matcher plumbing --------------------------------------------------------------------------------------
+// SLAMCU_MATCH_TC=0 keeps the integer-pipe kernels (A/B measurements); the tensor-core path also needs the TMA encoder.
+static bool match_tc_enabled() {
+    static const bool on = [] { const char* e = getenv("SLAMCU_MATCH_TC"); return !(e && e[0] == '0'); }();
+    return on;
+}
+// rank-2 u8 tensor {256 bytes of K, rows}, box {128, 128}, 128-byte swizzle (the UMMA K-major operand layout), zero fill
+static bool encode_tc_map(CUtensorMap* map, void* base, size_t rows) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    bool ok = false;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && fn &&
+        qres == cudaDriverEntryPointSuccess) {
+        auto encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(fn);
+        const cuuint64_t dims[2] = {(cuuint64_t)kTcRowBytes, (cuuint64_t)rows};
+        const cuuint64_t strides[1] = {(cuuint64_t)kTcRowBytes};
+        const cuuint32_t box[2] = {128, 128};
+        const cuuint32_t estr[2] = {1, 1};
+        ok = encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    }
+    cudaGetLastError();
+    return ok;
+}
+static bool seq_ensure_tc(slamcu_sequence* s) {
+    if (s->tc_state != 0) return s->tc_state > 0;
+    s->tc_state = -1;
+    if (!match_tc_enabled() || s->v.desc_words != 8) return false;
+    const int rows = (s->v.cap_kp + kTcRowAlign - 1) / kTcRowAlign * kTcRowAlign;
+    const size_t total = (size_t)s->max_frames * rows;
+    if (cudaMalloc(reinterpret_cast<void**>(&s->tc_x8), total * kTcRowBytes) != cudaSuccess ||
+        cudaMalloc(reinterpret_cast<void**>(&s->tc_ck), total * sizeof(uint32_t)) != cudaSuccess ||
+        !encode_tc_map(&s->tc.map_q, s->tc_x8, total)) {
+        cudaGetLastError();  // out of memory or no encoder: the integer-pipe kernels take over
+        if (s->tc_x8) cudaFree(s->tc_x8);
+        if (s->tc_ck) cudaFree(s->tc_ck);
+        s->tc_x8 = nullptr;
+        s->tc_ck = nullptr;
+        return false;
+    }
+    s->tc.map_t = s->tc.map_q;
+    s->tc_rows = rows;
+    s->tc_state = 1;
+    return true;
+}
+
 int slamcu_sequence_match(slamcu_sequence* s, slamcu_matcher* m, int first, int n_pairs, int with_kp) {
     if (!s || !m || s->ctx != m->ctx) return bad_args((s ? s->ctx : nullptr), __func__);
     slamcu_context* ctx = s->ctx;
@@ -866,8 +927,16 @@ int slamcu_sequence_match(slamcu_sequence* s, slamcu_matcher* m, int first, int 
     j.max_q = v.cap_kp;
     j.max_t = v.cap_kp;
     j.cap_out = v.cap_kp;
+    const MatchTc* tc = nullptr;
+    if (!with_kp && seq_ensure_tc(s)) {
+        // every frame of the range once (a frame is the train set of one pair and the query set of the next)
+        ctx->launches += launch_expand_bits(j.dq, dstride, j.nq, 1, n_pairs + 1, s->tc_rows, s->tc_x8 + (size_t)first * s->tc_rows * kTcRowBytes,
+                                            s->tc_ck + (size_t)first * s->tc_rows, ctx->stream);
+        s->tc.view = MatchTcView{s->tc_ck, s->tc_ck, first * s->tc_rows, (first + 1) * s->tc_rows, s->tc_rows, s->tc_rows};
+        tc = &s->tc;
+    }
     ctx->launches += launch_match(j, n_pairs, m->p, true, with_kp ? 1 : 0, s->sort_keys + (size_t)first * v.cap_kp,
-                                  ctx->stream);
+                                  ctx->stream, 1, 0, 0, tc);
     return check_launch(ctx, "match kernels");
 }
 
@@ -1586,9 +1655,12 @@ int slamcu_matcher_set_train_slices(slamcu_matcher* m, int n_slices) {
 }
 
 static void matcher_free(slamcu_matcher* m) {
-    void* ptrs[] = {m->d1, m->d2, m->k1, m->k2, m->cand, m->matches, m->keys, m->ors, m->counts};
+    void* ptrs[] = {m->d1, m->d2, m->k1, m->k2, m->cand, m->matches, m->keys, m->ors, m->counts, m->x1, m->x2, m->ck1, m->ck2};
     for (void* p : ptrs)
         if (p) cudaFree(p);
+    m->x1 = m->x2 = nullptr;
+    m->ck1 = m->ck2 = nullptr;
+    m->tc_rows1 = m->tc_rows2 = 0;
     m->d1 = m->d2 = nullptr;
     m->k1 = m->k2 = nullptr;
     m->cand = nullptr;
@@ -1681,13 +1753,46 @@ static int match_common(slamcu_matcher* m, const uint8_t* d1, int n1, int width1
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
     // blocks hold 256 queries (128 for small problems, launch_match decides): aim at ~8 blocks per SM, slices of at least 128
-    const int q_blocks = (n1 + 255) / 256;
-    int n_seg = std::min(std::min((8 * sms + q_blocks - 1) / q_blocks, (n2 + 127) / 128), kMaxMatchSlices);
+    const MatchTc* tc = nullptr;
+    if (!with_kp && words == 8 && match_tc_enabled()) {
+        const int r1 = (n1 + kTcRowAlign - 1) / kTcRowAlign * kTcRowAlign, r2 = (n2 + kTcRowAlign - 1) / kTcRowAlign * kTcRowAlign;
+        bool ok = true;
+        if (r1 > m->tc_rows1 || r2 > m->tc_rows2) {
+            CU(ctx, cudaStreamSynchronize(ctx->stream));
+            const int c1 = std::max(r1, m->tc_rows1), c2 = std::max(r2, m->tc_rows2);
+            void* old[] = {m->x1, m->x2, m->ck1, m->ck2};
+            for (void* q : old)
+                if (q) cudaFree(q);
+            m->x1 = m->x2 = nullptr;
+            m->ck1 = m->ck2 = nullptr;
+            m->tc_rows1 = m->tc_rows2 = 0;
+            ok = cudaMalloc(reinterpret_cast<void**>(&m->x1), (size_t)c1 * kTcRowBytes) == cudaSuccess &&
+                 cudaMalloc(reinterpret_cast<void**>(&m->x2), (size_t)c2 * kTcRowBytes) == cudaSuccess &&
+                 cudaMalloc(reinterpret_cast<void**>(&m->ck1), (size_t)c1 * sizeof(uint32_t)) == cudaSuccess &&
+                 cudaMalloc(reinterpret_cast<void**>(&m->ck2), (size_t)c2 * sizeof(uint32_t)) == cudaSuccess &&
+                 encode_tc_map(&m->tc.map_q, m->x1, (size_t)c1) && encode_tc_map(&m->tc.map_t, m->x2, (size_t)c2);
+            if (ok) {
+                m->tc_rows1 = c1;
+                m->tc_rows2 = c2;
+            } else {
+                cudaGetLastError();
+            }
+        }
+        if (ok) {
+            ctx->launches += launch_expand_bits(m->d1, 0, m->counts + 0, 1, 1, m->tc_rows1, m->x1, m->ck1, ctx->stream);
+            ctx->launches += launch_expand_bits(m->d2, 0, m->counts + 1, 1, 1, m->tc_rows2, m->x2, m->ck2, ctx->stream);
+            m->tc.view = MatchTcView{m->ck1, m->ck2, 0, 0, 0, 0};
+            tc = &m->tc;
+        }
+    }
+    // integer-pipe blocks hold 256 queries, tensor-core CTAs 128
+    const int q_blocks = tc ? (n1 + 127) / 128 : (n1 + 255) / 256;
+    int n_seg = std::min(std::min(((tc ? 4 : 8) * sms + q_blocks - 1) / q_blocks, (n2 + 127) / 128), kMaxMatchSlices);
     if (m->forced_slices > 0) n_seg = std::min(std::min(m->forced_slices, (n2 + 127) / 128), kMaxMatchSlices);
     n_seg = std::max(n_seg, 1);
     const int seg_len = ((n2 + n_seg - 1) / n_seg + 127) / 128 * 128;
     n_seg = (n2 + seg_len - 1) / seg_len;
-    ctx->launches += launch_match(j, 1, m->p, emit, with_kp ? 1 : 0, m->keys, ctx->stream, n_seg, seg_len, (size_t)m->cap1);
+    ctx->launches += launch_match(j, 1, m->p, emit, with_kp ? 1 : 0, m->keys, ctx->stream, n_seg, seg_len, (size_t)m->cap1, tc);
     return check_launch(ctx, "match kernels");
 }
 

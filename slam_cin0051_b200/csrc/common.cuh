@@ -78,8 +78,10 @@ struct MatchJob {
 // n_seg > 1 splits the train set into n_seg slices of seg_len descriptors (extra grid dimension, for single small
 // problems); job.cand must then hold n_seg blocks of seg_stride entries, slice 0 doubling as the merged result
 void init_match_attributes();
+struct MatchTc;  // match_tc.cuh: widened operands + tensor maps; non-null -> the 256-bit penalty-free search runs on the tensor cores
 int launch_match(const MatchJob& job, int n_pairs, const MatchParams& p, bool emit_matches, int with_kp,
-                 unsigned long long* sort_keys, cudaStream_t st, int n_seg = 1, int seg_len = 0, size_t seg_stride = 0);
+                 unsigned long long* sort_keys, cudaStream_t st, int n_seg = 1, int seg_len = 0, size_t seg_stride = 0,
+                 const MatchTc* tc = nullptr);
 
 int launch_prepare(const uint8_t* src, int channels, int src_stride, size_t src_frame_bytes, const int* map, uint8_t* dst, int pitch,
                    size_t dst_frame_bytes, int rows, int cols, int n, cudaStream_t st);

@@ -13,6 +13,7 @@
 
 #include "common.cuh"
 #include "exact.cuh"
+#include "match_tc.cuh"
 
 namespace slamcu {
 
@@ -445,10 +446,12 @@ void init_match_attributes() {
 }
 
 int launch_match(const MatchJob& job, int n_pairs, const MatchParams& p, bool emit_matches, int with_kp,
-                 unsigned long long* sort_keys, cudaStream_t st, int n_seg, int seg_len, size_t seg_stride) {
+                 unsigned long long* sort_keys, cudaStream_t st, int n_seg, int seg_len, size_t seg_stride, const MatchTc* tc) {
     if (n_pairs <= 0) return 0;
     if (n_seg < 1) n_seg = 1;
-    if (job.desc_words == 8 && !with_kp && job.max_t <= (1 << kKeyShift)) {
+    if (tc && job.desc_words == 8 && !with_kp && job.max_t <= (1 << kKeyShift) && (n_seg == 1 || seg_len % 128 == 0)) {
+        launch_match_tc(job, *tc, n_pairs, st, n_seg, seg_len, seg_stride);
+    } else if (job.desc_words == 8 && !with_kp && job.max_t <= (1 << kKeyShift)) {
         // 256-bit descriptors, no image-distance penalty: whole train slice in shared memory, two queries per thread
         const int span = n_seg > 1 ? seg_len : job.max_t;
         static const int tile_env = [] { const char* e = getenv("SLAMCU_MATCH_TILE"); return e ? atoi(e) : 0; }();  // tuning knob (descriptors per smem tile)
