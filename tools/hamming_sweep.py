@@ -42,8 +42,11 @@ def main():
         order = np.lexsort((np.broadcast_to(np.arange(n), dist.shape), dist), axis=1)[:, :2]
         ok = bool(np.array_equal(got["trainIdx0"][qs], order[:, 0]) and np.array_equal(got["trainIdx1"][qs], order[:, 1]) and
                   np.array_equal(got["distance0"][qs], np.take_along_axis(dist, order[:, :1], 1)[:, 0]))
-        row = {"n": n, "kernel_ms": k_ms, "kernel_gcmp_s": n * n / k_ms / 1e6, "host_call_ms": wall * 1e3,
-               "host_call_gcmp_s": n * n / wall / 1e9, "frac_of_4popc_peak": n * n / k_ms / 1e6 / (gpopc / 4.0), "spot_check": ok}
+        gcmp = n * n / k_ms / 1e6
+        row = {"n": n, "kernel_ms": k_ms, "kernel_gcmp_s": gcmp, "host_call_ms": wall * 1e3,
+               "host_call_gcmp_s": n * n / wall / 1e9, "frac_of_4popc_peak": gcmp / (gpopc / 4.0), "spot_check": ok,
+               "on_tensor_cores": "match_expand" in prof, "expand_ms": (prof["match_expand"][0] / reps) if "match_expand" in prof else None,
+               "u8_tops": gcmp * 512 / 1e3}
         out["rows"].append(row)
         if not quick:
             print(row, flush=True)
