@@ -450,14 +450,36 @@ def run_ours(args, w, rank, world, local_rank):
     outs = [out_set(), out_set()]
     seqs = [seq, seq2]
 
+    submit_s = [0.0]
+    padded = None
+    if os.environ.get("BENCH_E2E_PADDED") == "1":
+        padded = [(torch.empty((NF, max_kp, 5), dtype=torch.float32, pin_memory=True), torch.empty((NF, max_kp, det.descriptor_bytes), dtype=torch.uint8, pin_memory=True),
+                   torch.empty((NF, max_kp, 3), dtype=torch.int32, pin_memory=True)) for _ in range(2)]
+    noout = os.environ.get("BENCH_E2E_NOOUT") == "1"  # experiment knob: no result download (not a valid e2e number)
+
     def submit_e2e(i):
+        t_sub = time.perf_counter()
         k, d, m, c = outs[i % 2]
+        if os.environ.get("BENCH_E2E_PADDED") == "1":  # experiment knob: padded rows through the copy engine
+            kk, dd, mm = padded[i % 2]
+            seqs[i % 2].process_ptrs(det, mat, host_frames.data_ptr(), NF, chunk=args.chunk, with_keypoints=with_kp, kps_ptr=kk.data_ptr(),
+                                     desc_ptr=dd.data_ptr(), matches_ptr=mm.data_ptr(), counts_ptr=c.data_ptr())
+            gather_counts(seqs[i % 2])
+            submit_s[0] += time.perf_counter() - t_sub
+            return
+        if noout:
+            seqs[i % 2].process_dense_ptrs(det, mat, host_frames.data_ptr(), NF, chunk=args.chunk, with_keypoints=with_kp, counts_ptr=c.data_ptr(),
+                                           kp_capacity=kp_cap, match_capacity=m_cap)
+            gather_counts(seqs[i % 2])
+            submit_s[0] += time.perf_counter() - t_sub
+            return
         seqs[i % 2].process_dense_ptrs(det, mat, host_frames.data_ptr(), NF, chunk=args.chunk, with_keypoints=with_kp,
                                        kps_ptr=k.data_ptr(), desc_ptr=d.data_ptr(), matches_ptr=m.data_ptr(), counts_ptr=c.data_ptr(),
                                        kp_capacity=kp_cap, match_capacity=m_cap)
         if k4:  # E, inlier masks and counts stay on the device (read per pair with essential_result)
             seqs[i % 2].essential(k4, 0, NP)
         gather_counts(seqs[i % 2])
+        submit_s[0] += time.perf_counter() - t_sub
 
     def collect_e2e(i):
         seqs[i % 2].wait()  # the step's results are now in host memory (raises if a device list overflowed); read them
@@ -508,6 +530,7 @@ def run_ours(args, w, rank, world, local_rank):
     barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
+    submit_s[0] = 0.0
     tot = (0, 0, 0, 0)
     for i in range(args.steps):
         submit_e2e(i)
@@ -604,6 +627,7 @@ def run_ours(args, w, rank, world, local_rank):
                       "numa": numa},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / args.steps, "keypoints_last_step": tot[0], "matches_last_step": tot[1],
+                    "host_submit_ms_per_step": submit_s[0] * 1e3 / args.steps,
                     "pipeline_chunk_frames": args.chunk, "double_buffered_sequences": 2, "outputs": "dense (device compaction into pinned host memory)",
                     "h2d_gbs_per_rank": h2d / step_s / 1e9, "d2h_gbs_per_rank": d2h / step_s / 1e9,
                     "host_link_gbs_all_ranks": world * (h2d + d2h) / step_s / 1e9},

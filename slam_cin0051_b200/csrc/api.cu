@@ -5,6 +5,7 @@
 #include <climits>
 #include <cstring>
 #include <cmath>
+#include <algorithm>
 #include <cstdlib>
 #include <new>
 #include <random>
@@ -87,6 +88,8 @@ struct slamcu_context {
     size_t scratch_bytes = 0;
     // copy engines of the pipelined sequence path: H2D and D2H run on their own streams
     cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaStream_t s_dl = nullptr;  // exact-size downloads of dense outputs (issued by the host once the totals are known)
+    std::vector<struct slamcu_sequence*> pending_dl;  // sequences whose dense outputs are still on the device
     std::vector<cudaEvent_t> events;
     // auxiliary compute stream: kernels that are independent inside one extract call overlap with the main chain
     cudaStream_t s_aux = nullptr;
@@ -215,6 +218,14 @@ struct slamcu_sequence {
     int* h_counts = nullptr;                  // pinned [F][4]
     int* h_status = nullptr;                  // pinned [F + 1]: status words of the latest slamcu_sequence_process call (+ dense overflow bits)
     int* d_dense = nullptr;                   // [2][F + 1] running offsets of the dense outputs (keypoints, matches) + 1 overflow word
+    // dense outputs are compacted on the device and cross the link through the copy engine with their exact sizes, once the
+    // host has the totals (slamcu_sequence_wait / slamcu_synchronize): SM-written stores to mapped host memory slowed the
+    // concurrent compute kernels down by ~10 %
+    void *dd_kps = nullptr, *dd_desc = nullptr, *dd_matches = nullptr;
+    long long dd_kp_cap = 0, dd_m_cap = 0;
+    int* h_tot = nullptr;                     // pinned [2]: total keypoints, total matches of the latest dense call
+    void *dl_kps = nullptr, *dl_desc = nullptr, *dl_matches = nullptr;  // the caller's host buffers of that call
+    bool dl_active = false;
     int h_status_n = 0;                       // ... and how many frames it covered
     uint8_t* stage = nullptr;                 // [F][rows][cols] dense landing zone of linear H2D copies (lazy)
     uint8_t* prep_stage = nullptr;            // landing zone of slamcu_sequence_prepare (gray or BGR host frames; lazy)
@@ -358,8 +369,13 @@ int slamcu_set_stream(slamcu_context* ctx, void* cuda_stream) {
 }
 void* slamcu_get_stream(slamcu_context* ctx) { return ctx ? ctx->stream : nullptr; }
 
+static int seq_dense_flush(slamcu_sequence* s);
 int slamcu_synchronize(slamcu_context* ctx) {
     if (!ctx) return bad_args(ctx, __func__);
+    while (!ctx->pending_dl.empty()) {  // dense outputs still on the device: download them now
+        const int rc = seq_dense_flush(ctx->pending_dl.back());
+        if (rc != SLAMCU_OK) return rc;
+    }
     CU(ctx, cudaStreamSynchronize(ctx->stream));
     if (ctx->lane1) CU(ctx, cudaStreamSynchronize(ctx->lane1));
     if (ctx->s_in) CU(ctx, cudaStreamSynchronize(ctx->s_in));
@@ -517,6 +533,14 @@ void slamcu_sequence_destroy(slamcu_sequence* s) {
     if (s->h_counts) cudaFreeHost(s->h_counts);
     if (s->h_status) cudaFreeHost(s->h_status);
     if (s->d_dense) cudaFree(s->d_dense);
+    if (s->dd_kps) cudaFree(s->dd_kps);
+    if (s->dd_desc) cudaFree(s->dd_desc);
+    if (s->dd_matches) cudaFree(s->dd_matches);
+    if (s->h_tot) cudaFreeHost(s->h_tot);
+    {
+        auto& pd = s->ctx->pending_dl;
+        pd.erase(std::remove(pd.begin(), pd.end(), s), pd.end());
+    }
     if (s->tc_x8) cudaFree(s->tc_x8);
     if (s->tc_ck) cudaFree(s->tc_ck);
     delete s;
@@ -1129,11 +1153,35 @@ int slamcu_sequence_download(slamcu_sequence* s, int first, int n, slamcu_keypoi
     return SLAMCU_OK;
 }
 
+// The deferred half of slamcu_sequence_process_dense: the rows are dense in device memory; with the totals on the host the three
+// arrays cross the link as exact-size copy-engine transfers.
+static int seq_dense_flush(slamcu_sequence* s) {
+    if (!s->dl_active) return SLAMCU_OK;
+    slamcu_context* ctx = s->ctx;
+    s->dl_active = false;
+    {
+        auto& pd = ctx->pending_dl;
+        pd.erase(std::remove(pd.begin(), pd.end(), s), pd.end());
+    }
+    CU(ctx, cudaEventSynchronize(s->ev_out_done));  // compaction, totals and the overflow word are in
+    if (s->h_status && s->h_status[s->max_frames] != 0) return SLAMCU_OK;  // overflow: slamcu_sequence_wait reports it
+    const size_t n_kp = (size_t)std::max(s->h_tot[0], 0), n_m = (size_t)std::max(s->h_tot[1], 0);
+    if (s->dl_kps && n_kp) CU(ctx, cudaMemcpyAsync(s->dl_kps, s->dd_kps, n_kp * sizeof(slamcu_keypoint), cudaMemcpyDeviceToHost, ctx->s_dl));
+    if (s->dl_desc && n_kp) CU(ctx, cudaMemcpyAsync(s->dl_desc, s->dd_desc, n_kp * s->v.desc_words * 4, cudaMemcpyDeviceToHost, ctx->s_dl));
+    if (s->dl_matches && n_m) CU(ctx, cudaMemcpyAsync(s->dl_matches, s->dd_matches, n_m * sizeof(slamcu_dmatch), cudaMemcpyDeviceToHost, ctx->s_dl));
+    CU(ctx, cudaStreamSynchronize(ctx->s_dl));
+    return SLAMCU_OK;
+}
+
 int slamcu_sequence_wait(slamcu_sequence* s) {
     if (!s) return bad_args((s ? s->ctx : nullptr), __func__);
     slamcu_context* ctx = s->ctx;
     CU(ctx, cudaEventSynchronize(s->ev_compute_done));
     CU(ctx, cudaEventSynchronize(s->ev_out_done));
+    {
+        const int rc = seq_dense_flush(s);
+        if (rc != SLAMCU_OK) return rc;
+    }
     // a frame that overflowed one of its device lists holds truncated results: say so instead of returning them as OK
     for (int f = 0; f < s->h_status_n; f++)
         if (s->h_status[f] != 0) {
@@ -1154,6 +1202,7 @@ int slamcu_sequence_wait(slamcu_sequence* s) {
 static int ctx_pipeline_resources(slamcu_context* ctx, size_t n_events) {
     if (!ctx->s_in) CU(ctx, cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
     if (!ctx->s_out) CU(ctx, cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
+    if (!ctx->s_dl) CU(ctx, cudaStreamCreateWithFlags(&ctx->s_dl, cudaStreamNonBlocking));
     while (ctx->events.size() < n_events) {
         cudaEvent_t e;
         CU(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -1188,17 +1237,39 @@ static int seq_process(slamcu_sequence* s, slamcu_detector* det, slamcu_matcher*
             return fail(ctx, SLAMCU_CUDA_ERROR, "cudaMallocHost failed");
         s->h_status[s->max_frames] = 0;
     }
-    // dense outputs: device-visible addresses of the caller's page-locked buffers, running offsets on the device
+    // dense outputs: compacted into device buffers of the caller's capacities, running offsets on the device
     void *dk = nullptr, *dd = nullptr, *dm = nullptr;
     int *kp_off = nullptr, *m_off = nullptr, *d_over = nullptr;
     if (dense) {
         if (kp_capacity < 0 || match_capacity < 0 || kp_capacity > INT_MAX || match_capacity > INT_MAX)
             return fail(ctx, SLAMCU_INVALID_ARGUMENT, "dense capacities out of range");
-        if ((kps && cudaHostGetDevicePointer(&dk, kps, 0) != cudaSuccess) || (desc && cudaHostGetDevicePointer(&dd, desc, 0) != cudaSuccess) ||
-            (matches && cudaHostGetDevicePointer(&dm, matches, 0) != cudaSuccess)) {
+        void* probe = nullptr;  // asynchronous exact-size downloads need page-locked destinations
+        if ((kps && cudaHostGetDevicePointer(&probe, kps, 0) != cudaSuccess) || (desc && cudaHostGetDevicePointer(&probe, desc, 0) != cudaSuccess) ||
+            (matches && cudaHostGetDevicePointer(&probe, matches, 0) != cudaSuccess)) {
             cudaGetLastError();
             return fail(ctx, SLAMCU_INVALID_ARGUMENT, "dense outputs must be page-locked, device-mapped host memory (slamcu_alloc_pinned)");
         }
+        rc = seq_dense_flush(s);  // an earlier dense call on this sequence that nobody waited for
+        if (rc != SLAMCU_OK) return rc;
+        if (kp_capacity > s->dd_kp_cap || match_capacity > s->dd_m_cap) {
+            CU(ctx, cudaDeviceSynchronize());
+            if (s->dd_kps) cudaFree(s->dd_kps);
+            if (s->dd_desc) cudaFree(s->dd_desc);
+            if (s->dd_matches) cudaFree(s->dd_matches);
+            s->dd_kps = s->dd_desc = s->dd_matches = nullptr;
+            s->dd_kp_cap = s->dd_m_cap = 0;
+            const long long kc = std::max(kp_capacity, s->dd_kp_cap), mc = std::max(match_capacity, s->dd_m_cap);
+            CU(ctx, cudaMalloc(&s->dd_kps, (size_t)std::max(kc, 1LL) * sizeof(slamcu_keypoint)));
+            CU(ctx, cudaMalloc(&s->dd_desc, (size_t)std::max(kc, 1LL) * v.desc_words * 4));
+            CU(ctx, cudaMalloc(&s->dd_matches, (size_t)std::max(mc, 1LL) * sizeof(slamcu_dmatch)));
+            s->dd_kp_cap = kc;
+            s->dd_m_cap = mc;
+        }
+        if (!s->h_tot && cudaMallocHost(reinterpret_cast<void**>(&s->h_tot), 2 * sizeof(int)) != cudaSuccess)
+            return fail(ctx, SLAMCU_CUDA_ERROR, "cudaMallocHost failed");
+        dk = kps ? s->dd_kps : nullptr;
+        dd = desc ? s->dd_desc : nullptr;
+        dm = matches ? s->dd_matches : nullptr;
         const size_t F1 = (size_t)s->max_frames + 1;
         if (!s->d_dense) CU(ctx, cudaMalloc(reinterpret_cast<void**>(&s->d_dense), (2 * F1 + 1) * sizeof(int)));
         kp_off = s->d_dense;
@@ -1282,7 +1353,16 @@ static int seq_process(slamcu_sequence* s, slamcu_detector* det, slamcu_matcher*
         CU(ctx, cudaEventRecord(ctx->ev_lane, ctx->lane1));
         CU(ctx, cudaStreamWaitEvent(cs, ctx->ev_lane, 0));
     }
-    if (dense) CU(ctx, cudaMemcpyAsync(s->h_status + s->max_frames, d_over, sizeof(int), cudaMemcpyDeviceToHost, ctx->s_out));
+    if (dense) {
+        CU(ctx, cudaMemcpyAsync(s->h_status + s->max_frames, d_over, sizeof(int), cudaMemcpyDeviceToHost, ctx->s_out));
+        CU(ctx, cudaMemcpyAsync(s->h_tot + 0, kp_off + n, sizeof(int), cudaMemcpyDeviceToHost, ctx->s_out));
+        CU(ctx, cudaMemcpyAsync(s->h_tot + 1, m_off + std::max(n - 1, 0), sizeof(int), cudaMemcpyDeviceToHost, ctx->s_out));
+        s->dl_kps = kps;
+        s->dl_desc = desc;
+        s->dl_matches = matches;
+        s->dl_active = true;
+        ctx->pending_dl.push_back(s);
+    }
     CU(ctx, cudaMemcpyAsync(s->h_status, v.status, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, ctx->s_out));
     s->h_status_n = n;
     CU(ctx, cudaEventRecord(s->ev_compute_done, cs));

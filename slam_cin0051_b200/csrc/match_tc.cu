@@ -43,8 +43,11 @@ static_assert(TCN == TCM, "one tile geometry for both operands (one TMA box shap
 constexpr uint32_t kOffA = 0;
 constexpr uint32_t kOffB = kOffA + kOperandBytes;
 constexpr uint32_t kOffKeys = kOffB + TCSTAGES * kOperandBytes;
-constexpr int kKeySlots = 4;  // key constants of tile j live in slot j % 4: tile j + 4 is loaded after MMA j + 2 was issued, which
-                             // waited for the epilogue of tile j (accumulator stage free) -- so nobody still reads the slot
+constexpr int kKeySlots = 8;  // key constants of tile j live in slot j % 8.  Slot reuse: tile j + 8 is loaded after MMA j + 6 completed,
+                             // which was issued after all four epilogue warps had drained tile j + 4 -- and a warp that has reached
+                             // tile j + 4 is done with every read of tile j's keys.  (An epilogue warp releases the accumulator stage
+                             // BEFORE its last fold of the tile, so four slots left that fold racing the refill: seen as wrong
+                             // matches in the last wave of a launch when kernels of the other compute lane shared its SMs.)
 constexpr uint32_t kOffBars = kOffKeys + kKeySlots * TCN * 4;
 constexpr uint32_t kTcSmemBytes = kOffBars + 128 + 1024;  // barriers + TMEM base + alignment slack
 

@@ -3,10 +3,13 @@
 // The per-frame result arrays live in HBM as [F][cap_kp] rows (keypoints, descriptors, matches).  Copying them to the host
 // as they are moves cap_kp rows per frame although only n_kp (n_match) are defined: 40 % of the D2H bytes of the headline
 // configuration were padding.  dense_scan_kernel turns the per-frame device counts into running offsets, dense_copy_kernel
-// writes the defined rows back to back straight into page-locked, device-mapped host memory (coalesced 16-byte stores over
-// the link), so nothing depends on the host knowing the counts and the call stays asynchronous.
+// writes the defined rows back to back into dense DEVICE buffers; the host fetches them with exact-size copy-engine
+// transfers once the totals have reached it (slamcu_sequence_wait).  Round 2 first wrote the rows straight into mapped host
+// memory from the SMs: the posted writes queued behind the link and cost the concurrent compute kernels ~10 %.
 //   pack_counts_kernel: the four per-frame count arrays -> one int32[n][4] device array (the only data the multi-GPU path
 //   exchanges: one NCCL all-gather per step).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace slamcu {
@@ -52,11 +55,9 @@ __device__ __forceinline__ void copy_rows(const uint32_t* __restrict__ src, uint
     }
 }
 
-// A SMALL persistent grid (kDenseBlocks blocks): the kernel is bound by the host link (~50 GB/s), not by the SMs, and it runs
-// next to the compute kernels of the following chunk -- a grid of one block per frame held thousands of block slots for the
-// whole transfer and slowed those kernels down by 2 ms per 1000 frames.  Work items: (frame, keypoints + descriptors) and
-// (pair, matches), strided over the blocks.
-constexpr int kDenseBlocks = 32;
+// A persistent grid of kDenseBlocks blocks.  Work items: (frame, keypoints + descriptors) and (pair, matches), strided over
+// the blocks.
+constexpr int kDenseBlocks = 4 * 148;
 __global__ void __launch_bounds__(256) dense_copy_kernel(SeqView s, int first, int n_frames, int pair_first, int n_pairs, const int* __restrict__ kp_off,
                                                          const int* __restrict__ m_off, uint32_t* __restrict__ h_kps, uint32_t* __restrict__ h_desc,
                                                          uint32_t* __restrict__ h_matches, int kp_cap, int m_cap, int* __restrict__ overflow) {
@@ -113,7 +114,9 @@ int launch_dense_scan(const int* counts, int first, int n, int* off, cudaStream_
 int launch_dense_copy(const SeqView& s, int first, int n_frames, int pair_first, int n_pairs, const int* kp_off, const int* m_off, void* h_kps,
                       void* h_desc, void* h_matches, int kp_cap, int m_cap, int* overflow, cudaStream_t st) {
     if (n_frames + n_pairs <= 0) return 0;
-    const int grid = n_frames + n_pairs < kDenseBlocks ? n_frames + n_pairs : kDenseBlocks;
+    static const int blocks_env = [] { const char* e = getenv("SLAMCU_DENSE_BLOCKS"); return e ? atoi(e) : 0; }();  // tuning knob
+    const int cap = blocks_env > 0 ? blocks_env : kDenseBlocks;
+    const int grid = n_frames + n_pairs < cap ? n_frames + n_pairs : cap;
     SLAM_KERNEL("dense_copy", st,
                 dense_copy_kernel<<<grid, 256, 0, st>>>(s, first, n_frames, pair_first, n_pairs, kp_off, m_off, static_cast<uint32_t*>(h_kps),
                                                         static_cast<uint32_t*>(h_desc), static_cast<uint32_t*>(h_matches), kp_cap, m_cap, overflow));

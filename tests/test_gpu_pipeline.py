@@ -121,3 +121,29 @@ def test_two_lane_extract_match_equals_the_serial_calls(gpu_ctx, mode):
         assert tuple(x.tobytes() for x in b.frame(f)) == want[1][f]
     for f in range(5, 24):
         assert b.matches(f).tobytes() == want[2][f]
+
+
+def test_two_lanes_under_load_equal_one_lane(gpu_ctx):
+    """Regression: 400 headline-sized frames in small chunks, so that the last wave of one chunk's tensor-core matcher shares its
+    SMs with the other lane's extractor (a shared-memory slot reuse race showed up exactly there as a handful of wrong matches):
+    per-pair match counts and the matches themselves equal the one-lane run, three times in a row."""
+    import os
+
+    import slam_cin0051_b200 as s
+    from conftest import DATA
+    from slam_cin0051_b200.synth import make_sequence
+    det = s.FeatureDetector(os.path.join(DATA, "feature_detector_orb.yml"), gpu_ctx)
+    mat = s.FeatureMatcher(os.path.join(DATA, "feature_matcher_orb.yml"), gpu_ctx)
+    n = 400
+    frames = np.concatenate([make_sequence(376, 1241, 50, 14, seed=900 + g) for g in range(8)])[:n]
+    a = s.FrameSequence(376, 1241, n, desc_bytes=32, max_keypoints=2560, context=gpu_ctx)
+    a.upload(frames)
+    a.extract_match(det, mat, 0, n, with_keypoints=False, chunk=0)
+    want_counts = a.counts().copy()
+    assert (want_counts[:, 3] == 0).all()
+    want = [a.matches(f).tobytes() for f in range(0, n - 1, 7)]
+    for chunk in (25, 50, 25):
+        a.extract_match(det, mat, 0, n, with_keypoints=False, chunk=chunk)
+        got = a.counts()
+        assert np.array_equal(got, want_counts), (chunk, np.nonzero((got != want_counts).any(1))[0][:10])
+        assert [a.matches(f).tobytes() for f in range(0, n - 1, 7)] == want, chunk
