@@ -451,22 +451,11 @@ def run_ours(args, w, rank, world, local_rank):
     seqs = [seq, seq2]
 
     submit_s = [0.0]
-    padded = None
-    if os.environ.get("BENCH_E2E_PADDED") == "1":
-        padded = [(torch.empty((NF, max_kp, 5), dtype=torch.float32, pin_memory=True), torch.empty((NF, max_kp, det.descriptor_bytes), dtype=torch.uint8, pin_memory=True),
-                   torch.empty((NF, max_kp, 3), dtype=torch.int32, pin_memory=True)) for _ in range(2)]
     noout = os.environ.get("BENCH_E2E_NOOUT") == "1"  # experiment knob: no result download (not a valid e2e number)
 
     def submit_e2e(i):
         t_sub = time.perf_counter()
         k, d, m, c = outs[i % 2]
-        if os.environ.get("BENCH_E2E_PADDED") == "1":  # experiment knob: padded rows through the copy engine
-            kk, dd, mm = padded[i % 2]
-            seqs[i % 2].process_ptrs(det, mat, host_frames.data_ptr(), NF, chunk=args.chunk, with_keypoints=with_kp, kps_ptr=kk.data_ptr(),
-                                     desc_ptr=dd.data_ptr(), matches_ptr=mm.data_ptr(), counts_ptr=c.data_ptr())
-            gather_counts(seqs[i % 2])
-            submit_s[0] += time.perf_counter() - t_sub
-            return
         if noout:
             seqs[i % 2].process_dense_ptrs(det, mat, host_frames.data_ptr(), NF, chunk=args.chunk, with_keypoints=with_kp, counts_ptr=c.data_ptr(),
                                            kp_capacity=kp_cap, match_capacity=m_cap)

@@ -240,9 +240,11 @@ int slamcu_sequence_process(slamcu_sequence* seq, slamcu_detector* det, slamcu_m
                             int stride, int n, int chunk, int with_keypoints, slamcu_keypoint* keypoints,
                             uint8_t* descriptors, slamcu_dmatch* matches, int32_t* counts4);
 
-/* The same loop with DENSE outputs: a device compaction kernel writes only the defined rows, frame after frame, straight
- * into page-locked device-mapped host buffers (slamcu_alloc_pinned / cudaHostAlloc), so no padding crosses the link and the
- * call stays asynchronous (nothing waits for the host to learn the counts):
+/* The same loop with DENSE outputs: a device compaction kernel packs only the defined rows, frame after frame, and the three
+ * arrays cross the link as exact-size copy-engine transfers into the caller's page-locked buffers (slamcu_alloc_pinned /
+ * cudaHostAlloc), so no padding is moved.  The call itself stays asynchronous; the transfers are issued by
+ * slamcu_sequence_wait(seq) / slamcu_synchronize() once the totals have reached the host, and the buffers are valid when
+ * that call returns (the per-frame counts4 arrive as in slamcu_sequence_process):
  *   keypoints / descriptors of frame f at row kp_off[f] = counts4[0][0] + ... + counts4[f-1][0]
  *   matches of pair (f, f+1)           at row m_off[f]  = counts4[0][1] + ... + counts4[f-1][1]
  * kp_capacity / match_capacity: rows the buffers hold; slamcu_sequence_wait returns SLAMCU_CAPACITY when they were exceeded. */
