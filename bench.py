@@ -646,7 +646,7 @@ def extra_legs(args):
     out = {}
 
     def child(extra, timeout=600):
-        cmd = [sys.executable, os.path.abspath(__file__), "--gpus", "1", "--steps", str(max(2, min(args.steps, 3))), "--warmup", "3", "--no-extra-legs", *extra]
+        cmd = [sys.executable, os.path.abspath(__file__), "--gpus", "1", "--steps", str(max(2, min(args.steps, 10))), "--warmup", "3", "--no-extra-legs", *extra]
         try:
             r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
             lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
@@ -671,8 +671,8 @@ def extra_legs(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="orb", choices=["orb", "reference"],
                     help="orb: the OpenCV-ORB-compatible path BASELINE.json's headline config names; "

@@ -13,7 +13,11 @@ KEEP = ["launch__grid_size", "launch__block_size", "launch__registers_per_thread
         "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct",
-        "smsp__thread_inst_executed_per_inst_executed.ratio", "smsp__inst_executed.sum"]
+        "smsp__thread_inst_executed_per_inst_executed.ratio", "smsp__inst_executed.sum",
+        # tensor-core matcher: whichever of these this ncu version exposes
+        "sm__inst_executed_pipe_tc.avg.pct_of_peak_sustained_active", "sm__pipe_tc_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_tensor.avg.pct_of_peak_sustained_active", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_tmem.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_uniform.avg.pct_of_peak_sustained_active"]
 
 
 def main():
@@ -45,7 +49,7 @@ def main():
         for r in body:
             m = re.search(r"(\w+?)_kernel", r[kn])
             name = m.group(1) if m else r[kn]
-            name = {"orb_describe": "orb_describe", "desc_or": "desc_or", "finalize": "match_finalize", "match256": "match"}.get(name, name)
+            name = {"orb_describe": "orb_describe", "desc_or": "desc_or", "finalize": "match_finalize", "match256": "match", "match_tc": "match", "expand_bits": "match_expand"}.get(name, name)
             b = to_bytes(r[col["dram__bytes_read.sum"]], units[col["dram__bytes_read.sum"]]) + \
                 to_bytes(r[col["dram__bytes_write.sum"]], units[col["dram__bytes_write.sum"]])
             dram[name] = dram.get(name, 0.0) + b
