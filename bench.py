@@ -444,35 +444,36 @@ def run_ours(args, w, rank, world, local_rank):
             seq.essential(k4, 0, NP)
         gather_counts(seq)
 
-    # end-to-end leg: two sequences double-buffer, so step k+1's H2D runs under step k's kernels (a streaming
-    # deployment); every step still uploads its frames from pinned host memory and downloads all its results
-    seq2 = S.FrameSequence(ROWS, COLS, NF, desc_bytes=det.descriptor_bytes, max_keypoints=max_kp, context=ctx)
-    outs = [out_set(), out_set()]
-    seqs = [seq, seq2]
+    # end-to-end leg: N_SEQ sequences rotate and the host stays AHEAD steps in front of the results it collects, so step
+    # k+2's H2D runs under step k+1's kernels while step k's results are still being downloaded (a streaming deployment);
+    # every step still uploads its frames from pinned host memory and downloads all its results
+    N_SEQ, AHEAD = 3, 2
+    seqs = [seq] + [S.FrameSequence(ROWS, COLS, NF, desc_bytes=det.descriptor_bytes, max_keypoints=max_kp, context=ctx) for _ in range(N_SEQ - 1)]
+    outs = [out_set() for _ in range(N_SEQ)]
 
     submit_s = [0.0]
     noout = os.environ.get("BENCH_E2E_NOOUT") == "1"  # experiment knob: no result download (not a valid e2e number)
 
     def submit_e2e(i):
         t_sub = time.perf_counter()
-        k, d, m, c = outs[i % 2]
+        k, d, m, c = outs[i % N_SEQ]
         if noout:
-            seqs[i % 2].process_dense_ptrs(det, mat, host_frames.data_ptr(), NF, chunk=args.chunk, with_keypoints=with_kp, counts_ptr=c.data_ptr(),
+            seqs[i % N_SEQ].process_dense_ptrs(det, mat, host_frames.data_ptr(), NF, chunk=args.chunk, with_keypoints=with_kp, counts_ptr=c.data_ptr(),
                                            kp_capacity=kp_cap, match_capacity=m_cap)
-            gather_counts(seqs[i % 2])
+            gather_counts(seqs[i % N_SEQ])
             submit_s[0] += time.perf_counter() - t_sub
             return
-        seqs[i % 2].process_dense_ptrs(det, mat, host_frames.data_ptr(), NF, chunk=args.chunk, with_keypoints=with_kp,
+        seqs[i % N_SEQ].process_dense_ptrs(det, mat, host_frames.data_ptr(), NF, chunk=args.chunk, with_keypoints=with_kp,
                                        kps_ptr=k.data_ptr(), desc_ptr=d.data_ptr(), matches_ptr=m.data_ptr(), counts_ptr=c.data_ptr(),
                                        kp_capacity=kp_cap, match_capacity=m_cap)
         if k4:  # E, inlier masks and counts stay on the device (read per pair with essential_result)
-            seqs[i % 2].essential(k4, 0, NP)
-        gather_counts(seqs[i % 2])
+            seqs[i % N_SEQ].essential(k4, 0, NP)
+        gather_counts(seqs[i % N_SEQ])
         submit_s[0] += time.perf_counter() - t_sub
 
     def collect_e2e(i):
-        seqs[i % 2].wait()  # the step's results are now in host memory (raises if a device list overflowed); read them
-        c = outs[i % 2][3]
+        seqs[i % N_SEQ].wait()  # the step's results are now in host memory (raises if a device list overflowed); read them
+        c = outs[i % N_SEQ][3]
         return int(c[:B, 0].sum()), int(c[:B, 1].sum()), int(c[:, 0].sum()), int(c[:NP, 1].sum())
 
     seq.upload_ptr(host_frames.data_ptr(), NF)
@@ -511,10 +512,13 @@ def run_ours(args, w, rank, world, local_rank):
     ctx.profile_enable(False)
 
     # ---- end-to-end leg (host buffers, copies inside the timed region) ----
-    for i in range(2 * max(args.warmup, 3)):  # W untimed steps per sequence, results collected like the timed ones
+    n_warm = N_SEQ * max(args.warmup, 3)  # W untimed steps per sequence, results collected like the timed ones
+    for i in range(n_warm):
         submit_e2e(i)
-        if i >= 1:
-            collect_e2e(i - 1)
+        if i >= AHEAD:
+            collect_e2e(i - AHEAD)
+    for i in range(max(n_warm - AHEAD, 0), n_warm):
+        collect_e2e(i)
     ctx.synchronize()
     barrier()
     torch.cuda.synchronize()
@@ -523,9 +527,10 @@ def run_ours(args, w, rank, world, local_rank):
     tot = (0, 0, 0, 0)
     for i in range(args.steps):
         submit_e2e(i)
-        if i >= 1:
-            tot = collect_e2e(i - 1)
-    tot = collect_e2e(args.steps - 1)
+        if i >= AHEAD:
+            tot = collect_e2e(i - AHEAD)
+    for i in range(max(args.steps - AHEAD, 0), args.steps):
+        tot = collect_e2e(i)
     ctx.synchronize()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
@@ -617,7 +622,7 @@ def run_ours(args, w, rank, world, local_rank):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / args.steps, "keypoints_last_step": tot[0], "matches_last_step": tot[1],
                     "host_submit_ms_per_step": submit_s[0] * 1e3 / args.steps,
-                    "pipeline_chunk_frames": args.chunk, "double_buffered_sequences": 2, "outputs": "dense (device compaction into pinned host memory)",
+                    "pipeline_chunk_frames": args.chunk, "sequences_in_rotation": N_SEQ, "steps_in_flight": AHEAD + 1, "outputs": "dense (device compaction into pinned host memory)",
                     "h2d_gbs_per_rank": h2d / step_s / 1e9, "d2h_gbs_per_rank": d2h / step_s / 1e9,
                     "host_link_gbs_all_ranks": world * (h2d + d2h) / step_s / 1e9},
             "gpu_launches": int(launches),
@@ -632,7 +637,7 @@ def run_ours(args, w, rank, world, local_rank):
             n_s = max(8, min(NF, 8 * threads))
             line["cpu_baseline"] = cpu_baseline_leg(args, w, frames_np[:n_s], counts)
         if world == 1 and args.extra_legs:
-            del seq2, outs
+            del seqs, outs
             line.update(extra_legs(args))
         print(json.dumps(line), flush=True)
     if world > 1:
