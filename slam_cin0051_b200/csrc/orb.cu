@@ -775,8 +775,10 @@ __global__ void __launch_bounds__(BWARPS * 32) blur7_kernel(SeqView s, OrbView o
         const int y0 = t * BTH, buf = (t - t_begin) & 1;
         // ---- stage 1: the byte tile, zero outside the level (TMA: issued one tile ahead; LDG fallback: filled here)
         if (kTma) {
-            if (threadIdx.x == 0 && t + 1 < t_end)  // buffer buf^1 was last read before the barrier that ended tile t-1
+            if (threadIdx.x == 0 && t + 1 < t_end) {  // buffer buf^1 was last read (and, on border tiles, patched) before the barrier that ended tile t-1
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 tma_load_3d(tb[buf ^ 1], &tmap, x0 - BBX, (t + 1) * BTH - 3, f, &tma_bar[buf ^ 1], BBH * BBW);
+            }
             mbar_wait(&tma_bar[buf], ((t - t_begin) >> 1) & 1);
         } else {
             for (int i = threadIdx.x; i < BBH * (BBW / 4); i += BWARPS * 32) {
@@ -791,22 +793,33 @@ __global__ void __launch_bounds__(BWARPS * 32) blur7_kernel(SeqView s, OrbView o
             }
             __syncthreads();
         }
-        // ---- stage 2: bytes -> floats once per pixel, BORDER_REFLECT_101 applied by reading the reflected position INSIDE
-        // the byte tile (a reflected pixel is never more than 4 px / 3 rows away from the border)
+        // ---- stage 2: BORDER_REFLECT_101 is applied by mirroring the halo INSIDE the byte tile (a reflected pixel is never more
+        // than 4 px / 3 rows away from the border; only tiles on the level's border do this: rows first, then columns, so the
+        // corners come out doubly reflected), then every tile converts bytes -> floats once per pixel with one uniform loop
         const int rows_needed = min(BTH, L.rows - y0) + 6;
+        uint32_t* tb32 = reinterpret_cast<uint32_t*>(tb[buf]);
+        const bool edge_y = y0 - 3 < 0 || y0 + BTH + 3 > L.rows, edge_x = x0 - 4 < 0 || x0 + BW + 4 > L.cols;
+        if (edge_y) {
+            for (int i = threadIdx.x; i < rows_needed * (BBW / 4); i += BWARPS * 32) {
+                const int r = i / (BBW / 4), c = i - r * (BBW / 4);
+                const int vy = y0 - 3 + r;
+                if (vy < 0 || vy >= L.rows) tb32[i] = tb32[max(reflect101(vy, L.rows) - (y0 - 3), 0) * (BBW / 4) + c];
+            }
+            __syncthreads();
+        }
+        if (edge_x) {
+            for (int i = threadIdx.x; i < rows_needed * 8; i += BWARPS * 32) {
+                const int r = i >> 3, k = i & 7;
+                const int gx = k < 4 ? k - 4 : L.cols + (k - 4);  // the four pixels left of the level, the four right of it
+                const int tc = gx - (x0 - BBX);
+                if ((k < 4 ? x0 - 4 < 0 : x0 + BW + 4 > L.cols) && tc >= 0 && tc < BBW)
+                    tb[buf][r * BBW + tc] = tb[buf][r * BBW + min(max(reflect101(gx, L.cols) - (x0 - BBX), 0), BBW - 1)];
+            }
+            __syncthreads();
+        }
         for (int i = threadIdx.x; i < rows_needed * WPR; i += BWARPS * 32) {
             const int r = i / WPR, c = i - r * WPR;
-            const int gx = x0 - 4 + 4 * c;
-            const int tr = max(reflect101(y0 - 3 + r, L.rows) - (y0 - 3), 0);
-            const uint8_t* row = tb[buf] + tr * BBW;
-            unsigned w;
-            if (gx >= 0 && gx + 3 < L.cols) {
-                w = *reinterpret_cast<const uint32_t*>(row + 4 * c + (BBX - 4));
-            } else {
-                w = 0;
-#pragma unroll
-                for (int k = 0; k < 4; k++) w |= (unsigned)row[min(max(reflect101(gx + k, L.cols) - (x0 - BBX), 0), BBW - 1)] << (8 * k);
-            }
+            const unsigned w = tb32[r * (BBW / 4) + c + (BBX - 4) / 4];
             float4 v;
             v.x = byte_to_float(w, 0x7440u);
             v.y = byte_to_float(w, 0x7441u);
