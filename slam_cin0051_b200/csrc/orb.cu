@@ -726,11 +726,10 @@ __device__ __forceinline__ float byte_to_float(unsigned w, unsigned sel) {
     return __uint_as_float(__byte_perm(w, 0x4B000000u, sel)) - 8388608.0f;
 }
 
-__device__ __forceinline__ unsigned sat_u8_rn(float v) {  // cvRound (round half to even) + saturate_cast<uchar>
-    unsigned r;
-    asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(r) : "f"(v));
-    return r;
-}
+// cvRound (round half to even) + saturate_cast<uchar> of a blurred pixel.  The value is a convex combination of bytes (the float
+// weights sum to 1 + a few ulp), so it lies in [0, 255.0001]: adding 2^23 rounds it to an integer exactly like cvt.rni and leaves
+// that integer in the low byte -- an FADD on the FMA pipe instead of an F2I on the XU pipe; no saturation can trigger.
+__device__ __forceinline__ unsigned sat_u8_rn(float v) { return __float_as_uint(v + 8388608.0f); }
 
 constexpr int BBW = kBlurBoxW, BBH = kBlurBoxH, BBX = 16;  // byte tile: pixels x0-16 .. x0+143 (160 B rows), rows y0-3 .. y0+62
 static_assert(BBW == BW + 2 * BBX && BBH == BIH, "blur tile geometry");  // (the TMA start coordinate stays a multiple of 16 bytes)
