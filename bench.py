@@ -452,17 +452,10 @@ def run_ours(args, w, rank, world, local_rank):
     outs = [out_set() for _ in range(N_SEQ)]
 
     submit_s = [0.0]
-    noout = os.environ.get("BENCH_E2E_NOOUT") == "1"  # experiment knob: no result download (not a valid e2e number)
 
     def submit_e2e(i):
         t_sub = time.perf_counter()
         k, d, m, c = outs[i % N_SEQ]
-        if noout:
-            seqs[i % N_SEQ].process_dense_ptrs(det, mat, host_frames.data_ptr(), NF, chunk=args.chunk, with_keypoints=with_kp, counts_ptr=c.data_ptr(),
-                                           kp_capacity=kp_cap, match_capacity=m_cap)
-            gather_counts(seqs[i % N_SEQ])
-            submit_s[0] += time.perf_counter() - t_sub
-            return
         seqs[i % N_SEQ].process_dense_ptrs(det, mat, host_frames.data_ptr(), NF, chunk=args.chunk, with_keypoints=with_kp,
                                        kps_ptr=k.data_ptr(), desc_ptr=d.data_ptr(), matches_ptr=m.data_ptr(), counts_ptr=c.data_ptr(),
                                        kp_capacity=kp_cap, match_capacity=m_cap)
