@@ -80,3 +80,18 @@ def test_simple_recover_pose_equals_cv_svd_golden(path):
     assert np.abs(R - g["R"]).max() < 1e-12 and np.abs(t - g["t"]).max() < 1e-12
     assert sorted(front) == sorted(g["front"].tolist())
     assert abs(np.linalg.det(R) - 1.0) < 1e-12 and np.abs(R.T @ R - np.eye(3)).max() < 1e-12  # test_pose_estimator.cpp:34-43
+
+
+@pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p)[10:-4] for p in GOLD])
+def test_recovered_pose_is_one_of_cv2s_four_decompositions(path):
+    """An anchor for simpleRecoverPose that does not go through this repo's restatement: the committed (R, t) must be one of
+    the four candidates cv2.decomposeEssentialMat (OpenCV's own code) derives from the same E.  WHICH of the four wins is the
+    reference's own rule and cannot be anchored on OpenCV: simple_pose_recover.cpp votes with K-normalised points against
+    K [R|t] projections (pose_estimator.cpp:53-66), and on these scenes its winner puts the inliers BEHIND the cameras under a
+    textbook triangulation (cv2.triangulatePoints: under 1 % in front on syn300) -- reproduced literally, recorded here."""
+    import cv2
+    g = np.load(path)
+    R1, R2, t = cv2.decomposeEssentialMat(g["E"].astype(np.float64))
+    cands = [(R1, t), (R2, t), (R1, -t), (R2, -t)]
+    d = [max(np.abs(g["R"] - R).max(), np.abs(g["t"].reshape(3, 1) - tt).max()) for R, tt in cands]
+    assert min(d) < 1e-9, d
