@@ -348,6 +348,7 @@ void slamcu_destroy(slamcu_context* ctx) {
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->s_in) { cudaStreamSynchronize(ctx->s_in); cudaStreamDestroy(ctx->s_in); }
     if (ctx->s_out) { cudaStreamSynchronize(ctx->s_out); cudaStreamDestroy(ctx->s_out); }
+    if (ctx->s_dl) { cudaStreamSynchronize(ctx->s_dl); cudaStreamDestroy(ctx->s_dl); }
     for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
     if (ctx->s_aux) { cudaStreamSynchronize(ctx->s_aux); cudaStreamDestroy(ctx->s_aux); }
     if (ctx->lane1) { cudaStreamSynchronize(ctx->lane1); cudaStreamDestroy(ctx->lane1); }
@@ -380,6 +381,7 @@ int slamcu_synchronize(slamcu_context* ctx) {
     if (ctx->lane1) CU(ctx, cudaStreamSynchronize(ctx->lane1));
     if (ctx->s_in) CU(ctx, cudaStreamSynchronize(ctx->s_in));
     if (ctx->s_out) CU(ctx, cudaStreamSynchronize(ctx->s_out));
+    if (ctx->s_dl) CU(ctx, cudaStreamSynchronize(ctx->s_dl));
     return SLAMCU_OK;
 }
 int64_t slamcu_launch_count(const slamcu_context* ctx) { return ctx ? ctx->launches : 0; }
